@@ -1,0 +1,164 @@
+"""Synthetic LDU systems for the configurations of BASELINE.json.
+
+Meshes are blockMesh-equivalent single hex blocks: cell c = i + nx*(j + ny*k) (i fastest);
+internal faces in upper-triangular order: for each cell ascending, faces to c+1, c+nx,
+c+nx*ny when they exist (the ordering polyMeshFromShapeMesh produces for one block,
+reference src/OpenFOAM/meshes/polyMesh/polyMeshFromShapeMesh.C:176-269).
+
+All arrays are numpy: int32 addressing ("label", WM_LABEL_SIZE=32) and float64 coefficients.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+
+@dataclass
+class Interface:
+    """One processor patch of a decomposed system (reference: processorFvPatch)."""
+    neighb_rank: int
+    face_cells: np.ndarray          # int32 [nPatchFaces], local cell of each patch face
+    bou_coeffs: np.ndarray          # float64, interfaceBouCoeffs
+    int_coeffs: np.ndarray          # float64, interfaceIntCoeffs
+
+
+@dataclass
+class LduSystem:
+    n_cells: int
+    lower: np.ndarray               # int32 [nFaces]  owner ("l") of each face
+    upper: np.ndarray               # int32 [nFaces]  neighbour ("u") of each face
+    diag: np.ndarray                # float64 [nCells]
+    upper_coeffs: np.ndarray        # float64 [nFaces]
+    lower_coeffs: Optional[np.ndarray] = None   # None => symmetric
+    source: Optional[np.ndarray] = None
+    face_weights: Optional[np.ndarray] = None   # faceAreaPair agglomeration weights
+    face_dir: Optional[np.ndarray] = None       # 0/1/2 for block meshes
+    interfaces: List[Interface] = field(default_factory=list)
+    shape: tuple = ()
+
+    @property
+    def n_faces(self):
+        return int(self.lower.size)
+
+    @property
+    def symmetric(self):
+        return self.lower_coeffs is None
+
+
+def block_addressing(nx, ny, nz):
+    """lower/upper addressing + face direction for an nx*ny*nz block."""
+    n = nx * ny * nz
+    c = np.arange(n, dtype=np.int64)
+    i = c % nx
+    j = (c // nx) % ny
+    k = c // (nx * ny)
+    cand_u = np.stack([c + 1, c + nx, c + nx * ny], axis=1)
+    ok = np.stack([i < nx - 1, j < ny - 1, k < nz - 1], axis=1)
+    own = np.repeat(c[:, None], 3, axis=1)
+    dirs = np.broadcast_to(np.arange(3, dtype=np.int8), (n, 3))
+    lower = own[ok].astype(np.int32)
+    upper = cand_u[ok].astype(np.int32)
+    fdir = dirs[ok].astype(np.int8)
+    return lower, upper, fdir
+
+
+def face_area_pair_weights(nx, ny, nz, fdir):
+    """mag(cmptMultiply(Sf/sqrt(magSf), (1, 1.01, 1.02))) on a unit-cube block
+    (reference faceAreaPairGAMGAgglomeration.C:66-79)."""
+    dx, dy, dz = 1.0 / nx, 1.0 / ny, 1.0 / nz
+    area = np.array([dy * dz, dx * dz, dx * dy])
+    scale = np.array([1.0, 1.01, 1.02])
+    a = area / np.sqrt(area)
+    w = np.sqrt((a * scale) ** 2)
+    return w[fdir]
+
+
+def negsum_diag(n_cells, lower, upper, upper_coeffs, lower_coeffs):
+    """lduMatrix::negSumDiag (reference lduMatrixOperations.C): Diag[l] -= Lower, Diag[u] -= Upper,
+    sequential face order (np.subtract.at keeps index order)."""
+    diag = np.zeros(n_cells)
+    lo = upper_coeffs if lower_coeffs is None else lower_coeffs
+    np.subtract.at(diag, lower, lo)
+    np.subtract.at(diag, upper, upper_coeffs)
+    return diag
+
+
+def rhs(n, kind="sin", seed=20261017):
+    if kind == "sin":
+        return np.sin(0.37 * np.arange(n, dtype=np.float64))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.uniform(-1.0, 1.0, n)
+
+
+def cavity_laplacian(nx, ny, nz, coeffs="uniform", seed=20261017, rhs_kind="sin"):
+    """p-equation stand-in: fvm::laplacian on a uniform block, all-Neumann + setReference(0, 0)
+    (reference gaussLaplacianScheme.C:63-64, fvMatrix.C:553-565)."""
+    lower, upper, fdir = block_addressing(nx, ny, nz)
+    nf = lower.size
+    if coeffs == "uniform":
+        up = np.ones(nf)
+    else:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        up = 1.0 + 0.5 * rng.random(nf)
+    n = nx * ny * nz
+    diag = negsum_diag(n, lower, upper, up, None)
+    diag[0] += diag[0]
+    return LduSystem(
+        n_cells=n, lower=lower, upper=upper, diag=diag, upper_coeffs=up,
+        source=rhs(n, rhs_kind, seed + 1),
+        face_weights=face_area_pair_weights(nx, ny, nz, fdir), face_dir=fdir,
+        shape=(nx, ny, nz),
+    )
+
+
+def convection_diffusion(nx, ny, nz=1, nu=0.01, dt_coeff=0.5, seed=20261017, rhs_kind="sin"):
+    """Asymmetric U/k/epsilon stand-in: upwind convection + diffusion + ddt on a uniform block
+    (reference gaussConvectionScheme.C:140-142: lower = -w*phi, upper = lower + phi, negSumDiag;
+    laplacian as above with opposite sign)."""
+    lower, upper, fdir = block_addressing(nx, ny, nz)
+    n = nx * ny * nz
+    h = np.array([1.0 / nx, 1.0 / ny, 1.0 / max(nz, 1)])
+    # smooth solenoidal-ish flux: rotation about the block centre + seeded perturbation
+    cl = lower.astype(np.int64)
+    i = cl % nx
+    j = (cl // nx) % ny
+    xc = (i + 0.5) / nx
+    yc = (j + 0.5) / ny
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pert = 0.1 * (rng.random(lower.size) - 0.5)
+    ux = -(yc - 0.5) + pert
+    uy = (xc - 0.5) + pert
+    uz = 0.3 * np.sin(6.0 * xc) + pert
+    vel = np.stack([ux, uy, uz], axis=1)
+    area = np.array([h[1] * h[2], h[0] * h[2], h[0] * h[1]])
+    phi = vel[np.arange(lower.size), fdir] * area[fdir]
+    diff = nu * area[fdir] / h[fdir]
+    lo = -np.maximum(phi, 0.0) - diff
+    up = np.minimum(phi, 0.0) - diff
+    diag = negsum_diag(n, lower, upper, up, lo)
+    vol = h[0] * h[1] * h[2]
+    diag = diag + vol / (dt_coeff * h.min())
+    return LduSystem(
+        n_cells=n, lower=lower, upper=upper, diag=diag, upper_coeffs=up, lower_coeffs=lo,
+        source=rhs(n, rhs_kind, seed + 1) * vol,
+        face_weights=face_area_pair_weights(nx, ny, max(nz, 1), fdir), face_dir=fdir,
+        shape=(nx, ny, nz),
+    )
+
+
+def to_entries(sys_: LduSystem):
+    """B2LS entries understood by oracle/ref_harness.C and the C oracle."""
+    e = {
+        "nCells": int(sys_.n_cells),
+        "lower": sys_.lower.astype(np.int32),
+        "upper": sys_.upper.astype(np.int32),
+        "diag": sys_.diag.astype(np.float64),
+        "upperCoeffs": sys_.upper_coeffs.astype(np.float64),
+    }
+    if sys_.lower_coeffs is not None:
+        e["lowerCoeffs"] = sys_.lower_coeffs.astype(np.float64)
+    if sys_.source is not None:
+        e["source"] = sys_.source.astype(np.float64)
+    if sys_.face_weights is not None:
+        e["faceWeights"] = sys_.face_weights.astype(np.float64)
+    return e

@@ -1,0 +1,544 @@
+/*---------------------------------------------------------------------------*\
+  oracle/ref_harness.C  --  TEST INFRASTRUCTURE ONLY (never on the product path)
+
+  Drives the UNMODIFIED reference solver stack (oracle/_ref/libOpenFOAM.so, built
+  by oracle/build_ref.py from /root/reference/src) on an LDU system read from a
+  "B2LS" case file and writes every result the parity tests compare against:
+
+    * lduAddressing::losortAddr / ownerStartAddr / losortStartAddr
+      (src/OpenFOAM/matrices/lduMatrix/lduAddressing/lduAddressing.C:32-170)
+    * lduMatrix::Amul / residual / sumA   (lduMatrix/lduMatrixATmul.C:34-280)
+    * DIC / DILU calcReciprocalD + precondition
+    * GaussSeidel / DIC / DILU smoother sweeps (via lduMatrix::smoother::New)
+    * lduMatrix::solver::New(...)->solve(...) for any fvSolution-style dictionary,
+      repeated with maxIter = 1..k to obtain the exact residual history
+    * GAMGAgglomeration levels (restrictAddressing, faceRestrictAddressing,
+      faceFlipMap, coarse lower/upper) for the faceAreaPair agglomerator, which is
+      restated here on top of pairGAMGAgglomeration exactly as
+      src/finiteVolume/.../faceAreaPairGAMGAgglomeration.C:55-108 does, but taking the
+      face weights from the case file instead of an fvMesh.
+
+  One mesh per process: pairGAMGAgglomeration::forward_ is a process-global static.
+
+  File formats are documented in openfoam-dev_b200/ldu_io.py.
+\*---------------------------------------------------------------------------*/
+
+#include "Time.H"
+#include "lduPrimitiveMesh.H"
+#include "lduMatrix.H"
+#include "pairGAMGAgglomeration.H"
+#include "GAMGAgglomeration.H"
+#include "DICPreconditioner.H"
+#include "DILUPreconditioner.H"
+#include "addToRunTimeSelectionTable.H"
+#include "IStringStream.H"
+#include "OSspecific.H"
+#include "clockTime.H"
+#include "dlLibraryTable.H"
+
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+using namespace Foam;
+
+// ---------------------------------------------------------------------------
+// case-file globals (the harness handles exactly one mesh per process)
+// ---------------------------------------------------------------------------
+
+static std::vector<double> g_faceWeights;
+
+namespace Foam
+{
+
+//- lduPrimitiveMesh with an objectRegistry so that GAMGAgglomeration::New can
+//  cache itself (lduMesh::db() is NotImplemented in the base class,
+//  meshes/lduMesh/lduMesh.C:40-45)
+class harnessLduMesh
+:
+    public lduPrimitiveMesh
+{
+    const Time& runTime_;
+
+public:
+
+    harnessLduMesh
+    (
+        const Time& runTime,
+        const label nCells,
+        labelList& l,
+        labelList& u
+    )
+    :
+        lduPrimitiveMesh(nCells, l, u, 0, true),
+        runTime_(runTime)
+    {}
+
+    virtual const objectRegistry& db() const
+    {
+        return runTime_;
+    }
+};
+
+
+//- faceAreaPair restated on pairGAMGAgglomeration with file-supplied weights
+class harnessFaceAreaPairAgglomeration
+:
+    public pairGAMGAgglomeration
+{
+public:
+
+    TypeName("faceAreaPair");
+
+    harnessFaceAreaPairAgglomeration
+    (
+        const lduMesh& mesh,
+        const dictionary& controlDict
+    )
+    :
+        pairGAMGAgglomeration(mesh, controlDict)
+    {
+        scalarField w(g_faceWeights.size());
+        forAll(w, i)
+        {
+            w[i] = g_faceWeights[i];
+        }
+        agglomerate(mesh, w);
+    }
+};
+
+defineTypeNameAndDebug(harnessFaceAreaPairAgglomeration, 0);
+addToRunTimeSelectionTable
+(
+    GAMGAgglomeration,
+    harnessFaceAreaPairAgglomeration,
+    lduMesh
+);
+
+}
+
+
+// ---------------------------------------------------------------------------
+// B2LS container IO: a flat list of named arrays
+//   magic "B2LS0001"; int64 nEntries; per entry:
+//   int64 nameLen; name bytes; int64 dtype (0=i32, 1=f64, 2=u8); int64 count; data
+// ---------------------------------------------------------------------------
+
+struct Entry
+{
+    int64_t dtype;
+    std::vector<char> bytes;
+    int64_t count;
+};
+
+typedef std::map<std::string, Entry> Container;
+
+static size_t dtypeSize(int64_t dt)
+{
+    return dt == 0 ? 4 : dt == 1 ? 8 : 1;
+}
+
+static Container readContainer(const char* path)
+{
+    Container c;
+    FILE* f = fopen(path, "rb");
+    if (!f)
+    {
+        fprintf(stderr, "cannot open %s\n", path);
+        exit(2);
+    }
+    char magic[8];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "B2LS0001", 8) != 0)
+    {
+        fprintf(stderr, "bad magic in %s\n", path);
+        exit(2);
+    }
+    int64_t n;
+    if (fread(&n, 8, 1, f) != 1) exit(2);
+    for (int64_t i = 0; i < n; i++)
+    {
+        int64_t nameLen;
+        if (fread(&nameLen, 8, 1, f) != 1) exit(2);
+        std::string name(nameLen, ' ');
+        if (fread(&name[0], 1, nameLen, f) != size_t(nameLen)) exit(2);
+        Entry e;
+        if (fread(&e.dtype, 8, 1, f) != 1) exit(2);
+        if (fread(&e.count, 8, 1, f) != 1) exit(2);
+        e.bytes.resize(e.count*dtypeSize(e.dtype));
+        if (e.bytes.size() && fread(e.bytes.data(), 1, e.bytes.size(), f) != e.bytes.size())
+        {
+            exit(2);
+        }
+        c[name] = e;
+    }
+    fclose(f);
+    return c;
+}
+
+static void writeContainer(const char* path, const Container& c)
+{
+    FILE* f = fopen(path, "wb");
+    if (!f)
+    {
+        fprintf(stderr, "cannot write %s\n", path);
+        exit(2);
+    }
+    fwrite("B2LS0001", 1, 8, f);
+    int64_t n = c.size();
+    fwrite(&n, 8, 1, f);
+    for (Container::const_iterator it = c.begin(); it != c.end(); ++it)
+    {
+        int64_t nameLen = it->first.size();
+        fwrite(&nameLen, 8, 1, f);
+        fwrite(it->first.data(), 1, nameLen, f);
+        fwrite(&it->second.dtype, 8, 1, f);
+        fwrite(&it->second.count, 8, 1, f);
+        if (it->second.bytes.size())
+        {
+            fwrite(it->second.bytes.data(), 1, it->second.bytes.size(), f);
+        }
+    }
+    fclose(f);
+}
+
+static bool has(const Container& c, const std::string& k)
+{
+    return c.find(k) != c.end();
+}
+
+static const int32_t* i32(const Container& c, const std::string& k)
+{
+    return reinterpret_cast<const int32_t*>(c.at(k).bytes.data());
+}
+
+static const double* f64(const Container& c, const std::string& k)
+{
+    return reinterpret_cast<const double*>(c.at(k).bytes.data());
+}
+
+static std::string str(const Container& c, const std::string& k)
+{
+    const Entry& e = c.at(k);
+    return std::string(e.bytes.begin(), e.bytes.end());
+}
+
+static void putI32(Container& c, const std::string& k, const labelUList& l)
+{
+    Entry e;
+    e.dtype = 0;
+    e.count = l.size();
+    e.bytes.resize(4*l.size());
+    if (l.size()) memcpy(e.bytes.data(), l.begin(), 4*l.size());
+    c[k] = e;
+}
+
+static void putF64(Container& c, const std::string& k, const UList<scalar>& l)
+{
+    Entry e;
+    e.dtype = 1;
+    e.count = l.size();
+    e.bytes.resize(8*l.size());
+    if (l.size()) memcpy(e.bytes.data(), l.begin(), 8*l.size());
+    c[k] = e;
+}
+
+static void putF64(Container& c, const std::string& k, const std::vector<double>& l)
+{
+    Entry e;
+    e.dtype = 1;
+    e.count = l.size();
+    e.bytes.resize(8*l.size());
+    if (l.size()) memcpy(e.bytes.data(), l.data(), 8*l.size());
+    c[k] = e;
+}
+
+static void putU8(Container& c, const std::string& k, const boolList& l)
+{
+    Entry e;
+    e.dtype = 2;
+    e.count = l.size();
+    e.bytes.resize(l.size());
+    forAll(l, i)
+    {
+        e.bytes[i] = l[i] ? 1 : 0;
+    }
+    c[k] = e;
+}
+
+static scalarField toField(const Container& c, const std::string& k)
+{
+    const Entry& e = c.at(k);
+    scalarField f(e.count);
+    if (e.count) memcpy(f.begin(), e.bytes.data(), 8*e.count);
+    return f;
+}
+
+
+// ---------------------------------------------------------------------------
+
+int main(int argc, char* argv[])
+{
+    if (argc < 3)
+    {
+        fprintf
+        (
+            stderr,
+            "usage: ref_harness <case.b2ls> <out.b2ls> [scratchCaseDir]\n"
+        );
+        return 2;
+    }
+
+    Container in = readContainer(argv[1]);
+    Container out;
+
+    // Scratch case directory with a minimal system/controlDict for the Time
+    // object that backs lduMesh::db()
+    std::string scratch = argc > 3 ? argv[3] : "/tmp/b200ls_ref_case";
+    mkDir(fileName(scratch)/"system");
+    mkDir(fileName(scratch)/"constant");
+    {
+        FILE* f = fopen((scratch + "/system/controlDict").c_str(), "w");
+        fprintf
+        (
+            f,
+            "FoamFile{format ascii; class dictionary; object controlDict;}\n"
+            "application harness;\nstartFrom startTime;\nstartTime 0;\n"
+            "stopAt endTime;\nendTime 1;\ndeltaT 1;\nwriteControl timeStep;\n"
+            "writeInterval 1000000;\n"
+        );
+        fclose(f);
+    }
+
+    fileName scratchPath(scratch);
+    Time runTime
+    (
+        Time::controlDictName,
+        scratchPath.path(),
+        scratchPath.name(),
+        false
+    );
+
+    // Optional plugin libraries (the drop-in boundary: controlDict `libs`)
+    if (has(in, "libs"))
+    {
+        IStringStream is("libs (" + str(in, "libs") + ");");
+        dictionary libsDict(is);
+        libs.open(libsDict, "libs");
+    }
+
+    const label nCells = i32(in, "nCells")[0];
+    const label nFaces = in.at("lower").count;
+
+    labelList l(nFaces), u(nFaces);
+    for (label i = 0; i < nFaces; i++)
+    {
+        l[i] = i32(in, "lower")[i];
+        u[i] = i32(in, "upper")[i];
+    }
+
+    if (has(in, "faceWeights"))
+    {
+        g_faceWeights.assign
+        (
+            f64(in, "faceWeights"),
+            f64(in, "faceWeights") + in.at("faceWeights").count
+        );
+    }
+
+    harnessLduMesh mesh(runTime, nCells, l, u);
+    lduInterfacePtrsList noInterfaces(0);
+    mesh.addInterfaces(noInterfaces, lduSchedule());
+
+    // --- integer addressing -------------------------------------------------
+    putI32(out, "losort", mesh.lduAddr().losortAddr());
+    putI32(out, "ownerStart", mesh.lduAddr().ownerStartAddr());
+    putI32(out, "losortStart", mesh.lduAddr().losortStartAddr());
+
+    lduMatrix A(mesh);
+    if (has(in, "diag"))
+    {
+        A.diag() = toField(in, "diag");
+        A.upper() = toField(in, "upperCoeffs");
+        if (has(in, "lowerCoeffs"))
+        {
+            A.lower() = toField(in, "lowerCoeffs");
+        }
+    }
+
+    const Field<Field<scalar>> noCoeffs(0);
+    const lduInterfaceFieldPtrsList noIfaces(0);
+
+    // --- operators ------------------------------------------------------------
+    if (has(in, "x"))
+    {
+        const scalarField x(toField(in, "x"));
+        scalarField Ax(nCells);
+        A.Amul(Ax, x, noCoeffs, noIfaces, 0);
+        putF64(out, "Amul", Ax);
+
+        scalarField sA(nCells);
+        A.sumA(sA, noCoeffs, noIfaces);
+        putF64(out, "sumA", sA);
+
+        if (has(in, "source"))
+        {
+            scalarField rA(nCells);
+            A.residual(rA, x, toField(in, "source"), noCoeffs, noIfaces, 0);
+            putF64(out, "residual", rA);
+        }
+
+        // DIC (symmetric) or DILU (asymmetric) factor + one application to x
+        if (!A.asymmetric())
+        {
+            scalarField rD(A.diag());
+            DICPreconditioner::calcReciprocalD(rD, A);
+            putF64(out, "DIC_rD", rD);
+        }
+        else
+        {
+            scalarField rD(A.diag());
+            DILUPreconditioner::calcReciprocalD(rD, A);
+            putF64(out, "DILU_rD", rD);
+        }
+        {
+            // precondition through the selection table, as PCG/PBiCGStab do
+            IStringStream is
+            (
+                A.asymmetric()
+              ? "solver PBiCGStab; preconditioner DILU;"
+              : "solver PCG; preconditioner DIC;"
+            );
+            dictionary d(is);
+            autoPtr<lduMatrix::solver> sol = lduMatrix::solver::New
+            (
+                "p", A, noCoeffs, noCoeffs, noIfaces, d
+            );
+            autoPtr<lduMatrix::preconditioner> pre =
+                lduMatrix::preconditioner::New(sol(), d);
+            scalarField wA(nCells);
+            pre->precondition(wA, x, 0);
+            putF64(out, "precondition", wA);
+        }
+    }
+
+    // --- smoothers: entries "smooth.<i>.dict" (e.g. "smoother GaussSeidel;"),
+    //     "smooth.<i>.nSweeps"; psi0 = x, rhs = source
+    for (int i = 0; ; i++)
+    {
+        const std::string key = "smooth." + std::to_string(i);
+        if (!has(in, key + ".dict")) break;
+
+        IStringStream is(str(in, key + ".dict"));
+        dictionary d(is);
+        autoPtr<lduMatrix::smoother> sm = lduMatrix::smoother::New
+        (
+            "p", A, noCoeffs, noCoeffs, noIfaces, d
+        );
+        scalarField psi(toField(in, "x"));
+        const scalarField b(toField(in, "source"));
+        sm->smooth(psi, b, 0, i32(in, key + ".nSweeps")[0]);
+        putF64(out, key + ".psi", psi);
+    }
+
+    // --- solves: entries "solve.<i>.dict", optional "solve.<i>.history" = k:
+    //     re-run with maxIter=1..k and store the final residual of each run
+    for (int i = 0; ; i++)
+    {
+        const std::string key = "solve." + std::to_string(i);
+        if (!has(in, key + ".dict")) break;
+
+        const std::string dictStr = str(in, key + ".dict");
+        const scalarField b(toField(in, "source"));
+        const scalarField psi0
+        (
+            has(in, "psi0") ? toField(in, "psi0") : scalarField(nCells, 0.0)
+        );
+
+        IStringStream is(dictStr);
+        dictionary d(is);
+
+        scalarField psi(psi0);
+        clockTime timer;
+        solverPerformance perf = lduMatrix::solver::New
+        (
+            "p", A, noCoeffs, noCoeffs, noIfaces, d
+        )->solve(psi, b);
+        const double secs = timer.elapsedTime();
+
+        std::vector<double> p(6);
+        p[0] = perf.initialResidual();
+        p[1] = perf.finalResidual();
+        p[2] = perf.nIterations();
+        p[3] = perf.converged();
+        p[4] = perf.singular();
+        p[5] = secs;
+        putF64(out, key + ".perf", p);
+        putF64(out, key + ".psi", psi);
+        {
+            Entry e;
+            const std::string nm = perf.solverName();
+            e.dtype = 2;
+            e.count = nm.size();
+            e.bytes.assign(nm.begin(), nm.end());
+            out[key + ".solverName"] = e;
+        }
+
+        if (has(in, key + ".history"))
+        {
+            const label k = i32(in, key + ".history")[0];
+            std::vector<double> hist;
+            for (label it = 1; it <= k; it++)
+            {
+                dictionary dk(d);
+                dk.set("maxIter", it);
+                dk.set("tolerance", 0);
+                dk.set("relTol", 0);
+                scalarField psik(psi0);
+                solverPerformance pk = lduMatrix::solver::New
+                (
+                    "p", A, noCoeffs, noCoeffs, noIfaces, dk
+                )->solve(psik, b);
+                hist.push_back(pk.finalResidual());
+            }
+            putF64(out, key + ".historyResiduals", hist);
+        }
+    }
+
+    // --- agglomeration dump: entry "agglomerate.dict" (GAMG controls) --------
+    if (has(in, "agglomerate.dict"))
+    {
+        IStringStream is(str(in, "agglomerate.dict"));
+        dictionary d(is);
+        const GAMGAgglomeration& agg = GAMGAgglomeration::New(mesh, d);
+
+        labelList nLevels(1, agg.size());
+        putI32(out, "agg.nLevels", nLevels);
+
+        for (label lev = 0; lev < agg.size(); lev++)
+        {
+            const std::string k = "agg." + std::to_string(lev);
+            labelList sizes(2);
+            sizes[0] = agg.nCells(lev);
+            sizes[1] = agg.nFaces(lev);
+            putI32(out, k + ".sizes", sizes);
+            putI32(out, k + ".restrictAddressing", agg.restrictAddressing(lev));
+            putI32
+            (
+                out,
+                k + ".faceRestrictAddressing",
+                agg.faceRestrictAddressing(lev)
+            );
+            putU8(out, k + ".faceFlipMap", agg.faceFlipMap(lev));
+            const lduAddressing& ca = agg.meshLevel(lev + 1).lduAddr();
+            putI32(out, k + ".coarseLower", ca.lowerAddr());
+            putI32(out, k + ".coarseUpper", ca.upperAddr());
+        }
+    }
+
+    writeContainer(argv[2], out);
+
+    return 0;
+}
