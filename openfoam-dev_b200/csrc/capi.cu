@@ -1,0 +1,415 @@
+// extern "C" surface of libb200ls.so (include/b200ls.h): argument checking, exception -> error-code
+// translation, host<->device staging.  No compute lives here.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+#include "solver.cuh"
+
+using namespace b200ls;
+
+namespace {
+
+thread_local std::string g_lastError;
+bool g_forward = true;   // mirror of the reference's process-global pairGAMGAgglomeration::forward_
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return 1;
+    } catch (...) {
+        g_lastError = "unknown error";
+        return 1;
+    }
+}
+
+template <class T>
+T* sym(void* h, const char* name) {
+    void* p = dlsym(h, name);
+    if (!p) throw CudaError(std::string("NCCL symbol not found: ") + name);
+    return reinterpret_cast<T*>(p);
+}
+
+void loadNccl(NcclApi& n) {
+    if (n.handle) return;
+    n.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.handle) n.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.handle) throw CudaError(std::string("cannot load NCCL: ") + dlerror());
+    n.GetUniqueId = sym<std::remove_pointer_t<decltype(n.GetUniqueId)>>(n.handle, "ncclGetUniqueId");
+    n.CommInitRank = sym<std::remove_pointer_t<decltype(n.CommInitRank)>>(n.handle, "ncclCommInitRank");
+    n.CommDestroy = sym<std::remove_pointer_t<decltype(n.CommDestroy)>>(n.handle, "ncclCommDestroy");
+    n.AllReduce = sym<std::remove_pointer_t<decltype(n.AllReduce)>>(n.handle, "ncclAllReduce");
+    n.Send = sym<std::remove_pointer_t<decltype(n.Send)>>(n.handle, "ncclSend");
+    n.Recv = sym<std::remove_pointer_t<decltype(n.Recv)>>(n.handle, "ncclRecv");
+    n.GroupStart = sym<std::remove_pointer_t<decltype(n.GroupStart)>>(n.handle, "ncclGroupStart");
+    n.GroupEnd = sym<std::remove_pointer_t<decltype(n.GroupEnd)>>(n.handle, "ncclGroupEnd");
+    n.GetErrorString = sym<std::remove_pointer_t<decltype(n.GetErrorString)>>(n.handle, "ncclGetErrorString");
+}
+
+// stage a host vector of level-0 size into `dev` (cell order)
+void h2d(double* dev, const double* host, int n) {
+    if (n) B2_CUDA(cudaMemcpyAsync(dev, host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx().stream));
+}
+void d2h(double* host, const double* dev, int n) {
+    if (n) B2_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx().stream));
+    B2_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+void requireValues(b200ls_matrix_t m) {
+    if (!m || !m->valuesSet) throw CudaError("matrix coefficients not set (call b200ls_matrix_set)");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200ls_last_error(void) { return g_lastError.c_str(); }
+
+int b200ls_device_available(void) {
+    int n = 0;
+    return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+}
+
+int b200ls_nccl_unique_id(void* out128) {
+    return guarded([&] {
+        loadNccl(ctx().nccl);
+        ncclUniqueId id;
+        int r = ctx().nccl.GetUniqueId(&id);
+        if (r != 0) throw CudaError("ncclGetUniqueId failed");
+        static_assert(sizeof(id) == 128, "ncclUniqueId size");
+        memcpy(out128, &id, 128);
+    });
+}
+
+int b200ls_init(int device, const void* ncclUniqueId_, int rank, int nRanks) {
+    return guarded([&] {
+        Context& c = ctx();
+        if (c.initialised && (c.device != device || c.nRanks != nRanks || c.rank != rank)) {
+            throw CudaError("b200ls_init called twice with different arguments");
+        }
+        c.device = device;
+        ensureInit();
+        if (nRanks > 1 && !c.comm) {
+            if (!ncclUniqueId_) throw CudaError("nRanks > 1 needs an ncclUniqueId");
+            loadNccl(c.nccl);
+            ncclUniqueId id;
+            memcpy(&id, ncclUniqueId_, 128);
+            int r = c.nccl.CommInitRank(&c.comm, nRanks, id, rank);
+            if (r != 0) throw CudaError(std::string("ncclCommInitRank: ") + c.nccl.GetErrorString((ncclResult_t)r));
+        }
+        c.rank = rank;
+        c.nRanks = nRanks;
+    });
+}
+
+void b200ls_finalize(void) {
+    Context& c = ctx();
+    if (!c.initialised) return;
+    cudaStreamSynchronize(c.stream);
+    if (c.comm) {
+        c.nccl.CommDestroy(c.comm);
+        c.comm = nullptr;
+    }
+}
+
+b200ls_mesh_t b200ls_mesh_create(int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
+                                 int32_t nInterfaces, const int32_t* ifaceSizes,
+                                 const int32_t* const* ifaceFaceCells, const int32_t* ifaceNeighbRank) {
+    b200ls_mesh_t mesh = nullptr;
+    int rc = guarded([&] {
+        std::vector<HostInterface> ifs(nInterfaces);
+        for (int i = 0; i < nInterfaces; i++) {
+            ifs[i].neighbRank = ifaceNeighbRank[i];
+            ifs[i].faceCells.assign(ifaceFaceCells[i], ifaceFaceCells[i] + ifaceSizes[i]);
+        }
+        std::unique_ptr<b200ls_mesh_s> m(new b200ls_mesh_s);
+        m->host.levels.resize(1);
+        m->host.nRanks = ctx().nRanks;
+        m->host.rank = ctx().rank;
+        buildLevel(m->host.levels[0], nCells, nFaces, lower, upper, std::move(ifs));
+        mesh = m.release();
+    });
+    return rc == 0 ? mesh : nullptr;
+}
+
+void b200ls_mesh_free(b200ls_mesh_t mesh) { delete mesh; }
+
+int b200ls_mesh_n_levels(b200ls_mesh_t mesh) { return mesh ? int(mesh->host.levels.size()) : 0; }
+
+int b200ls_mesh_get_i32(b200ls_mesh_t mesh, int which, int level, const int32_t** data, int64_t* n) {
+    return guarded([&] {
+        if (!mesh) throw CudaError("null mesh");
+        if (level < 0 || level >= int(mesh->host.levels.size())) throw CudaError("level out of range");
+        LevelHost& L = mesh->host.levels[level];
+        static thread_local std::vector<int32_t> sizes;
+        const std::vector<int32_t>* v = nullptr;
+        switch (which) {
+            case B200LS_LOSORT: v = &L.losort; break;
+            case B200LS_OWNER_START: v = &L.ownerStart; break;
+            case B200LS_LOSORT_START: v = &L.losortStart; break;
+            case B200LS_FWD_LEVEL_OFFSETS: v = &L.fwdOffsets; break;
+            case B200LS_FWD_LEVEL_ROWS: v = &L.fwdRows; break;
+            case B200LS_BWD_LEVEL_OFFSETS: v = &L.bwdOffsets; break;
+            case B200LS_BWD_LEVEL_ROWS: v = &L.bwdRows; break;
+            case B200LS_RESTRICT_ADDRESSING: v = &L.restrictAddr; break;
+            case B200LS_FACE_RESTRICT_ADDRESSING: v = &L.faceRestrictAddr; break;
+            case B200LS_FACE_FLIP_MAP: v = &L.faceFlip; break;
+            case B200LS_LOWER_ADDR: v = &L.lower; break;
+            case B200LS_UPPER_ADDR: v = &L.upper; break;
+            case B200LS_LEVEL_SIZES:
+                sizes = {L.nCells, L.nFaces};
+                v = &sizes;
+                break;
+            default: throw CudaError("unknown array id");
+        }
+        if ((which == B200LS_RESTRICT_ADDRESSING || which == B200LS_FACE_RESTRICT_ADDRESSING ||
+             which == B200LS_FACE_FLIP_MAP) && !L.hasCoarse) {
+            throw CudaError("level has no coarser level");
+        }
+        *data = v->data();
+        *n = int64_t(v->size());
+    });
+}
+
+int b200ls_agglomerate(b200ls_mesh_t mesh, const double* faceWeights, int32_t minCellsPerProcessor,
+                       int32_t mergeLevels, int32_t forwardStart) {
+    int nCoarse = -1;
+    int rc = guarded([&] {
+        if (!mesh) throw CudaError("null mesh");
+        bool fwd = forwardStart < 0 ? g_forward : (forwardStart != 0);
+        nCoarse = agglomerate(mesh->host, faceWeights, minCellsPerProcessor, mergeLevels, fwd);
+        g_forward = fwd;
+        mesh->dev.reset();
+        mesh->generation++;
+    });
+    return rc == 0 ? nCoarse : -1;
+}
+
+b200ls_matrix_t b200ls_matrix_create(b200ls_mesh_t mesh) {
+    if (!mesh) {
+        g_lastError = "null mesh";
+        return nullptr;
+    }
+    b200ls_matrix_t m = new b200ls_matrix_s;
+    m->mesh = mesh;
+    return m;
+}
+
+void b200ls_matrix_free(b200ls_matrix_t m) { delete m; }
+
+int b200ls_matrix_set(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
+                      const double* const* bou, const double* const* inn) {
+    return guarded([&] {
+        if (!m) throw CudaError("null matrix");
+        matrixSet(m, diag, upper, lower, bou, inn);
+    });
+}
+
+int b200ls_amul(b200ls_matrix_t m, const double* psi, double* Apsi) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        double* x = m->vec("psi");
+        double* y = m->vec("wA");
+        h2d(m->stageA.p, psi, n);
+        toPositions(m, 0, x, m->stageA.p);
+        opAmul(m, 0, y, x);
+        toCells(m, 0, m->stageA.p, y);
+        d2h(Apsi, m->stageA.p, n);
+    });
+}
+
+int b200ls_residual(b200ls_matrix_t m, const double* psi, const double* source, double* rA) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        double* x = m->vec("psi");
+        double* b = m->vec("source");
+        double* y = m->vec("wA");
+        h2d(m->stageA.p, psi, n);
+        toPositions(m, 0, x, m->stageA.p);
+        h2d(m->stageA.p, source, n);
+        toPositions(m, 0, b, m->stageA.p);
+        opResidual(m, 0, y, x, b);
+        toCells(m, 0, m->stageA.p, y);
+        d2h(rA, m->stageA.p, n);
+    });
+}
+
+int b200ls_sum_a(b200ls_matrix_t m, double* sumA) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        double* y = m->vec("wA");
+        opSumA(m, 0, y);
+        toCells(m, 0, m->stageA.p, y);
+        d2h(sumA, m->stageA.p, n);
+    });
+}
+
+int b200ls_precondition(b200ls_matrix_t m, int precond, const double* rA, double* wA) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        double* x = m->vec("rA");
+        double* y = m->vec("wA");
+        h2d(m->stageA.p, rA, n);
+        toPositions(m, 0, x, m->stageA.p);
+        opPrecondition(m, 0, precond, y, x);
+        toCells(m, 0, m->stageA.p, y);
+        d2h(wA, m->stageA.p, n);
+        checkSweepError();
+    });
+}
+
+int b200ls_reciprocal_d(b200ls_matrix_t m, int precond, double* rD) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        m->levels[0].rDValid = false;
+        ensureFactor(m, 0, precond);
+        toCells(m, 0, m->stageA.p, m->levels[0].rD.p);
+        d2h(rD, m->stageA.p, n);
+        checkSweepError();
+    });
+}
+
+int b200ls_smooth(b200ls_matrix_t m, int smoother, double* psi, const double* source, int32_t nSweeps) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        b200ls::Vec& vPsi = m->vecs["psi"];
+        b200ls::Vec& vSpare = m->vecs["psiSpare"];
+        m->vec("psi");
+        m->vec("psiSpare");
+        double* b = m->vec("source");
+        h2d(m->stageA.p, psi, n);
+        toPositions(m, 0, vPsi.buf.p, m->stageA.p);
+        h2d(m->stageA.p, source, n);
+        toPositions(m, 0, b, m->stageA.p);
+        if (smoother == B200LS_DIC || smoother == B200LS_DILU) {
+            m->levels[0].rDValid = false;
+            ensureFactor(m, 0, smoother);
+        }
+        opSmooth(m, 0, smoother, vPsi.buf.p, vSpare.buf.p, b, nSweeps);
+        toCells(m, 0, m->stageA.p, vPsi.buf.p);
+        d2h(psi, m->stageA.p, n);
+        checkSweepError();
+    });
+}
+
+void b200ls_controls_default(b200ls_controls* c) {
+    memset(c, 0, sizeof(*c));
+    c->solver = B200LS_PCG;
+    c->precond = B200LS_DIC;
+    c->tolerance = 1e-6;
+    c->relTol = 0;
+    c->maxIter = 1000;
+    c->minIter = 0;
+    c->nPreSweeps = 0;
+    c->preSweepsLevelMultiplier = 1;
+    c->maxPreSweeps = 4;
+    c->nPostSweeps = 2;
+    c->postSweepsLevelMultiplier = 1;
+    c->maxPostSweeps = 4;
+    c->nFinestSweeps = 2;
+    c->scaleCorrection = -1;
+    c->nSweeps = 1;
+    c->recordHistory = 0;
+}
+
+int b200ls_solve_dev(b200ls_matrix_t m, const b200ls_controls* c, double* psi_dev, const double* source_dev,
+                     b200ls_perf* perf) {
+    return guarded([&] {
+        requireValues(m);
+        solveDev(m, *c, psi_dev, source_dev, perf);
+    });
+}
+
+int b200ls_solve(b200ls_matrix_t m, const b200ls_controls* c, double* psi, const double* source,
+                 b200ls_perf* perf) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        m->stageA.alloc(std::max<size_t>(m->stageA.n, n));
+        m->stageB.alloc(std::max<size_t>(m->stageB.n, n));
+        cudaEvent_t e0, e1, e2, e3;
+        B2_CUDA(cudaEventCreate(&e0));
+        B2_CUDA(cudaEventCreate(&e1));
+        B2_CUDA(cudaEventCreate(&e2));
+        B2_CUDA(cudaEventCreate(&e3));
+        B2_CUDA(cudaEventRecord(e0, ctx().stream));
+        h2d(m->stageA.p, psi, n);
+        h2d(m->stageB.p, source, n);
+        B2_CUDA(cudaEventRecord(e1, ctx().stream));
+        solveDev(m, *c, m->stageA.p, m->stageB.p, perf);
+        B2_CUDA(cudaEventRecord(e2, ctx().stream));
+        d2h(psi, m->stageA.p, n);
+        B2_CUDA(cudaEventRecord(e3, ctx().stream));
+        B2_CUDA(cudaEventSynchronize(e3));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e2, e3);
+        perf->h2dMs = a + b;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaEventDestroy(e2);
+        cudaEventDestroy(e3);
+    });
+}
+
+int b200ls_time_kernel(b200ls_matrix_t m, int which, int reps, double* ms) {
+    return guarded([&] {
+        requireValues(m);
+        const int n = m->mesh->host.levels[0].nCells;
+        double* x = m->vec("psi");
+        double* y = m->vec("wA");
+        double* r = m->vec("rA");
+        cudaStream_t s = ctx().stream;
+        // deterministic, finite contents
+        if (n) {
+            k_fill<<<1024, 256, 0, s>>>(x, 1.0, n);
+            k_fill<<<1024, 256, 0, s>>>(r, 1.0, n);
+        }
+        b200ls::Vec& vPsi = m->vecs["psi"];
+        b200ls::Vec& vSpare = m->vecs["psiSpare"];
+        m->vec("psiSpare");
+        if (which == 1) ensureFactor(m, 0, m->symmetric ? B200LS_DIC : B200LS_DILU);
+        cudaEvent_t e0, e1;
+        B2_CUDA(cudaEventCreate(&e0));
+        B2_CUDA(cudaEventCreate(&e1));
+        auto once = [&] {
+            switch (which) {
+                case 0: opAmul(m, 0, y, x); break;
+                case 1: opPrecondition(m, 0, m->symmetric ? B200LS_DIC : B200LS_DILU, y, r); break;
+                case 2: opSmooth(m, 0, B200LS_GAUSS_SEIDEL, vPsi.buf.p, vSpare.buf.p, r, 1); break;
+                default: throw CudaError("unknown kernel id");
+            }
+        };
+        for (int i = 0; i < 3; i++) once();
+        B2_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < reps; i++) once();
+        B2_CUDA(cudaEventRecord(e1, s));
+        B2_CUDA(cudaEventSynchronize(e1));
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        *ms = double(t) / reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        checkSweepError();
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// Device-side containers of libb200ls: context (stream, NCCL), per-level addressing in HBM, per-matrix
+// coefficient storage and the work-vector pool.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mesh.hpp"
+
+namespace b200ls {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define B2_CUDA(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            throw ::b200ls::CudaError(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + \
+                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");                  \
+        }                                                                                                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        if (count == n && p) return;
+        release();
+        n = count;
+        if (count) B2_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T>& h, cudaStream_t s) {
+        alloc(h.size());
+        if (!h.empty()) B2_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+// NCCL entry points resolved with dlopen at b200ls_init (no link-time dependency: the library must load on
+// machines without NCCL/GPU for the host-logic tests)
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+struct Context {
+    bool initialised = false;
+    int device = 0;
+    int numSMs = 148;
+    int rank = 0, nRanks = 1;
+    cudaStream_t stream = nullptr;
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    // reduction scratch
+    DevBuf<double> partials;
+    DevBuf<unsigned int> ticket;
+    DevBuf<int> errFlag;
+    double* pinned = nullptr;       // pinned host scratch for scalar read-back (64 doubles)
+    int64_t launches = 0;           // kernels launched since the counter was last reset
+    int sweepBlocksPerSM = 0;       // 0 = occupancy maximum
+};
+
+Context& ctx();
+void ensureInit();
+
+// Addressing of one level in HBM (built once per mesh)
+struct DevLevel {
+    int nCells = 0, nFaces = 0;
+    DevBuf<int> perm, ipos;
+    DevBuf<int> Lptr, Lcol, Lface, Uptr, Ucol, Uface, LtoU;
+    DevBuf<int2> fwdTasks, bwdTasks;
+    DevBuf<int> bwdPos;
+    int nFwdTasks = 0, nBwdTasks = 0;
+    // interfaces
+    int nIfaces = 0;
+    std::vector<int> ifaceSize, ifaceNbr;
+    std::vector<DevBuf<int>> ifaceCellsPos;
+    DevBuf<int> bRowPos, bRowPtr, bEntIface, bEntFace;
+    int nBRows = 0;
+    // maps to the next coarser level
+    bool hasCoarse = false;
+    DevBuf<int> rPtr, rFine, pMap, auPtr, auSrc, alPtr, alSrc, adPtr, adU, adL;
+    std::vector<DevBuf<int>> aiPtr, aiSrc;
+    // coarsest-level direct data (reference order) for the single-thread coarsest solve
+    DevBuf<int> refLower, refUpper, Uidx, Lidx;
+};
+
+struct DeviceMesh {
+    std::vector<std::unique_ptr<DevLevel>> levels;
+};
+
+}  // namespace b200ls
+
+struct b200ls_mesh_s {
+    b200ls::HostMesh host;
+    std::unique_ptr<b200ls::DeviceMesh> dev;   // created lazily at first device use
+    int generation = 0;                        // bumped by re-agglomeration
+};

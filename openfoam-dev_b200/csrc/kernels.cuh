@@ -1,0 +1,629 @@
+// sm_100a kernels of libb200ls.  Every kernel on this path is HBM/L2-latency bound fp64 + int32 work:
+// plain CUDA cores, no tensor cores (nothing here is a dense contraction).
+//
+// Numerical contract (SURVEY.md 8(a) "canonical derived integer data"): each row accumulates in the
+// reference's order -- diagonal term, neighbour-side faces ascending, owner-side faces ascending (descending
+// for backward sweeps) -- and the translation unit is compiled with -fmad=false, so per-row results are
+// bit-identical to the reference's sequential face loops.  Only the global reductions (dot products) differ
+// in summation order.
+//
+// Rows live in "positions" = forward-wavefront-major order (mesh.hpp).  L* arrays hold the neighbour-side
+// entries of each row, U* arrays the owner-side entries.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200ls {
+
+// Signalling-NaN bit pattern that fp64 arithmetic can never produce (arithmetic yields the canonical quiet
+// NaN): used as "row not finished yet" marker by the sync-free sweeps.
+static constexpr unsigned long long kSentinelBits = 0x7FF4B2005E471AE1ull;
+
+__device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)kSentinelBits); }
+
+// L2-coherent load/store (sweeps communicate between SMs through L2; L1 must be bypassed)
+__device__ __forceinline__ double ld_l2(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_l2(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == (long long)kSentinelBits; }
+
+// Poll budget of one wait: ~2^22 L2 round trips (seconds).  A logic error sets *err instead of hanging the GPU.
+static constexpr unsigned kMaxSpins = 1u << 22;
+
+// ------------------------------------------------------------------------------------------------------------
+// elementwise / permutation
+// ------------------------------------------------------------------------------------------------------------
+
+__global__ void k_gather(double* __restrict__ out, const double* __restrict__ in, const int* __restrict__ idx,
+                         int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[idx[i]];
+}
+
+__global__ void k_fill(double* __restrict__ out, double v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = v;
+}
+
+__global__ void k_fill_sentinel(double* __restrict__ out, int n) {
+    const double s = sentinel();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = s;
+}
+
+// out = a - b
+__global__ void k_sub(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] - b[i];
+}
+
+// x += y
+__global__ void k_add_inplace(double* __restrict__ x, const double* __restrict__ y, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += y[i];
+}
+
+// x -= y
+__global__ void k_sub_inplace(double* __restrict__ x, const double* __restrict__ y, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] -= y[i];
+}
+
+// out = a * b   (diagonalPreconditioner::precondition: wA = rD*rA)
+__global__ void k_mul(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] * b[i];
+}
+
+// out = x / d   (diagonal preconditioner / diagonalSolver)
+__global__ void k_div(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ d, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[i] / d[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SpMV family: lduMatrix::Amul / residual / sumA  (lduMatrixATmul.C:34-92, 203-280, 154-200)
+// ------------------------------------------------------------------------------------------------------------
+
+enum { SPMV_AMUL = 0, SPMV_RESIDUAL = 1, SPMV_AMUL_AND_RESIDUAL = 2, SPMV_SUMA = 3 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_spmv(double* __restrict__ out, double* __restrict__ out2, const double* __restrict__ x,
+       const double* __restrict__ b, const double* __restrict__ diag, const int* __restrict__ Lptr,
+       const int* __restrict__ Lcol, const double* __restrict__ Lval, const int* __restrict__ Uptr,
+       const int* __restrict__ Ucol, const double* __restrict__ Uval, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int l0 = Lptr[p], l1 = Lptr[p + 1];
+    const int u0 = Uptr[p], u1 = Uptr[p + 1];
+    double acc;
+    if (MODE == SPMV_SUMA) {
+        acc = diag[p];
+        for (int j = l0; j < l1; j++) acc += Lval[j];
+        for (int j = u0; j < u1; j++) acc += Uval[j];
+        out[p] = acc;
+        return;
+    }
+    if (MODE == SPMV_RESIDUAL) {
+        acc = b[p] - diag[p] * x[p];
+        for (int j = l0; j < l1; j++) acc -= Lval[j] * x[Lcol[j]];
+        for (int j = u0; j < u1; j++) acc -= Uval[j] * x[Ucol[j]];
+        out[p] = acc;
+        return;
+    }
+    acc = diag[p] * x[p];
+    for (int j = l0; j < l1; j++) acc += Lval[j] * x[Lcol[j]];
+    for (int j = u0; j < u1; j++) acc += Uval[j] * x[Ucol[j]];
+    out[p] = acc;
+    if (MODE == SPMV_AMUL_AND_RESIDUAL) out2[p] = b[p] - acc;
+}
+
+// Coupled-interface epilogue: result[faceCells[i]] -= coeffs[i]*recv[i] in (patch, face) order
+// (processorFvPatchScalarField.C:133-136).  One thread per boundary row.  sign = +1 for Amul, -1 when the
+// caller negated the coefficients (residual, GaussSeidel).
+struct IfaceView {
+    const double* coeffs;   // per patch face
+    const double* recv;     // per patch face, neighbour values
+};
+__global__ void k_iface_apply(double* __restrict__ result, const int* __restrict__ rowPos,
+                              const int* __restrict__ rowPtr, const int* __restrict__ entIface,
+                              const int* __restrict__ entFace, const IfaceView* __restrict__ views, double sign,
+                              int nRows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRows) return;
+    const int p = rowPos[r];
+    double acc = result[p];
+    for (int e = rowPtr[r]; e < rowPtr[r + 1]; e++) {
+        const IfaceView v = views[entIface[e]];
+        const int f = entFace[e];
+        acc -= (sign * v.coeffs[f]) * v.recv[f];
+    }
+    result[p] = acc;
+}
+
+// send[i] = psi[faceCellsPos[i]]  (patchInternalField, processorFvPatchScalarField.C:45)
+__global__ void k_iface_pack(double* __restrict__ send, const double* __restrict__ psi,
+                             const int* __restrict__ faceCellsPos, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) send[i] = psi[faceCellsPos[i]];
+}
+
+// sumA -= bouCoeffs on interface rows (lduMatrixATmul.C:185-199)
+__global__ void k_iface_suma(double* __restrict__ sumA, const int* __restrict__ rowPos,
+                             const int* __restrict__ rowPtr, const int* __restrict__ entIface,
+                             const int* __restrict__ entFace, const IfaceView* __restrict__ views, int nRows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRows) return;
+    const int p = rowPos[r];
+    double acc = sumA[p];
+    for (int e = rowPtr[r]; e < rowPtr[r + 1]; e++) acc -= views[entIface[e]].coeffs[entFace[e]];
+    sumA[p] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Sync-free wavefront sweeps.  Persistent grid (every CTA co-resident, cooperative launch): warp w takes tasks
+// w, w+W, ... ; a task is <=32 rows of ONE wavefront, so lanes of a warp never wait on each other, and a warp
+// only ever waits on tasks with a smaller index => deadlock free.  A row publishes its result with a single
+// 8-byte L2 store; consumers spin on the sentinel (wait_row).
+// ------------------------------------------------------------------------------------------------------------
+
+struct SweepArgs {
+    const int2* tasks;
+    int nTasks;
+    const int* rowOf;       // backward sweeps: processing slot -> position (nullptr = identity)
+    const int* ptr;         // Lptr (forward) / Uptr (backward)
+    const int* col;
+    const double* val;
+    const int* ptr2;        // the other triangle (GaussSeidel, factor)
+    const int* col2;
+    const double* val2;
+    const double* diag;
+    const double* rD;
+    const double* in;       // rA (forward) / forward result (backward) / source (GS)
+    const double* old;      // GS: previous iterate
+    double* out;            // sentinel-initialised result
+    double* out2;           // optional second output (factor: rD)
+    double* clear;          // optional: array whose entry p is reset to the sentinel once row p is done
+    int* err;
+};
+
+// Dependency gather of one row: acc -= (scale*val[j]) * y[col[j]] for j ascending (DESC=false) or descending
+// (DESC=true), waiting for each y entry to be published.  The static loads (col, val) of a chunk of 4 entries
+// are issued first, then ALL outstanding dependencies are polled together in every spin round: a row whose
+// dependencies become visible at about the same time pays one L2 round trip, not one per entry.  (Measured on
+// B200, 128^3: 1.8 ms per sweep polling entry by entry, 0.25 ms polling all at once + warp reconvergence.)
+template <bool DESC, bool SCALE>
+__device__ __forceinline__ double gather_deps(double acc, double scale, int j0, int j1, const int* __restrict__ col,
+                                              const double* __restrict__ val, const double* y, int* err) {
+    for (int base = 0; base < j1 - j0; base += 4) {
+        const int n = min(4, j1 - j0 - base);
+        int c[4];
+        double v[4], w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < n) {
+                const int j = DESC ? (j1 - 1 - base - k) : (j0 + base + k);
+                c[k] = col[j];
+                v[k] = val[j];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < n) w[k] = ld_l2(y + c[k]);
+        unsigned spins = 0;
+        while (true) {
+            bool pending = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < n && is_sentinel(w[k])) pending = true;
+            if (!pending) break;
+            if (++spins > kMaxSpins) {
+                *err = 1;
+                break;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < n && is_sentinel(w[k])) w[k] = ld_l2(y + c[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < n) acc -= (SCALE ? scale * v[k] : v[k]) * w[k];
+    }
+    return acc;
+}
+
+#define SWEEP_TASK_LOOP(a)                                                            \
+    const int wpb = blockDim.x >> 5;                                                  \
+    const int nW = gridDim.x * wpb;                                                   \
+    const int lane = threadIdx.x & 31;                                                \
+    int t = blockIdx.x * wpb + (threadIdx.x >> 5);                                    \
+    int2 task = t < (a).nTasks ? (a).tasks[t] : make_int2(0, 0);                      \
+    for (; t < (a).nTasks; t += nW)
+
+#define SWEEP_NEXT_TASK(a) ((t + nW) < (a).nTasks ? (a).tasks[t + nW] : make_int2(0, 0))
+
+// DIC/DILU calcReciprocalD (DICPreconditioner.C:71-83, DILUPreconditioner.C:72-84):
+//   d[u] = diag[u] - sum_{f: upper(f)=u, ascending} upper[f]*lower[f]/d[lower(f)] ;  rD = 1/d
+// val = Lval (lower[f]), val2 = the matching upper[f] gathered through LtoU (col2).
+__global__ void __launch_bounds__(256) k_factor(SweepArgs a) {
+    const double sent = sentinel();
+    SWEEP_TASK_LOOP(a) {
+        const int2 next = SWEEP_NEXT_TASK(a);
+        if (lane < task.y) {
+            const int p = task.x + lane;
+            double acc = a.diag[p];
+            const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
+            for (int base = j0; base < j1; base += 4) {
+                const int n = min(4, j1 - base);
+                int c[4];
+                double num[4], w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < n) {
+                        const double lo = a.val[base + k];
+                        const double up = a.col2 ? a.val2[a.col2[base + k]] : lo;
+                        c[k] = a.col[base + k];
+                        num[k] = up * lo;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < n) w[k] = ld_l2(a.out + c[k]);
+                unsigned spins = 0;
+                while (true) {
+                    bool pending = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k < n && is_sentinel(w[k])) pending = true;
+                    if (!pending) break;
+                    if (++spins > kMaxSpins) {
+                        *a.err = 1;
+                        break;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k < n && is_sentinel(w[k])) w[k] = ld_l2(a.out + c[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < n) acc -= num[k] / w[k];
+            }
+            st_l2(a.out + p, acc);
+            a.out2[p] = 1.0 / acc;
+            if (a.clear) a.clear[p] = sent;
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
+// forward substitution of DIC/DILU precondition with the scaling pass fused:
+//   y[u] = rD[u]*rA[u] - sum_{f ascending} (rD[u]*lower[f]) * y[lower(f)]
+__global__ void __launch_bounds__(256) k_sweep_fwd(SweepArgs a) {
+    const double sent = sentinel();
+    SWEEP_TASK_LOOP(a) {
+        const int2 next = SWEEP_NEXT_TASK(a);
+        if (lane < task.y) {
+            const int p = task.x + lane;
+            const double rd = a.rD[p];
+            const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
+            double acc = rd * a.in[p];
+            acc = gather_deps<false, true>(acc, rd, j0, j1, a.col, a.val, a.out, a.err);
+            st_l2(a.out + p, acc);
+            if (a.clear) a.clear[p] = sent;
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
+// backward substitution:  z[l] = y[l] - sum_{f descending} (rD[l]*upper[f]) * z[upper(f)]
+__global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
+    const double sent = sentinel();
+    SWEEP_TASK_LOOP(a) {
+        const int2 next = SWEEP_NEXT_TASK(a);
+        if (lane < task.y) {
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
+            const double rd = a.rD[p];
+            const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
+            double acc = a.in[p];
+            acc = gather_deps<true, true>(acc, rd, j0, j1, a.col, a.val, a.out, a.err);
+            st_l2(a.out + p, acc);
+            if (a.clear) a.clear[p] = sent;
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
+// Gauss-Seidel sweep (GaussSeidelSmoother.C:151-176) in gather form:
+//   psi_new[c] = ( b'[c] - sum_{nbr faces asc} lower[f]*psi_new[l] - sum_{own faces asc} upper[f]*psi_old[u] ) / diag[c]
+__global__ void __launch_bounds__(256) k_gs_sweep(SweepArgs a) {
+    const double sent = sentinel();
+    SWEEP_TASK_LOOP(a) {
+        const int2 next = SWEEP_NEXT_TASK(a);
+        if (lane < task.y) {
+            const int p = task.x + lane;
+            const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
+            const int k0 = a.ptr2[p], k1 = a.ptr2[p + 1];
+            const double dg = a.diag[p];
+            double acc = a.in[p];
+            // owner-side products only need the old iterate: fetch them before waiting on anything
+            double up[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k0 + k < k1) up[k] = a.val2[k0 + k] * a.old[a.col2[k0 + k]];
+            acc = gather_deps<false, false>(acc, 1.0, j0, j1, a.col, a.val, a.out, a.err);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k0 + k < k1) acc -= up[k];
+            for (int k = k0 + 4; k < k1; k++) acc -= a.val2[k] * a.old[a.col2[k]];
+            st_l2(a.out + p, acc / dg);
+            if (a.clear) a.clear[p] = sent;
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Reductions: per-thread grid-stride partial -> warp shuffle -> shared memory -> one partial per block; the
+// last block to finish (atomic ticket) folds the partials in a fixed order.  Deterministic for a fixed grid.
+// ------------------------------------------------------------------------------------------------------------
+
+static constexpr int kReduceBlocks = 592;    // 4 per SM on 148 SMs
+static constexpr int kReduceThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-level sum of up to 2 values; returns true in the single thread that holds the grid totals.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials,
+                                            unsigned int* __restrict__ ticket) {
+    __shared__ double sm[NV][kReduceThreads / 32];
+    __shared__ bool isLast;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) sm[k][w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = lane < (blockDim.x >> 5) ? sm[k][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) partials[k * gridDim.x + blockIdx.x] = s;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return false;
+    __threadfence();
+    // fixed-order fold of the block partials by warp 0
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = 0.0;
+            for (int i = lane; i < gridDim.x; i += 32) s += ld_l2(partials + k * gridDim.x + i);
+            v[k] = warp_sum(s);
+        }
+        return lane == 0;
+    }
+    return false;
+}
+
+enum { RED_DOT = 0, RED_SUMMAG = 1, RED_SUM = 2, RED_SUMSQR = 3 };
+
+// out[0] = sum f(x, y)
+template <int OP>
+__global__ void __launch_bounds__(kReduceThreads)
+k_reduce(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ y, int n,
+         double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    double v[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (OP == RED_DOT) v[0] += x[i] * y[i];
+        if (OP == RED_SUMMAG) v[0] += fabs(x[i]);
+        if (OP == RED_SUM) v[0] += x[i];
+        if (OP == RED_SUMSQR) v[0] += x[i] * x[i];
+    }
+    if (grid_reduce<1>(v, partials, ticket)) out[0] = v[0];
+}
+
+// out[0] = sum x*y, out[1] = sum z*y   (GAMG scale: source.field, Acf.field ; PBiCGStab: tA.sA, tA.tA)
+__global__ void __launch_bounds__(kReduceThreads)
+k_dot2(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ z,
+       const double* __restrict__ y, int n, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    double v[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double yi = y[i];
+        v[0] += x[i] * yi;
+        v[1] += z[i] * yi;
+    }
+    if (grid_reduce<2>(v, partials, ticket)) {
+        out[0] = v[0];
+        out[1] = v[1];
+    }
+}
+
+// normFactor (lduMatrixSolver.C:174-197): out[0] = sum |Apsi - xbar*sumA| + |source - xbar*sumA|,
+// xbar = sumPsi[0]/nGlobal
+__global__ void __launch_bounds__(kReduceThreads)
+k_norm_factor(double* __restrict__ out, const double* __restrict__ Apsi, const double* __restrict__ source,
+              const double* __restrict__ sumA, const double* __restrict__ sumPsi, double nGlobal, int n,
+              double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    const double xbar = sumPsi[0] / nGlobal;
+    double v[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double t = sumA[i] * xbar;
+        v[0] += fabs(Apsi[i] - t) + fabs(source[i] - t);
+    }
+    if (grid_reduce<1>(v, partials, ticket)) out[0] = v[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PCG vector updates (PCG.C:142-179); scalars stay on the device
+// ------------------------------------------------------------------------------------------------------------
+
+// pA = wA + (wArA/wArAold)*pA       (first iteration: pA = wA)
+__global__ void k_pcg_update_p(double* __restrict__ pA, const double* __restrict__ wA,
+                               const double* __restrict__ wArA, const double* __restrict__ wArAold, int first,
+                               int n) {
+    if (first) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pA[i] = wA[i];
+        return;
+    }
+    const double beta = wArA[0] / wArAold[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        pA[i] = wA[i] + beta * pA[i];
+}
+
+// alpha = wArA/wApA ; psi += alpha*pA ; rA -= alpha*wA ; out = sum |rA|
+__global__ void __launch_bounds__(kReduceThreads)
+k_pcg_update_xr(double* __restrict__ psi, double* __restrict__ rA, const double* __restrict__ pA,
+                const double* __restrict__ wA, const double* __restrict__ wArA, const double* __restrict__ wApA,
+                double* __restrict__ out, int n, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    const double alpha = wArA[0] / wApA[0];
+    double v[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        psi[i] += alpha * pA[i];
+        const double r = rA[i] - alpha * wA[i];
+        rA[i] = r;
+        v[0] += fabs(r);
+    }
+    if (grid_reduce<1>(v, partials, ticket)) out[0] = v[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PBiCGStab vector updates (PBiCGStab.C:166-242)
+// ------------------------------------------------------------------------------------------------------------
+
+// pA = rA + beta*(pA - omega*AyA), beta = (rA0rA/rA0rAold)*(alpha/omega)
+__global__ void k_bicg_update_p(double* __restrict__ pA, const double* __restrict__ rA,
+                                const double* __restrict__ AyA, const double* __restrict__ S, int iRho,
+                                int iRhoOld, int iAlpha, int iOmega, int first, int n) {
+    if (first) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pA[i] = rA[i];
+        return;
+    }
+    const double omega = S[iOmega];
+    const double beta = (S[iRho] / S[iRhoOld]) * (S[iAlpha] / omega);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        pA[i] = rA[i] + beta * (pA[i] - omega * AyA[i]);
+}
+
+// alpha = rA0rA/rA0AyA ; sA = rA - alpha*AyA ; out = sum |sA| ; alphaOut = alpha
+__global__ void __launch_bounds__(kReduceThreads)
+k_bicg_update_s(double* __restrict__ sA, const double* __restrict__ rA, const double* __restrict__ AyA,
+                const double* __restrict__ rho, const double* __restrict__ rA0AyA, double* __restrict__ alphaOut,
+                double* __restrict__ out, int n, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    const double alpha = rho[0] / rA0AyA[0];
+    double v[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double s = rA[i] - alpha * AyA[i];
+        sA[i] = s;
+        v[0] += fabs(s);
+    }
+    if (grid_reduce<1>(v, partials, ticket)) {
+        out[0] = v[0];
+        alphaOut[0] = alpha;
+    }
+}
+
+// psi += alpha*yA   (early exit of PBiCGStab, PBiCGStab.C:213-216)
+__global__ void k_axpy_s(double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ a, int n) {
+    const double alpha = a[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += alpha * y[i];
+}
+
+// omega = tAsA/tAtA ; psi += alpha*yA + omega*zA ; rA = sA - omega*tA ; out = sum |rA|
+__global__ void __launch_bounds__(kReduceThreads)
+k_bicg_update_xr(double* __restrict__ psi, double* __restrict__ rA, const double* __restrict__ yA,
+                 const double* __restrict__ zA, const double* __restrict__ sA, const double* __restrict__ tA,
+                 const double* __restrict__ alphaP, const double* __restrict__ tAsA_tAtA,
+                 double* __restrict__ omegaOut, double* __restrict__ out, int n, double* __restrict__ partials,
+                 unsigned int* __restrict__ ticket) {
+    const double alpha = alphaP[0];
+    const double omega = tAsA_tAtA[0] / tAsA_tAtA[1];
+    double v[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        psi[i] += alpha * yA[i] + omega * zA[i];
+        const double r = sA[i] - omega * tA[i];
+        rA[i] = r;
+        v[0] += fabs(r);
+    }
+    if (grid_reduce<1>(v, partials, ticket)) {
+        out[0] = v[0];
+        omegaOut[0] = omega;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GAMG transfer operators and coarse-matrix assembly (all order-preserving gathers)
+// ------------------------------------------------------------------------------------------------------------
+
+// restrictField (GAMGAgglomerationTemplates.C:76-89): cf[c] = sum of ff over the fine cells of c, ascending
+__global__ void k_restrict(double* __restrict__ cf, const double* __restrict__ ff, const int* __restrict__ rPtr,
+                           const int* __restrict__ rFine, int nCoarse) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCoarse) return;
+    double acc = 0.0;
+    for (int k = rPtr[c]; k < rPtr[c + 1]; k++) acc += ff[rFine[k]];
+    cf[c] = acc;
+}
+
+// prolongField (:214-217): ff[i] = cf[map[i]]
+__global__ void k_prolong(double* __restrict__ ff, const double* __restrict__ cf, const int* __restrict__ pMap,
+                          int nFine) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nFine) ff[i] = cf[pMap[i]];
+}
+
+// coarse off-diagonal entry = sum of the referenced fine coefficients, ascending fine face
+// (GAMGSolverAgglomerateMatrix.C:142-190); fineVals = [Uval | Lval]
+__global__ void k_agglomerate_offdiag(double* __restrict__ cv, const double* __restrict__ fineVals,
+                                      const int* __restrict__ ptr, const int* __restrict__ src, int nEntries) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nEntries) return;
+    double acc = 0.0;
+    for (int k = ptr[j]; k < ptr[j + 1]; k++) acc += fineVals[src[k]];
+    cv[j] = acc;
+}
+
+// coarse diagonal = restrict(fine diag) then += upper+lower of every fine face interior to the coarse cell
+// (:61-69, :164, :188)
+__global__ void k_agglomerate_diag(double* __restrict__ cd, const double* __restrict__ fd,
+                                   const double* __restrict__ fU, const double* __restrict__ fL,
+                                   const int* __restrict__ rPtr, const int* __restrict__ rFine,
+                                   const int* __restrict__ dPtr, const int* __restrict__ dU,
+                                   const int* __restrict__ dL, int nCoarse) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCoarse) return;
+    double acc = 0.0;
+    for (int k = rPtr[c]; k < rPtr[c + 1]; k++) acc += fd[rFine[k]];
+    for (int k = dPtr[c]; k < dPtr[c + 1]; k++) acc += fU[dU[k]] + fL[dL[k]];
+    cd[c] = acc;
+}
+
+// GAMGSolver::scale second half (GAMGSolverScale.C:62-75):
+//   sf = num/stabilise(den, vSmall) ; field = sf*field + (source - sf*Acf)/D
+__global__ void k_gamg_scale(double* __restrict__ field, const double* __restrict__ source,
+                             const double* __restrict__ Acf, const double* __restrict__ D,
+                             const double* __restrict__ numDen, int n) {
+    const double den = numDen[1];
+    const double vSmall = 2.2250738585072014e-308;
+    const double sf = numDen[0] / (den >= 0 ? den + vSmall : den - vSmall);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        field[i] = sf * field[i] + (source[i] - sf * Acf[i]) / D[i];
+}
+
+}  // namespace b200ls

@@ -1,0 +1,464 @@
+// Host-side mesh analysis (integer data, built once per mesh).  See mesh.hpp.
+//
+// Reference behaviour restated here (paths under /root/reference/src/OpenFOAM/matrices/lduMatrix):
+//   lduAddressing/lduAddressing.C:32-170          losort / ownerStart / losortStart
+//   solvers/GAMG/GAMGAgglomerations/pairGAMGAgglomeration/pairGAMGAgglomerate.C:31-301
+//   solvers/GAMG/GAMGAgglomerations/GAMGAgglomeration/GAMGAgglomerateLduAddressing.C:32-353
+//   solvers/GAMG/GAMGAgglomerations/GAMGAgglomeration/GAMGAgglomeration.C:205-230
+//   solvers/GAMG/GAMGAgglomerations/GAMGAgglomeration/GAMGAgglomerationTemplates.C:137-167
+#include "mesh.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <stdexcept>
+
+namespace b200ls {
+
+namespace {
+
+// Stable bucket sort of items 0..n-1 by key[i] in [0, nKeys): offsets[nKeys+1], order[n]
+void bucketSort(const std::vector<int32_t>& key, int32_t nKeys, std::vector<int32_t>& offsets,
+                std::vector<int32_t>& order) {
+    const size_t n = key.size();
+    offsets.assign(size_t(nKeys) + 1, 0);
+    for (size_t i = 0; i < n; i++) offsets[size_t(key[i]) + 1]++;
+    for (int32_t k = 0; k < nKeys; k++) offsets[k + 1] += offsets[k];
+    order.resize(n);
+    std::vector<int32_t> cursor(offsets.begin(), offsets.end() - 1);
+    for (size_t i = 0; i < n; i++) order[cursor[key[i]]++] = int32_t(i);
+}
+
+void makeTasks(const std::vector<int32_t>& offsets, std::vector<SweepTask>& tasks) {
+    tasks.clear();
+    for (size_t k = 0; k + 1 < offsets.size(); k++) {
+        for (int32_t s = offsets[k]; s < offsets[k + 1]; s += 32) {
+            tasks.push_back({s, std::min<int32_t>(32, offsets[k + 1] - s)});
+        }
+    }
+}
+
+}  // namespace
+
+void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
+                std::vector<HostInterface> interfaces) {
+    if (nCells < 0 || nFaces < 0) throw std::runtime_error("negative mesh size");
+    L.nCells = nCells;
+    L.nFaces = nFaces;
+    L.lower.assign(lower, lower + nFaces);
+    L.upper.assign(upper, upper + nFaces);
+    for (int32_t f = 0; f < nFaces; f++) {
+        const int32_t l = lower[f], u = upper[f];
+        if (l < 0 || u >= nCells || l >= u) {
+            throw std::runtime_error("face " + std::to_string(f) + ": need 0 <= lower < upper < nCells");
+        }
+        if (f > 0 && lower[f - 1] > l) {
+            throw std::runtime_error("faces are not in upper-triangular (owner-sorted) order at face " +
+                                     std::to_string(f));
+        }
+    }
+
+    // losort: faces grouped by upper cell, ascending face index inside a group
+    std::vector<int32_t> nbrStart;   // proper CSR start of each losort group
+    bucketSort(L.upper, nCells, nbrStart, L.losort);
+
+    // ownerStart: number of faces whose owner is below the cell (faces are owner-sorted)
+    L.ownerStart.assign(size_t(nCells) + 1, 0);
+    for (int32_t f = 0; f < nFaces; f++) L.ownerStart[size_t(lower[f]) + 1]++;
+    for (int32_t c = 0; c < nCells; c++) L.ownerStart[c + 1] += L.ownerStart[c];
+
+    // losortStart as the reference leaves it: entries above the largest neighbour label are never
+    // written and stay 0 (lduAddressing.C:139-169), the last entry is nFaces
+    L.losortStart = nbrStart;
+    {
+        const int32_t maxNbr = nFaces ? L.upper[L.losort[nFaces - 1]] : -1;
+        for (int32_t c = std::max(maxNbr + 1, 0); c < nCells; c++) L.losortStart[c] = 0;
+        if (nFaces == 0) std::fill(L.losortStart.begin(), L.losortStart.end(), 0);
+        L.losortStart[nCells] = nFaces;
+    }
+
+    // canonical wavefront levels
+    std::vector<int32_t> lf(nCells, 0), lb(nCells, 0);
+    int32_t nFwd = nCells ? 1 : 0, nBwd = nCells ? 1 : 0;
+    for (int32_t f = 0; f < nFaces; f++) {
+        const int32_t v = lf[lower[f]] + 1;
+        if (v > lf[upper[f]]) lf[upper[f]] = v;
+    }
+    for (int32_t f = nFaces - 1; f >= 0; f--) {
+        const int32_t v = lb[upper[f]] + 1;
+        if (v > lb[lower[f]]) lb[lower[f]] = v;
+    }
+    for (int32_t c = 0; c < nCells; c++) {
+        nFwd = std::max(nFwd, lf[c] + 1);
+        nBwd = std::max(nBwd, lb[c] + 1);
+    }
+    bucketSort(lf, nFwd, L.fwdOffsets, L.fwdRows);
+    bucketSort(lb, nBwd, L.bwdOffsets, L.bwdRows);
+
+    // native layout: position = rank in forward-wavefront-major order
+    L.perm = L.fwdRows;
+    L.ipos.resize(nCells);
+    for (int32_t p = 0; p < nCells; p++) L.ipos[L.perm[p]] = p;
+
+    L.Lptr.assign(size_t(nCells) + 1, 0);
+    L.Uptr.assign(size_t(nCells) + 1, 0);
+    for (int32_t p = 0; p < nCells; p++) {
+        const int32_t c = L.perm[p];
+        L.Lptr[p + 1] = L.Lptr[p] + (nbrStart[c + 1] - nbrStart[c]);
+        L.Uptr[p + 1] = L.Uptr[p] + (L.ownerStart[c + 1] - L.ownerStart[c]);
+    }
+    L.Lcol.resize(nFaces);
+    L.Lface.resize(nFaces);
+    L.Lidx.resize(nFaces);
+    L.Ucol.resize(nFaces);
+    L.Uface.resize(nFaces);
+    L.Uidx.resize(nFaces);
+    for (int32_t p = 0; p < nCells; p++) {
+        const int32_t c = L.perm[p];
+        int32_t j = L.Lptr[p];
+        for (int32_t k = nbrStart[c]; k < nbrStart[c + 1]; k++, j++) {
+            const int32_t f = L.losort[k];
+            L.Lcol[j] = L.ipos[lower[f]];
+            L.Lface[j] = f;
+            L.Lidx[f] = j;
+        }
+        j = L.Uptr[p];
+        for (int32_t f = L.ownerStart[c]; f < L.ownerStart[c + 1]; f++, j++) {
+            L.Ucol[j] = L.ipos[upper[f]];
+            L.Uface[j] = f;
+            L.Uidx[f] = j;
+        }
+    }
+
+    makeTasks(L.fwdOffsets, L.fwdTasks);
+
+    // backward processing order: by backward level, ascending position inside a level
+    {
+        std::vector<int32_t> lbByPos(nCells);
+        for (int32_t p = 0; p < nCells; p++) lbByPos[p] = lb[L.perm[p]];
+        std::vector<int32_t> offs;
+        bucketSort(lbByPos, nBwd, offs, L.bwdPos);
+        makeTasks(offs, L.bwdTasks);
+        // structured meshes: the backward order is the forward order walked level by level from the end;
+        // record whether it is a pure reversal of level blocks with ascending positions inside (always true
+        // by construction) and whether bwdPos is affine so kernels may skip the indirection
+        L.bwdIsReverse = false;
+    }
+
+    // interfaces and the rows they touch
+    L.interfaces = std::move(interfaces);
+    {
+        std::vector<int32_t> cellOf, ifaceOf, faceOf;
+        for (size_t i = 0; i < L.interfaces.size(); i++) {
+            const auto& fc = L.interfaces[i].faceCells;
+            for (size_t k = 0; k < fc.size(); k++) {
+                if (fc[k] < 0 || fc[k] >= nCells) throw std::runtime_error("interface faceCells out of range");
+                cellOf.push_back(fc[k]);
+                ifaceOf.push_back(int32_t(i));
+                faceOf.push_back(int32_t(k));
+            }
+        }
+        std::vector<int32_t> order(cellOf.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int32_t a, int32_t b) { return L.ipos[cellOf[a]] < L.ipos[cellOf[b]]; });
+        L.bRowPos.clear();
+        L.bRowPtr.assign(1, 0);
+        L.bEntryIface.clear();
+        L.bEntryFace.clear();
+        for (size_t k = 0; k < order.size(); k++) {
+            const int32_t e = order[k];
+            const int32_t pos = L.ipos[cellOf[e]];
+            if (L.bRowPos.empty() || L.bRowPos.back() != pos) {
+                if (!L.bRowPos.empty()) L.bRowPtr.push_back(int32_t(L.bEntryIface.size()));
+                L.bRowPos.push_back(pos);
+            }
+            L.bEntryIface.push_back(ifaceOf[e]);
+            L.bEntryFace.push_back(faceOf[e]);
+        }
+        if (!L.bRowPos.empty()) L.bRowPtr.push_back(int32_t(L.bEntryIface.size()));
+    }
+}
+
+std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fine,
+                                     const std::vector<double>& w, bool& forward) {
+    const int32_t n = fine.nCells;
+    const int32_t nF = fine.nFaces;
+    const int32_t* up = fine.upper.data();
+    const int32_t* lo = fine.lower.data();
+
+    // faces of a cell in the reference's visiting order: neighbour-side faces (ascending), then
+    // owner-side faces (ascending)  (pairGAMGAgglomerate.C:139-181)
+    std::vector<int32_t> nbrStart(size_t(n) + 1, 0);
+    for (int32_t f = 0; f < nF; f++) nbrStart[size_t(up[f]) + 1]++;
+    for (int32_t c = 0; c < n; c++) nbrStart[c + 1] += nbrStart[c];
+
+    std::vector<int32_t> map(n, -1);
+    nCoarseCells = 0;
+    const double minusGreat = -1.0e+15;   // -great (reference primitives/Scalar/doubleScalar: great = 1e+15)
+
+    auto visit = [&](int32_t c) { return forward ? c : n - 1 - c; };
+
+    for (int32_t ci = 0; ci < n; ci++) {
+        const int32_t c = visit(ci);
+        if (map[c] >= 0) continue;
+
+        int32_t match = -1;
+        double best = minusGreat;
+        for (int32_t k = nbrStart[c]; k < nbrStart[c + 1]; k++) {
+            const int32_t f = fine.losort[k];
+            if (map[up[f]] < 0 && map[lo[f]] < 0 && w[f] > best) {
+                match = f;
+                best = w[f];
+            }
+        }
+        for (int32_t f = fine.ownerStart[c]; f < fine.ownerStart[c + 1]; f++) {
+            if (map[up[f]] < 0 && map[lo[f]] < 0 && w[f] > best) {
+                match = f;
+                best = w[f];
+            }
+        }
+
+        if (match >= 0) {
+            map[up[match]] = nCoarseCells;
+            map[lo[match]] = nCoarseCells;
+            nCoarseCells++;
+            continue;
+        }
+
+        // no free neighbour: join the cluster across the heaviest face
+        int32_t join = -1;
+        best = minusGreat;
+        for (int32_t k = nbrStart[c]; k < nbrStart[c + 1]; k++) {
+            const int32_t f = fine.losort[k];
+            if (w[f] > best) {
+                join = f;
+                best = w[f];
+            }
+        }
+        for (int32_t f = fine.ownerStart[c]; f < fine.ownerStart[c + 1]; f++) {
+            if (w[f] > best) {
+                join = f;
+                best = w[f];
+            }
+        }
+        if (join >= 0) map[c] = std::max(map[up[join]], map[lo[join]]);
+    }
+
+    // isolated cells become single-cell clusters, same visiting order
+    for (int32_t ci = 0; ci < n; ci++) {
+        const int32_t c = visit(ci);
+        if (map[c] < 0) map[c] = nCoarseCells++;
+    }
+
+    if (!forward) {
+        const int32_t last = nCoarseCells - 1;
+        for (int32_t c = 0; c < n; c++) map[c] = last - map[c];
+    }
+    forward = !forward;
+    return map;
+}
+
+namespace {
+
+// GAMGAgglomeration::agglomerateLduAddressing for one level: fills fine.faceRestrictAddr/faceFlip and
+// returns the coarse lower/upper addressing.
+void agglomerateAddressing(LevelHost& fine, std::vector<int32_t>& cLower, std::vector<int32_t>& cUpper) {
+    const int32_t nF = fine.nFaces;
+    const int32_t nC = fine.nCoarseCells;
+    const std::vector<int32_t>& rm = fine.restrictAddr;
+
+    fine.faceRestrictAddr.resize(nF);
+    fine.faceFlip.assign(nF, 0);
+
+    // per coarse owner: singly linked list of its provisional coarse faces, in creation order
+    std::vector<int32_t> head(nC, -1), tail(nC, -1);
+    std::vector<int32_t> next, nei, own;
+    next.reserve(nF / 2);
+    nei.reserve(nF / 2);
+    own.reserve(nF / 2);
+
+    for (int32_t f = 0; f < nF; f++) {
+        const int32_t ru = rm[fine.upper[f]];
+        const int32_t rl = rm[fine.lower[f]];
+        if (ru == rl) {
+            fine.faceRestrictAddr[f] = -(ru + 1);
+            continue;
+        }
+        const int32_t cOwn = std::min(ru, rl), cNei = std::max(ru, rl);
+        int32_t found = -1;
+        for (int32_t e = head[cOwn]; e >= 0; e = next[e]) {
+            if (nei[e] == cNei) {
+                found = e;
+                break;
+            }
+        }
+        if (found < 0) {
+            found = int32_t(nei.size());
+            nei.push_back(cNei);
+            own.push_back(cOwn);
+            next.push_back(-1);
+            if (tail[cOwn] >= 0) next[tail[cOwn]] = found;
+            else head[cOwn] = found;
+            tail[cOwn] = found;
+        }
+        fine.faceRestrictAddr[f] = found;
+    }
+
+    // renumber into owner-major order, creation order inside an owner
+    const int32_t nCF = int32_t(nei.size());
+    fine.nCoarseFaces = nCF;
+    std::vector<int32_t> renum(nCF);
+    cLower.resize(nCF);
+    cUpper.resize(nCF);
+    int32_t k = 0;
+    for (int32_t c = 0; c < nC; c++) {
+        for (int32_t e = head[c]; e >= 0; e = next[e]) {
+            cLower[k] = c;
+            cUpper[k] = nei[e];
+            renum[e] = k++;
+        }
+    }
+    for (int32_t f = 0; f < nF; f++) {
+        int32_t& cf = fine.faceRestrictAddr[f];
+        if (cf >= 0) {
+            cf = renum[cf];
+            // flipped when the fine neighbour side maps to the coarse owner
+            fine.faceFlip[f] = (rm[fine.upper[f]] == cLower[cf]) ? 1 : 0;
+        }
+    }
+}
+
+void buildMaps(LevelHost& fine, const LevelHost& coarse) {
+    AgglomMaps& M = fine.maps;
+    const int32_t nCf = fine.nCells, nCc = coarse.nCells;
+    const int32_t nFf = fine.nFaces, nFc = coarse.nFaces;
+
+    // restrict: coarse position -> fine positions in ascending fine cell order
+    M.rPtr.assign(size_t(nCc) + 1, 0);
+    for (int32_t c = 0; c < nCf; c++) M.rPtr[size_t(coarse.ipos[fine.restrictAddr[c]]) + 1]++;
+    for (int32_t p = 0; p < nCc; p++) M.rPtr[p + 1] += M.rPtr[p];
+    M.rFine.resize(nCf);
+    {
+        std::vector<int32_t> cur(M.rPtr.begin(), M.rPtr.end() - 1);
+        for (int32_t c = 0; c < nCf; c++) M.rFine[cur[coarse.ipos[fine.restrictAddr[c]]]++] = fine.ipos[c];
+    }
+    M.pMap.resize(nCf);
+    for (int32_t p = 0; p < nCf; p++) M.pMap[p] = coarse.ipos[fine.restrictAddr[fine.perm[p]]];
+
+    // coarse off-diagonals: for each coarse U / L entry the fine value refs, ascending fine face
+    M.uPtr.assign(size_t(nFc) + 1, 0);
+    M.lPtr.assign(size_t(nFc) + 1, 0);
+    M.dPtr.assign(size_t(nCc) + 1, 0);
+    for (int32_t f = 0; f < nFf; f++) {
+        const int32_t cf = fine.faceRestrictAddr[f];
+        if (cf >= 0) {
+            M.uPtr[size_t(coarse.Uidx[cf]) + 1]++;
+            M.lPtr[size_t(coarse.Lidx[cf]) + 1]++;
+        } else {
+            M.dPtr[size_t(coarse.ipos[-1 - cf]) + 1]++;
+        }
+    }
+    for (int32_t j = 0; j < nFc; j++) {
+        M.uPtr[j + 1] += M.uPtr[j];
+        M.lPtr[j + 1] += M.lPtr[j];
+    }
+    for (int32_t p = 0; p < nCc; p++) M.dPtr[p + 1] += M.dPtr[p];
+    M.uSrc.resize(M.uPtr[nFc]);
+    M.lSrc.resize(M.lPtr[nFc]);
+    M.dU.resize(M.dPtr[nCc]);
+    M.dL.resize(M.dPtr[nCc]);
+    {
+        std::vector<int32_t> cu(M.uPtr.begin(), M.uPtr.end() - 1), cl(M.lPtr.begin(), M.lPtr.end() - 1),
+            cd(M.dPtr.begin(), M.dPtr.end() - 1);
+        for (int32_t f = 0; f < nFf; f++) {
+            const int32_t cf = fine.faceRestrictAddr[f];
+            const int32_t uRef = fine.Uidx[f];            // fine upper[f]
+            const int32_t lRef = nFf + fine.Lidx[f];      // fine lower[f]
+            if (cf >= 0) {
+                const bool flip = fine.faceFlip[f] != 0;
+                M.uSrc[cu[coarse.Uidx[cf]]++] = flip ? lRef : uRef;
+                M.lSrc[cl[coarse.Lidx[cf]]++] = flip ? uRef : lRef;
+            } else {
+                const int32_t p = coarse.ipos[-1 - cf];
+                M.dU[cd[p]] = fine.Uidx[f];
+                M.dL[cd[p]] = fine.Lidx[f];
+                cd[p]++;
+            }
+        }
+    }
+
+    // interface coefficients: coarse patch face -> fine patch faces (ascending)
+    const size_t nI = fine.interfaces.size();
+    M.iPtr.assign(nI, {});
+    M.iSrc.assign(nI, {});
+    for (size_t i = 0; i < nI; i++) {
+        const auto& pr = fine.patchFaceRestrictAddr[i];
+        const int32_t nCoarsePatch = int32_t(coarse.interfaces[i].faceCells.size());
+        std::vector<int32_t> key(pr.begin(), pr.end());
+        bucketSort(key, nCoarsePatch, M.iPtr[i], M.iSrc[i]);
+    }
+}
+
+}  // namespace
+
+int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
+                bool& forward) {
+    if (mergeLevels != 1) throw std::runtime_error("mergeLevels != 1 is not supported");
+    if (mesh.nRanks != 1 && !mesh.levels[0].interfaces.empty()) {
+        // multi-rank agglomeration needs the neighbour restrictMap exchange; see capi multi-rank path
+    }
+    mesh.levels.resize(1);
+    mesh.levels[0].hasCoarse = false;
+    mesh.agglomerated = false;
+
+    const int32_t maxLevels = 50;   // GAMGAgglomeration.C:248
+    std::vector<double> w(faceWeights, faceWeights + mesh.levels[0].nFaces);
+
+    int nCreated = 0;
+    while (nCreated < maxLevels - 1) {
+        LevelHost& fine = mesh.levels[nCreated];
+        int32_t nCoarse = -1;
+        std::vector<int32_t> map = pairAgglomerate(nCoarse, fine, w, forward);
+
+        // continueAgglomerating (single rank: global sums are local values)
+        const int64_t totalCoarse = nCoarse;
+        const int64_t totalFine = fine.nCells;
+        if (totalCoarse < int64_t(mesh.nRanks) * minCellsPerProcessor || !(totalCoarse < totalFine)) break;
+
+        fine.hasCoarse = true;
+        fine.nCoarseCells = nCoarse;
+        fine.restrictAddr = std::move(map);
+
+        std::vector<int32_t> cLower, cUpper;
+        agglomerateAddressing(fine, cLower, cUpper);
+
+        // coarse interfaces: single-rank meshes have none
+        std::vector<HostInterface> coarseIfaces;
+        fine.patchFaceRestrictAddr.assign(fine.interfaces.size(), {});
+        if (!fine.interfaces.empty()) {
+            throw std::runtime_error("agglomeration with processor interfaces needs b200ls_agglomerate_parallel");
+        }
+
+        mesh.levels.emplace_back();
+        LevelHost& fineRef = mesh.levels[nCreated];   // emplace_back may have moved the storage
+        LevelHost& coarse = mesh.levels[nCreated + 1];
+        buildLevel(coarse, nCoarse, int32_t(cLower.size()), cLower.data(), cUpper.data(), std::move(coarseIfaces));
+
+        // restrictFaceField of the weights for the next level (sequential adds in fine-face order)
+        std::vector<double> cw(coarse.nFaces, 0.0);
+        for (int32_t f = 0; f < fineRef.nFaces; f++) {
+            const int32_t cf = fineRef.faceRestrictAddr[f];
+            if (cf >= 0) cw[cf] += w[f];
+        }
+        w.swap(cw);
+
+        buildMaps(fineRef, coarse);
+        nCreated++;
+    }
+    mesh.agglomerated = true;
+    return nCreated;
+}
+
+}  // namespace b200ls

@@ -1,0 +1,88 @@
+// Host-side mesh analysis for libb200ls: everything that is integer data and built once per
+// mesh (SURVEY.md 8(a) rows a5, a17, a18 + the canonical wavefront definition).
+//
+// No CUDA in this translation unit: it is exercised on CPU-only machines through
+// b200ls_mesh_create / b200ls_agglomerate / b200ls_mesh_get_i32.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200ls {
+
+struct HostInterface {
+    int32_t neighbRank = -1;
+    std::vector<int32_t> faceCells;      // reference cell index of each patch face
+};
+
+// One (start, count<=32) slice of a wavefront: the unit of work of one warp in the sweep kernels.
+struct SweepTask {
+    int32_t start;
+    int32_t count;
+};
+
+// Native-space maps from one level to the next coarser one (device gathers, all order-preserving).
+struct AgglomMaps {
+    // restrictField: coarse position -> fine positions, ascending FINE CELL index
+    std::vector<int32_t> rPtr, rFine;
+    // prolongField: fine position -> coarse position
+    std::vector<int32_t> pMap;
+    // agglomerateMatrix: coarse U/L entry -> fine value refs (ascending fine face index);
+    // ref r < nFineFaces selects fine Uval[r], otherwise fine Lval[r - nFineFaces]
+    std::vector<int32_t> uPtr, uSrc, lPtr, lSrc;
+    // fine faces interior to a coarse cell, by coarse position (ascending fine face): Uval + Lval entry
+    std::vector<int32_t> dPtr, dU, dL;
+    // interface coefficient restriction, per interface: coarse patch face -> fine patch faces
+    std::vector<std::vector<int32_t>> iPtr, iSrc;
+};
+
+struct LevelHost {
+    int32_t nCells = 0, nFaces = 0;
+    std::vector<int32_t> lower, upper;                      // reference face order
+    std::vector<int32_t> losort, ownerStart, losortStart;   // reference-exact (lduAddressing.C:32-170)
+    std::vector<int32_t> fwdOffsets, fwdRows, bwdOffsets, bwdRows;   // canonical wavefronts (cells)
+
+    // ---- native layout: rows in forward-wavefront-major order ("positions") ----
+    std::vector<int32_t> perm;      // position -> cell
+    std::vector<int32_t> ipos;      // cell -> position
+    std::vector<int32_t> Lptr, Lcol, Lface;   // neighbour-side entries of each row (ascending face)
+    std::vector<int32_t> Uptr, Ucol, Uface;   // owner-side entries of each row (ascending face)
+    std::vector<int32_t> Lidx, Uidx;          // face -> entry index in the L / U arrays
+    std::vector<SweepTask> fwdTasks, bwdTasks;
+    std::vector<int32_t> bwdPos;    // backward processing order -> position
+    bool bwdIsReverse = false;      // bwdPos[q] == nCells-1-q (structured meshes)
+
+    std::vector<HostInterface> interfaces;
+    // rows touched by interfaces: boundary-row CSR in (patch, face) order
+    std::vector<int32_t> bRowPos, bRowPtr, bEntryIface, bEntryFace;
+
+    // ---- agglomeration to the next level (empty on the coarsest) ----
+    bool hasCoarse = false;
+    int32_t nCoarseCells = 0, nCoarseFaces = 0;
+    std::vector<int32_t> restrictAddr, faceRestrictAddr, faceFlip;
+    std::vector<std::vector<int32_t>> patchFaceRestrictAddr;   // per interface
+    AgglomMaps maps;
+};
+
+struct HostMesh {
+    std::vector<LevelHost> levels;      // [0] = finest
+    bool agglomerated = false;
+    int nRanks = 1, rank = 0;
+};
+
+// Throws std::runtime_error on invalid input (not upper-triangular ordered, out-of-range labels).
+void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
+                std::vector<HostInterface> interfaces);
+
+// pairGAMGAgglomeration::agglomerate(nCoarseCells, addressing, weights) (pairGAMGAgglomerate.C:123-301).
+// `forward` is the reference's static forward_ flag: read, used, and toggled.
+std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fine,
+                                     const std::vector<double>& faceWeights, bool& forward);
+
+// Whole level loop of pairGAMGAgglomeration::agglomerate(mesh, weights) (pairGAMGAgglomerate.C:31-118)
+// with continueAgglomerating (GAMGAgglomeration.C:205-230).  Returns number of coarse levels.
+int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
+                bool& forward);
+
+}  // namespace b200ls

@@ -1,0 +1,1268 @@
+// Solver drivers of libb200ls: matrix upload, SpMV family, DIC/DILU, smoothers, PCG, PBiCGStab, GAMG.
+//
+// Reference algorithms (paths under /root/reference/src/OpenFOAM/matrices/lduMatrix):
+//   solvers/PCG/PCG.C:65-193, solvers/PBiCGStab/PBiCGStab.C:68-254, solvers/smoothSolver/smoothSolver.C:77-193
+//   solvers/GAMG/GAMGSolverSolve.C:31-552, GAMGSolverScale.C:31-76, GAMGSolverAgglomerateMatrix.C:33-270
+//   lduMatrix/lduMatrixSolver.C:174-197 (normFactor), LduMatrix/LduMatrix/SolverPerformance.C:32-92
+#include "solver.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace b200ls {
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+
+Context& ctx() {
+    static Context c;
+    return c;
+}
+
+void ensureInit() {
+    Context& c = ctx();
+    if (c.initialised) return;
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0) {
+        throw CudaError("no CUDA device available: libb200ls has no CPU fallback (" +
+                        std::string(cudaGetErrorString(e)) + ")");
+    }
+    B2_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    c.numSMs = prop.multiProcessorCount;
+    B2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.partials.alloc(4 * kReduceBlocks);
+    c.ticket.alloc(1);
+    c.errFlag.alloc(1);
+    B2_CUDA(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned int), c.stream));
+    B2_CUDA(cudaMemsetAsync(c.errFlag.p, 0, sizeof(int), c.stream));
+    B2_CUDA(cudaMallocHost(&c.pinned, 64 * sizeof(double)));
+    if (const char* s = getenv("B200LS_SWEEP_BLOCKS_PER_SM")) c.sweepBlocksPerSM = atoi(s);
+    c.initialised = true;
+}
+
+static inline cudaStream_t S() { return ctx().stream; }
+
+static inline int gridStride(int n) {
+    const int b = (n + 255) / 256;
+    return std::max(1, std::min(b, ctx().numSMs * 8));
+}
+static inline int gridRows(int n) { return std::max(1, (n + 255) / 256); }
+
+#define LAUNCH(kernel, grid, block, ...)                  \
+    do {                                                  \
+        kernel<<<(grid), (block), 0, S()>>>(__VA_ARGS__); \
+        ctx().launches++;                                 \
+    } while (0)
+
+static void checkLaunch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class K>
+static void launchSweep(K kernel, SweepArgs& a) {
+    if (a.nTasks == 0) return;
+    static std::map<const void*, int> occCache;
+    Context& c = ctx();
+    int occ;
+    auto it = occCache.find((const void*)kernel);
+    if (it == occCache.end()) {
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
+        occCache[(const void*)kernel] = occ;
+    } else {
+        occ = it->second;
+    }
+    // look-ahead of ~4 CTAs per SM hides the static-load latency; more only adds polling traffic (measured)
+    occ = std::min(occ, c.sweepBlocksPerSM > 0 ? c.sweepBlocksPerSM : 4);
+    const int blocks = std::max(1, std::min(occ * c.numSMs, (a.nTasks + 7) / 8));
+    a.err = c.errFlag.p;
+    void* args[] = {&a};
+    B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(256), args, 0, c.stream));
+    c.launches++;
+}
+
+void checkSweepError() {
+    Context& c = ctx();
+    int h = 0;
+    B2_CUDA(cudaMemcpyAsync(&h, c.errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    if (h) {
+        B2_CUDA(cudaMemsetAsync(c.errFlag.p, 0, sizeof(int), c.stream));
+        throw CudaError("wavefront sweep timed out waiting for a dependency (internal error)");
+    }
+}
+
+static void readScalars(const double* dev, int n) {
+    B2_CUDA(cudaMemcpyAsync(ctx().pinned, dev, n * sizeof(double), cudaMemcpyDeviceToHost, S()));
+    B2_CUDA(cudaStreamSynchronize(S()));
+}
+
+// sum over ranks of `count` device doubles (gSum*/reduce(sumOp), allReduceTemplates.C:157)
+static void allReduce(double* dev, int count) {
+    Context& c = ctx();
+    if (c.nRanks == 1) return;
+    int r = c.nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, c.comm, c.stream);
+    if (r != 0) throw CudaError(std::string("ncclAllReduce: ") + c.nccl.GetErrorString((ncclResult_t)r));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device mesh
+// ------------------------------------------------------------------------------------------------------------
+
+static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
+    cudaStream_t s = S();
+    D.nCells = H.nCells;
+    D.nFaces = H.nFaces;
+    D.perm.upload(H.perm, s);
+    D.ipos.upload(H.ipos, s);
+    D.Lptr.upload(H.Lptr, s);
+    D.Lcol.upload(H.Lcol, s);
+    D.Lface.upload(H.Lface, s);
+    D.Uptr.upload(H.Uptr, s);
+    D.Ucol.upload(H.Ucol, s);
+    D.Uface.upload(H.Uface, s);
+    {
+        std::vector<int32_t> ltou(H.nFaces);
+        for (int32_t j = 0; j < H.nFaces; j++) ltou[j] = H.Uidx[H.Lface[j]];
+        D.LtoU.upload(ltou, s);
+        B2_CUDA(cudaStreamSynchronize(s));   // ltou is a temporary
+    }
+    static_assert(sizeof(SweepTask) == sizeof(int2), "task layout");
+    D.nFwdTasks = int(H.fwdTasks.size());
+    D.nBwdTasks = int(H.bwdTasks.size());
+    D.fwdTasks.alloc(H.fwdTasks.size());
+    D.bwdTasks.alloc(H.bwdTasks.size());
+    if (D.nFwdTasks)
+        B2_CUDA(cudaMemcpyAsync(D.fwdTasks.p, H.fwdTasks.data(), H.fwdTasks.size() * sizeof(int2),
+                                cudaMemcpyHostToDevice, s));
+    if (D.nBwdTasks)
+        B2_CUDA(cudaMemcpyAsync(D.bwdTasks.p, H.bwdTasks.data(), H.bwdTasks.size() * sizeof(int2),
+                                cudaMemcpyHostToDevice, s));
+    D.bwdPos.upload(H.bwdPos, s);
+
+    D.nIfaces = int(H.interfaces.size());
+    D.ifaceSize.clear();
+    D.ifaceNbr.clear();
+    D.ifaceCellsPos.clear();
+    D.ifaceCellsPos.resize(D.nIfaces);
+    for (int i = 0; i < D.nIfaces; i++) {
+        const auto& fc = H.interfaces[i].faceCells;
+        D.ifaceSize.push_back(int(fc.size()));
+        D.ifaceNbr.push_back(H.interfaces[i].neighbRank);
+        std::vector<int32_t> pos(fc.size());
+        for (size_t k = 0; k < fc.size(); k++) pos[k] = H.ipos[fc[k]];
+        D.ifaceCellsPos[i].upload(pos, s);
+        B2_CUDA(cudaStreamSynchronize(s));
+    }
+    D.nBRows = int(H.bRowPos.size());
+    D.bRowPos.upload(H.bRowPos, s);
+    D.bRowPtr.upload(H.bRowPtr, s);
+    D.bEntIface.upload(H.bEntryIface, s);
+    D.bEntFace.upload(H.bEntryFace, s);
+
+    D.hasCoarse = H.hasCoarse;
+    if (H.hasCoarse) {
+        const AgglomMaps& M = H.maps;
+        D.rPtr.upload(M.rPtr, s);
+        D.rFine.upload(M.rFine, s);
+        D.pMap.upload(M.pMap, s);
+        D.auPtr.upload(M.uPtr, s);
+        D.auSrc.upload(M.uSrc, s);
+        D.alPtr.upload(M.lPtr, s);
+        D.alSrc.upload(M.lSrc, s);
+        D.adPtr.upload(M.dPtr, s);
+        D.adU.upload(M.dU, s);
+        D.adL.upload(M.dL, s);
+        D.aiPtr.clear();
+        D.aiSrc.clear();
+        D.aiPtr.resize(M.iPtr.size());
+        D.aiSrc.resize(M.iSrc.size());
+        for (size_t i = 0; i < M.iPtr.size(); i++) {
+            D.aiPtr[i].upload(M.iPtr[i], s);
+            D.aiSrc[i].upload(M.iSrc[i], s);
+        }
+    }
+    if (coarsest) {
+        D.refLower.upload(H.lower, s);
+        D.refUpper.upload(H.upper, s);
+        D.Uidx.upload(H.Uidx, s);
+        D.Lidx.upload(H.Lidx, s);
+    }
+    B2_CUDA(cudaStreamSynchronize(s));
+}
+
+void ensureDeviceMesh(b200ls_mesh_s* mesh) {
+    ensureInit();
+    if (mesh->dev) return;
+    mesh->dev.reset(new DeviceMesh);
+    const size_t nL = mesh->host.levels.size();
+    for (size_t k = 0; k < nL; k++) {
+        mesh->dev->levels.emplace_back(new DevLevel);
+        uploadLevel(*mesh->dev->levels.back(), mesh->host.levels[k], k + 1 == nL);
+    }
+}
+
+}  // namespace b200ls
+
+double* b200ls_matrix_s::vec(const std::string& name) {
+    b200ls::Vec& v = vecs[name];
+    const size_t n = mesh->host.levels[0].nCells;
+    if (v.buf.n != n || !v.buf.p) v.buf.alloc(n);
+    return v.buf.p;
+}
+
+namespace b200ls {
+
+static DevLevel& DL(b200ls_matrix_s* m, int level) { return *m->mesh->dev->levels[level]; }
+
+void toPositions(b200ls_matrix_s* m, int level, double* outPos, const double* inCell) {
+    DevLevel& D = DL(m, level);
+    if (D.nCells) LAUNCH(k_gather, gridStride(D.nCells), 256, outPos, inCell, D.perm.p, D.nCells);
+}
+void toCells(b200ls_matrix_s* m, int level, double* outCell, const double* inPos) {
+    DevLevel& D = DL(m, level);
+    if (D.nCells) LAUNCH(k_gather, gridStride(D.nCells), 256, outCell, inPos, D.ipos.p, D.nCells);
+}
+
+static void syncMatrixWithMesh(b200ls_matrix_s* m) {
+    ensureDeviceMesh(m->mesh);
+    if (m->meshGeneration != m->mesh->generation || m->levels.size() != m->mesh->dev->levels.size()) {
+        m->levels.clear();
+        m->levels.resize(m->mesh->dev->levels.size());
+        m->meshGeneration = m->mesh->generation;
+        m->coarseValid = false;
+        m->valuesSet = false;
+    }
+}
+
+static void setupIfaceViews(b200ls_matrix_s* m, int level) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (D.nIfaces == 0) return;
+    std::vector<IfaceView> v(D.nIfaces);
+    for (int i = 0; i < D.nIfaces; i++) {
+        M.sendBuf[i].alloc(D.ifaceSize[i]);
+        M.recvBuf[i].alloc(D.ifaceSize[i]);
+        v[i].coeffs = M.bou[i].p;
+        v[i].recv = M.recvBuf[i].p;
+    }
+    M.ifaceViews.alloc(v.size() * sizeof(IfaceView));
+    B2_CUDA(cudaMemcpyAsync(M.ifaceViews.p, v.data(), v.size() * sizeof(IfaceView), cudaMemcpyHostToDevice, S()));
+    B2_CUDA(cudaStreamSynchronize(S()));
+}
+
+void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, const double* lower,
+               const double* const* bou, const double* const* inn) {
+    syncMatrixWithMesh(m);
+    DevLevel& D = DL(m, 0);
+    MatLevel& M = m->levels[0];
+    const int nC = D.nCells, nF = D.nFaces;
+    m->symmetric = (lower == nullptr);
+    m->stageA.alloc(std::max(nC, nF));
+    M.diag.alloc(nC);
+    M.vals.alloc(size_t(2) * nF);
+    cudaStream_t s = S();
+    if (nC) {
+        B2_CUDA(cudaMemcpyAsync(m->stageA.p, diag, sizeof(double) * nC, cudaMemcpyHostToDevice, s));
+        LAUNCH(k_gather, gridStride(nC), 256, M.diag.p, m->stageA.p, D.perm.p, nC);
+    }
+    if (nF) {
+        B2_CUDA(cudaMemcpyAsync(m->stageA.p, upper, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+        LAUNCH(k_gather, gridStride(nF), 256, M.Uval(), m->stageA.p, D.Uface.p, nF);
+        if (lower) {
+            m->stageB.alloc(std::max(nC, nF));
+            B2_CUDA(cudaMemcpyAsync(m->stageB.p, lower, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), m->stageB.p, D.Lface.p, nF);
+        } else {
+            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), m->stageA.p, D.Lface.p, nF);
+        }
+    }
+    M.bou.resize(D.nIfaces);
+    M.inn.resize(D.nIfaces);
+    M.sendBuf.resize(D.nIfaces);
+    M.recvBuf.resize(D.nIfaces);
+    for (int i = 0; i < D.nIfaces; i++) {
+        M.bou[i].alloc(D.ifaceSize[i]);
+        M.inn[i].alloc(D.ifaceSize[i]);
+        if (D.ifaceSize[i]) {
+            B2_CUDA(cudaMemcpyAsync(M.bou[i].p, bou[i], sizeof(double) * D.ifaceSize[i], cudaMemcpyHostToDevice, s));
+            B2_CUDA(cudaMemcpyAsync(M.inn[i].p, inn[i], sizeof(double) * D.ifaceSize[i], cudaMemcpyHostToDevice, s));
+        }
+    }
+    setupIfaceViews(m, 0);
+    B2_CUDA(cudaStreamSynchronize(s));
+    checkLaunch("matrixSet");
+    for (auto& L : m->levels) L.rDValid = false;
+    m->coarseValid = false;
+    m->valuesSet = true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// halo exchange (initMatrixInterfaces/updateMatrixInterfaces, lduMatrixUpdateMatrixInterfaces.C:30-266;
+// processorFvPatchScalarField.C:36-152): pack -> ncclSend/ncclRecv group -> ordered apply
+// ------------------------------------------------------------------------------------------------------------
+
+static void haloExchange(b200ls_matrix_s* m, int level, const double* psi) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    Context& c = ctx();
+    if (D.nIfaces == 0) return;
+    if (c.nRanks == 1) throw CudaError("matrix has processor interfaces but b200ls_init was called with nRanks=1");
+    for (int i = 0; i < D.nIfaces; i++) {
+        if (D.ifaceSize[i])
+            LAUNCH(k_iface_pack, gridRows(D.ifaceSize[i]), 256, M.sendBuf[i].p, psi, D.ifaceCellsPos[i].p,
+                   D.ifaceSize[i]);
+    }
+    c.nccl.GroupStart();
+    for (int i = 0; i < D.nIfaces; i++) {
+        c.nccl.Send(M.sendBuf[i].p, D.ifaceSize[i], ncclDouble, D.ifaceNbr[i], c.comm, c.stream);
+        c.nccl.Recv(M.recvBuf[i].p, D.ifaceSize[i], ncclDouble, D.ifaceNbr[i], c.comm, c.stream);
+    }
+    int r = c.nccl.GroupEnd();
+    if (r != 0) throw CudaError(std::string("nccl halo exchange: ") + c.nccl.GetErrorString((ncclResult_t)r));
+}
+
+static void ifaceApply(b200ls_matrix_s* m, int level, double* result, double sign) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (D.nBRows == 0) return;
+    LAUNCH(k_iface_apply, gridRows(D.nBRows), 256, result, D.bRowPos.p, D.bRowPtr.p, D.bEntIface.p, D.bEntFace.p,
+           reinterpret_cast<const IfaceView*>(M.ifaceViews.p), sign, D.nBRows);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SpMV family
+// ------------------------------------------------------------------------------------------------------------
+
+template <int MODE>
+static void spmv(b200ls_matrix_s* m, int level, double* out, double* out2, const double* x, const double* b) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (D.nCells == 0) return;
+    LAUNCH(k_spmv<MODE>, gridRows(D.nCells), 256, out, out2, x, b, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
+           D.Uptr.p, D.Ucol.p, M.Uval(), D.nCells);
+}
+
+void opAmul(b200ls_matrix_s* m, int level, double* out, const double* x) {
+    haloExchange(m, level, x);
+    spmv<SPMV_AMUL>(m, level, out, nullptr, x, nullptr);
+    ifaceApply(m, level, out, 1.0);
+}
+
+void opResidual(b200ls_matrix_s* m, int level, double* out, const double* x, const double* b) {
+    haloExchange(m, level, x);
+    spmv<SPMV_RESIDUAL>(m, level, out, nullptr, x, b);
+    ifaceApply(m, level, out, -1.0);
+}
+
+// wA = A psi ; rA = source - wA   (PCG.C:93-96)
+static void opAmulAndResidual(b200ls_matrix_s* m, int level, double* wA, double* rA, const double* x,
+                              const double* b) {
+    DevLevel& D = DL(m, level);
+    if (D.nIfaces == 0) {
+        spmv<SPMV_AMUL_AND_RESIDUAL>(m, level, wA, rA, x, b);
+    } else {
+        opAmul(m, level, wA, x);
+        LAUNCH(k_sub, gridStride(D.nCells), 256, rA, b, wA, D.nCells);
+    }
+}
+
+void opSumA(b200ls_matrix_s* m, int level, double* out) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    spmv<SPMV_SUMA>(m, level, out, nullptr, nullptr, nullptr);
+    if (D.nBRows)
+        LAUNCH(k_iface_suma, gridRows(D.nBRows), 256, out, D.bRowPos.p, D.bRowPtr.p, D.bEntIface.p, D.bEntFace.p,
+               reinterpret_cast<const IfaceView*>(M.ifaceViews.p), D.nBRows);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// DIC / DILU
+// ------------------------------------------------------------------------------------------------------------
+
+static void fillSentinel(double* p, int n) {
+    static const bool noWait = getenv("B200LS_DEBUG_NO_WAIT") != nullptr;   // profiling aid: dependencies pre-satisfied
+    if (noWait) {
+        if (n) LAUNCH(k_fill, gridStride(n), 256, p, 1.0, n);
+        return;
+    }
+    if (n) LAUNCH(k_fill_sentinel, gridStride(n), 256, p, n);
+}
+
+static void ensureLevelScratch(b200ls_matrix_s* m, int level) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (M.tmpA.n != size_t(D.nCells) || (!M.tmpA.p && D.nCells)) {
+        M.tmpA.alloc(D.nCells);
+        M.tmpB.alloc(D.nCells);
+        M.tmpC.alloc(D.nCells);
+        M.tmpASentinel = false;
+    }
+}
+
+void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (M.rDValid) return;
+    M.rD.alloc(D.nCells);
+    if (precond == B200LS_DIAGONAL) {
+        // rD = 1/diag (diagonalPreconditioner.C:59-62)
+        if (D.nCells) {
+            LAUNCH(k_fill, gridStride(D.nCells), 256, M.rD.p, 1.0, D.nCells);
+            LAUNCH(k_div, gridStride(D.nCells), 256, M.rD.p, M.rD.p, M.diag.p, D.nCells);
+        }
+        M.rDValid = true;
+        return;
+    }
+    M.dWork.alloc(D.nCells);
+    fillSentinel(M.dWork.p, D.nCells);
+    SweepArgs a{};
+    a.tasks = D.fwdTasks.p;
+    a.nTasks = D.nFwdTasks;
+    a.ptr = D.Lptr.p;
+    a.col = D.Lcol.p;
+    a.val = M.Lval(D.nFaces);
+    a.col2 = m->symmetric ? nullptr : D.LtoU.p;
+    a.val2 = M.Uval();
+    a.diag = M.diag.p;
+    a.out = M.dWork.p;
+    a.out2 = M.rD.p;
+    launchSweep(k_factor, a);
+    M.rDValid = true;
+}
+
+// wA = M^-1 rA.  DIC/DILU: forward sweep into the level's sentinel scratch, backward sweep into wA; each sweep
+// re-arms the other's output buffer, so no fill kernels run in steady state.
+void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    const int n = D.nCells;
+    if (n == 0) return;
+    if (precond == B200LS_NONE) {
+        B2_CUDA(cudaMemcpyAsync(wA, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+        return;
+    }
+    ensureFactor(m, level, precond);
+    if (precond == B200LS_DIAGONAL) {
+        // wA = rD*rA  (diagonalPreconditioner.C:80-83); rD holds 1/diag
+        LAUNCH(k_mul, gridStride(n), 256, wA, M.rD.p, rA, n);
+        return;
+    }
+    if (precond != B200LS_DIC && precond != B200LS_DILU) throw CudaError("unknown preconditioner");
+    ensureLevelScratch(m, level);
+    if (!M.tmpASentinel) {
+        fillSentinel(M.tmpA.p, n);
+        M.tmpASentinel = true;
+    }
+    SweepArgs f{};
+    f.tasks = D.fwdTasks.p;
+    f.nTasks = D.nFwdTasks;
+    f.ptr = D.Lptr.p;
+    f.col = D.Lcol.p;
+    f.val = M.Lval(D.nFaces);
+    f.rD = M.rD.p;
+    f.in = rA;
+    f.out = M.tmpA.p;
+    f.clear = wA;
+    launchSweep(k_sweep_fwd, f);
+
+    SweepArgs b{};
+    b.tasks = D.bwdTasks.p;
+    b.nTasks = D.nBwdTasks;
+    b.rowOf = D.bwdPos.p;
+    b.ptr = D.Uptr.p;
+    b.col = D.Ucol.p;
+    b.val = M.Uval();
+    b.rD = M.rD.p;
+    b.in = M.tmpA.p;
+    b.out = wA;
+    b.clear = M.tmpA.p;
+    launchSweep(k_sweep_bwd, b);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// smoothers
+// ------------------------------------------------------------------------------------------------------------
+
+// psi/spare are swapped by Gauss-Seidel sweeps: on return `psi` holds the result.
+void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*& spare, const double* source,
+              int nSweeps) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    const int n = D.nCells;
+    if (n == 0) return;
+    ensureLevelScratch(m, level);
+    if (smoother == B200LS_GAUSS_SEIDEL) {
+        for (int sweep = 0; sweep < nSweeps; sweep++) {
+            const double* bPrime = source;
+            if (D.nIfaces) {
+                // bPrime = source + bouCoeffs*psi_nbr (negated coefficients, GaussSeidelSmoother.C:110-145)
+                B2_CUDA(cudaMemcpyAsync(M.tmpB.p, source, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+                haloExchange(m, level, psi);
+                ifaceApply(m, level, M.tmpB.p, -1.0);
+                bPrime = M.tmpB.p;
+            }
+            fillSentinel(spare, n);
+            SweepArgs a{};
+            a.tasks = D.fwdTasks.p;
+            a.nTasks = D.nFwdTasks;
+            a.ptr = D.Lptr.p;
+            a.col = D.Lcol.p;
+            a.val = M.Lval(D.nFaces);
+            a.ptr2 = D.Uptr.p;
+            a.col2 = D.Ucol.p;
+            a.val2 = M.Uval();
+            a.diag = M.diag.p;
+            a.in = bPrime;
+            a.old = psi;
+            a.out = spare;
+            launchSweep(k_gs_sweep, a);
+            std::swap(psi, spare);
+        }
+        return;
+    }
+    if (smoother == B200LS_DIC || smoother == B200LS_DILU) {
+        // DICSmoother.C:84-115 / DILUSmoother.C: rA = residual ; rA = M^-1 rA ; psi += rA
+        for (int sweep = 0; sweep < nSweeps; sweep++) {
+            opResidual(m, level, M.tmpB.p, psi, source);
+            opPrecondition(m, level, smoother, M.tmpC.p, M.tmpB.p);
+            LAUNCH(k_add_inplace, gridStride(n), 256, psi, M.tmpC.p, n);
+        }
+        return;
+    }
+    throw CudaError("unknown smoother");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------------------
+
+template <int OP>
+static void reduce(double* out, const double* x, const double* y, int n) {
+    Context& c = ctx();
+    LAUNCH(k_reduce<OP>, kReduceBlocks, kReduceThreads, out, x, y, n, c.partials.p, c.ticket.p);
+}
+
+enum {
+    S_SUMPSI = 0, S_NORM = 1, S_RES = 2, S_WARA0 = 3, S_WARA1 = 4, S_WAPA = 5,
+    S_RHO0 = 6, S_RHO1 = 7, S_RA0AYA = 8, S_ALPHA = 9, S_OMEGA = 10, S_TASA = 11, S_TATA = 12,
+    S_NUM = 13, S_DEN = 14, S_COUNT = 32
+};
+
+static double* scalar(b200ls_matrix_s* m, int i) {
+    if (m->scalars.n != S_COUNT) {
+        m->scalars.alloc(S_COUNT);
+        B2_CUDA(cudaMemsetAsync(m->scalars.p, 0, S_COUNT * sizeof(double), S()));
+    }
+    return m->scalars.p + i;
+}
+
+// normFactor (lduMatrixSolver.C:174-197). tmp is clobbered.
+static double normFactor(b200ls_matrix_s* m, const double* psi, const double* source, const double* Apsi,
+                         double* tmp, int64_t nGlobalCells) {
+    Context& c = ctx();
+    DevLevel& D = DL(m, 0);
+    const int n = D.nCells;
+    opSumA(m, 0, tmp);
+    reduce<RED_SUM>(scalar(m, S_SUMPSI), psi, nullptr, n);
+    allReduce(scalar(m, S_SUMPSI), 1);
+    LAUNCH(k_norm_factor, kReduceBlocks, kReduceThreads, scalar(m, S_NORM), Apsi, source, tmp, scalar(m, S_SUMPSI),
+           double(nGlobalCells), n, c.partials.p, c.ticket.p);
+    allReduce(scalar(m, S_NORM), 1);
+    readScalars(scalar(m, S_NORM), 1);
+    return c.pinned[0] + 1e-20;   // solverPerformance::small_
+}
+
+static bool converged(double finalRes, double initRes, double tol, double relTol) {
+    // SolverPerformance.C:75-82
+    return finalRes < tol || (relTol > 1e-20 && finalRes < relTol * initRes);
+}
+
+static int64_t globalCells(b200ls_matrix_s* m) {
+    Context& c = ctx();
+    const int64_t n = DL(m, 0).nCells;
+    if (c.nRanks == 1) return n;
+    double* s = scalar(m, S_NUM);
+    const double h = double(n);
+    B2_CUDA(cudaMemcpyAsync(s, &h, sizeof(double), cudaMemcpyHostToDevice, S()));
+    B2_CUDA(cudaStreamSynchronize(S()));
+    allReduce(s, 1);
+    readScalars(s, 1);
+    return int64_t(c.pinned[0] + 0.5);
+}
+
+static const double kVSmall = 2.2250738585072014e-308;   // vSmall = DBL_MIN (doubleScalar.H:57)
+
+static void record(b200ls_perf* perf, const b200ls_controls& c, double r) {
+    if (c.recordHistory && perf->nHistory < B200LS_MAX_HISTORY) perf->history[perf->nHistory++] = r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PCG (PCG.C:65-193)
+// ------------------------------------------------------------------------------------------------------------
+
+static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, const double* source,
+                     b200ls_perf* perf, cudaEvent_t evLoopStart) {
+    Context& cx = ctx();
+    const int n = DL(m, 0).nCells;
+    double* pA = m->vec("pA");
+    double* wA = m->vec("wA");
+    double* rA = m->vec("rA");
+
+    opAmulAndResidual(m, 0, wA, rA, psi, source);
+    const double nf = normFactor(m, psi, source, wA, pA, globalCells(m));
+    perf->normFactor = nf;
+    reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
+    allReduce(scalar(m, S_RES), 1);
+    readScalars(scalar(m, S_RES), 1);
+    perf->initialResidual = cx.pinned[0] / nf;
+    perf->finalResidual = perf->initialResidual;
+    perf->nIterations = 0;
+
+    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+        ensureFactor(m, 0, c.precond);
+        do {
+            const int cur = S_WARA0 + (perf->nIterations & 1);
+            const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
+            opPrecondition(m, 0, c.precond, wA, rA);
+            reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
+            allReduce(scalar(m, cur), 1);
+            LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
+                   perf->nIterations == 0 ? 1 : 0, n);
+            opAmul(m, 0, wA, pA);
+            reduce<RED_DOT>(scalar(m, S_WAPA), wA, pA, n);
+            allReduce(scalar(m, S_WAPA), 1);
+            // singularity test needs wApA on the host before psi is touched (PCG.C:165)
+            readScalars(scalar(m, S_WAPA), 1);
+            if (std::fabs(cx.pinned[0]) / nf < kVSmall) {
+                perf->singular = 1;
+                break;
+            }
+            LAUNCH(k_pcg_update_xr, kReduceBlocks, kReduceThreads, psi, rA, pA, wA, scalar(m, cur),
+                   scalar(m, S_WAPA), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
+            allReduce(scalar(m, S_RES), 1);
+            readScalars(scalar(m, S_RES), 1);
+            perf->finalResidual = cx.pinned[0] / nf;
+            record(perf, c, perf->finalResidual);
+        } while ((++perf->nIterations < c.maxIter &&
+                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                 perf->nIterations < c.minIter);
+    }
+    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PBiCGStab (PBiCGStab.C:68-254)
+// ------------------------------------------------------------------------------------------------------------
+
+static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, const double* source,
+                           b200ls_perf* perf, cudaEvent_t evLoopStart) {
+    Context& cx = ctx();
+    const int n = DL(m, 0).nCells;
+    double* pA = m->vec("pA");
+    double* yA = m->vec("yA");
+    double* rA = m->vec("rA");
+
+    opAmulAndResidual(m, 0, yA, rA, psi, source);
+    const double nf = normFactor(m, psi, source, yA, pA, globalCells(m));
+    perf->normFactor = nf;
+    reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
+    allReduce(scalar(m, S_RES), 1);
+    readScalars(scalar(m, S_RES), 1);
+    perf->initialResidual = cx.pinned[0] / nf;
+    perf->finalResidual = perf->initialResidual;
+    perf->nIterations = 0;
+
+    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+        double* AyA = m->vec("AyA");
+        double* sA = m->vec("sA");
+        double* zA = m->vec("zA");
+        double* tA = m->vec("tA");
+        double* rA0 = m->vec("rA0");
+        B2_CUDA(cudaMemcpyAsync(rA0, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+        ensureFactor(m, 0, c.precond);
+        double omega = 0;
+        do {
+            const int cur = S_RHO0 + (perf->nIterations & 1);
+            const int old = S_RHO0 + ((perf->nIterations + 1) & 1);
+            reduce<RED_DOT>(scalar(m, cur), rA0, rA, n);
+            allReduce(scalar(m, cur), 1);
+            readScalars(scalar(m, cur), 1);
+            if (std::fabs(cx.pinned[0]) < kVSmall) {
+                perf->singular = 1;
+                break;
+            }
+            if (perf->nIterations > 0 && std::fabs(omega) < kVSmall) {
+                perf->singular = 1;
+                break;
+            }
+            LAUNCH(k_bicg_update_p, gridStride(n), 256, pA, rA, AyA, m->scalars.p, cur, old, S_ALPHA, S_OMEGA,
+                   perf->nIterations == 0 ? 1 : 0, n);
+            opPrecondition(m, 0, c.precond, yA, pA);
+            opAmul(m, 0, AyA, yA);
+            reduce<RED_DOT>(scalar(m, S_RA0AYA), rA0, AyA, n);
+            allReduce(scalar(m, S_RA0AYA), 1);
+            LAUNCH(k_bicg_update_s, kReduceBlocks, kReduceThreads, sA, rA, AyA, scalar(m, cur), scalar(m, S_RA0AYA),
+                   scalar(m, S_ALPHA), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
+            allReduce(scalar(m, S_RES), 1);
+            readScalars(scalar(m, S_RES), 1);
+            perf->finalResidual = cx.pinned[0] / nf;
+            if (++perf->nIterations >= c.minIter &&
+                converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+                LAUNCH(k_axpy_s, gridStride(n), 256, psi, yA, scalar(m, S_ALPHA), n);
+                record(perf, c, perf->finalResidual);
+                perf->converged = 1;
+                return;
+            }
+            opPrecondition(m, 0, c.precond, zA, sA);
+            opAmul(m, 0, tA, zA);
+            // tAsA and tAtA in one pass (and one 2-element allreduce)
+            LAUNCH(k_dot2, kReduceBlocks, kReduceThreads, scalar(m, S_TASA), sA, tA, tA, n, cx.partials.p,
+                   cx.ticket.p);
+            allReduce(scalar(m, S_TASA), 2);
+            LAUNCH(k_bicg_update_xr, kReduceBlocks, kReduceThreads, psi, rA, yA, zA, sA, tA, scalar(m, S_ALPHA),
+                   scalar(m, S_TASA), scalar(m, S_OMEGA), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
+            allReduce(scalar(m, S_RES), 1);
+            readScalars(scalar(m, S_OMEGA), 1);
+            omega = cx.pinned[0];
+            readScalars(scalar(m, S_RES), 1);
+            perf->finalResidual = cx.pinned[0] / nf;
+            record(perf, c, perf->finalResidual);
+        } while ((perf->nIterations < c.maxIter &&
+                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                 perf->nIterations < c.minIter);
+    }
+    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// smoothSolver (smoothSolver.C:77-193)
+// ------------------------------------------------------------------------------------------------------------
+
+static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, double*& spare,
+                        const double* source, b200ls_perf* perf, cudaEvent_t evLoopStart) {
+    Context& cx = ctx();
+    const int n = DL(m, 0).nCells;
+    perf->nIterations = 0;
+    if (c.nSweeps < 0) {
+        B2_CUDA(cudaEventRecord(evLoopStart, S()));
+        if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) ensureFactor(m, 0, c.precond);
+        opSmooth(m, 0, c.precond, psi, spare, source, -c.nSweeps);
+        perf->nIterations -= c.nSweeps;
+        return;
+    }
+    double* Apsi = m->vec("wA");
+    double* tmp = m->vec("pA");
+    double* rA = m->vec("rA");
+    opAmulAndResidual(m, 0, Apsi, rA, psi, source);
+    const double nf = normFactor(m, psi, source, Apsi, tmp, globalCells(m));
+    perf->normFactor = nf;
+    reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
+    allReduce(scalar(m, S_RES), 1);
+    readScalars(scalar(m, S_RES), 1);
+    perf->initialResidual = cx.pinned[0] / nf;
+    perf->finalResidual = perf->initialResidual;
+    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+        if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) ensureFactor(m, 0, c.precond);
+        do {
+            opSmooth(m, 0, c.precond, psi, spare, source, c.nSweeps);
+            opResidual(m, 0, rA, psi, source);
+            reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
+            allReduce(scalar(m, S_RES), 1);
+            readScalars(scalar(m, S_RES), 1);
+            perf->finalResidual = cx.pinned[0] / nf;
+            record(perf, c, perf->finalResidual);
+        } while (((perf->nIterations += c.nSweeps) < c.maxIter &&
+                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                 perf->nIterations < c.minIter);
+    }
+    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GAMG
+// ------------------------------------------------------------------------------------------------------------
+
+// agglomerateMatrix for every level (GAMGSolver.C:196-208 -> GAMGSolverAgglomerateMatrix.C:33-193)
+static void buildCoarseMatrices(b200ls_matrix_s* m) {
+    if (m->coarseValid) return;
+    const int nL = int(m->levels.size());
+    for (int k = 0; k + 1 < nL; k++) {
+        DevLevel& F = DL(m, k);
+        DevLevel& C = DL(m, k + 1);
+        MatLevel& MF = m->levels[k];
+        MatLevel& MC = m->levels[k + 1];
+        MC.diag.alloc(C.nCells);
+        MC.vals.alloc(size_t(2) * C.nFaces);
+        MC.rDValid = false;
+        if (C.nCells)
+            LAUNCH(k_agglomerate_diag, gridRows(C.nCells), 256, MC.diag.p, MF.diag.p, MF.Uval(), MF.Lval(F.nFaces),
+                   F.rPtr.p, F.rFine.p, F.adPtr.p, F.adU.p, F.adL.p, C.nCells);
+        if (C.nFaces) {
+            LAUNCH(k_agglomerate_offdiag, gridRows(C.nFaces), 256, MC.Uval(), MF.vals.p, F.auPtr.p, F.auSrc.p,
+                   C.nFaces);
+            LAUNCH(k_agglomerate_offdiag, gridRows(C.nFaces), 256, MC.Lval(C.nFaces), MF.vals.p, F.alPtr.p,
+                   F.alSrc.p, C.nFaces);
+        }
+        // interface coefficients: restrictField over patchFaceRestrictAddressing (:253-267)
+        MC.bou.resize(C.nIfaces);
+        MC.inn.resize(C.nIfaces);
+        MC.sendBuf.resize(C.nIfaces);
+        MC.recvBuf.resize(C.nIfaces);
+        for (int i = 0; i < C.nIfaces; i++) {
+            MC.bou[i].alloc(C.ifaceSize[i]);
+            MC.inn[i].alloc(C.ifaceSize[i]);
+            if (C.ifaceSize[i]) {
+                LAUNCH(k_agglomerate_offdiag, gridRows(C.ifaceSize[i]), 256, MC.bou[i].p, MF.bou[i].p, F.aiPtr[i].p,
+                       F.aiSrc[i].p, C.ifaceSize[i]);
+                LAUNCH(k_agglomerate_offdiag, gridRows(C.ifaceSize[i]), 256, MC.inn[i].p, MF.inn[i].p, F.aiPtr[i].p,
+                       F.aiSrc[i].p, C.ifaceSize[i]);
+            }
+        }
+        setupIfaceViews(m, k + 1);
+        MC.corr.alloc(C.nCells);
+        MC.src.alloc(C.nCells);
+    }
+    m->coarseValid = true;
+}
+
+// Coarsest-level solve on one thread, in the reference's exact sequential order (PCG+DIC for symmetric,
+// PBiCGStab+DILU for asymmetric, diagonalSolver when the level has no faces; GAMGSolver.C:269-319,
+// GAMGSolverSolve.C:520-552).  The level has ~10-20 cells: latency, not throughput.
+struct CoarsestArgs {
+    int nCells, nFaces, symmetric;
+    const int *lower, *upper, *Uidx, *Lidx, *ipos;
+    const double *diag, *Uval, *Lval;
+    const double* source;   // position order
+    double* psi;            // position order, overwritten (initial guess 0)
+    double* work;           // 10*nCells + 2*nFaces doubles
+    double tolerance, relTol;
+    int maxIter;
+};
+
+__device__ static void c_amul(const CoarsestArgs& a, const double* up, const double* lo, const double* dg,
+                              double* out, const double* x) {
+    for (int c = 0; c < a.nCells; c++) out[c] = dg[c] * x[c];
+    for (int f = 0; f < a.nFaces; f++) {
+        out[a.upper[f]] += lo[f] * x[a.lower[f]];
+        out[a.lower[f]] += up[f] * x[a.upper[f]];
+    }
+}
+
+__device__ static void c_precondition(const CoarsestArgs& a, const double* up, const double* lo, const double* rD,
+                                      double* w, const double* r) {
+    for (int c = 0; c < a.nCells; c++) w[c] = rD[c] * r[c];
+    // faces sorted by upper cell == losort order: walk cells' neighbour-side faces through a stable scan
+    // (DILU uses losort order, DIC plain face order: both give ascending faces per row)
+    for (int f = 0; f < a.nFaces; f++) {
+        // plain face order is valid for both because every row only depends on finished rows (owner-sorted)
+        w[a.upper[f]] -= rD[a.upper[f]] * lo[f] * w[a.lower[f]];
+    }
+    for (int f = a.nFaces - 1; f >= 0; f--) w[a.lower[f]] -= rD[a.lower[f]] * up[f] * w[a.upper[f]];
+}
+
+__device__ static bool c_converged(double fin, double ini, double tol, double relTol) {
+    return fin < tol || (relTol > 1e-20 && fin < relTol * ini);
+}
+
+__global__ void k_coarsest_solve(CoarsestArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = a.nCells, nF = a.nFaces;
+    double* w = a.work;
+    double* up = w;            w += nF;
+    double* lo = w;            w += nF;
+    double* dg = w;            w += n;
+    double* b = w;             w += n;
+    double* x = w;             w += n;
+    double* v0 = w;            w += n;
+    double* v1 = w;            w += n;
+    double* v2 = w;            w += n;
+    double* rD = w;            w += n;
+    double* v3 = w;            w += n;
+    double* v4 = w;            w += n;
+    double* v5 = w;            w += n;
+    double* v6 = w;            w += n;
+    double* v7 = w;            w += n;
+    for (int f = 0; f < nF; f++) {
+        up[f] = a.Uval[a.Uidx[f]];
+        lo[f] = a.Lval[a.Lidx[f]];
+    }
+    for (int c = 0; c < n; c++) {
+        dg[c] = a.diag[a.ipos[c]];
+        b[c] = a.source[a.ipos[c]];
+        x[c] = 0.0;
+    }
+    const double vSmall = 2.2250738585072014e-308;
+
+    if (nF == 0) {
+        for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = b[c] / dg[c];   // diagonalSolver.C:66
+        return;
+    }
+
+    // common prologue: Amul, residual, normFactor
+    double* Ax = v0;
+    double* r = v1;
+    double* tmp = v2;
+    c_amul(a, up, lo, dg, Ax, x);
+    for (int c = 0; c < n; c++) r[c] = b[c] - Ax[c];
+    for (int c = 0; c < n; c++) tmp[c] = dg[c];
+    for (int f = 0; f < nF; f++) {
+        tmp[a.upper[f]] += lo[f];
+        tmp[a.lower[f]] += up[f];
+    }
+    double sumX = 0.0;
+    for (int c = 0; c < n; c++) sumX += x[c];
+    const double xbar = sumX / n;
+    double nfac = 0.0;
+    for (int c = 0; c < n; c++) {
+        const double t = tmp[c] * xbar;
+        nfac += fabs(Ax[c] - t) + fabs(b[c] - t);
+    }
+    nfac += 1e-20;
+    double sm = 0.0;
+    for (int c = 0; c < n; c++) sm += fabs(r[c]);
+    const double ini = sm / nfac;
+    double fin = ini;
+
+    if (!c_converged(fin, ini, a.tolerance, a.relTol)) {
+        // reciprocal preconditioned diagonal
+        for (int c = 0; c < n; c++) rD[c] = dg[c];
+        for (int f = 0; f < nF; f++) rD[a.upper[f]] -= up[f] * lo[f] / rD[a.lower[f]];
+        for (int c = 0; c < n; c++) rD[c] = 1.0 / rD[c];
+
+        if (a.symmetric) {
+            double* p = v3;
+            double* wA = Ax;
+            double wArA = 1e20, wArAold;
+            int it = 0;
+            do {
+                wArAold = wArA;
+                c_precondition(a, up, lo, rD, wA, r);
+                wArA = 0.0;
+                for (int c = 0; c < n; c++) wArA += wA[c] * r[c];
+                if (it == 0) {
+                    for (int c = 0; c < n; c++) p[c] = wA[c];
+                } else {
+                    const double beta = wArA / wArAold;
+                    for (int c = 0; c < n; c++) p[c] = wA[c] + beta * p[c];
+                }
+                c_amul(a, up, lo, dg, wA, p);
+                double wApA = 0.0;
+                for (int c = 0; c < n; c++) wApA += wA[c] * p[c];
+                if (fabs(wApA) / nfac < vSmall) break;
+                const double alpha = wArA / wApA;
+                for (int c = 0; c < n; c++) {
+                    x[c] += alpha * p[c];
+                    r[c] -= alpha * wA[c];
+                }
+                sm = 0.0;
+                for (int c = 0; c < n; c++) sm += fabs(r[c]);
+                fin = sm / nfac;
+            } while (++it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
+        } else {
+            double* p = v3;
+            double* y = Ax;
+            double* AyA = v2;
+            double* s = v4;
+            double* z = v5;
+            double* t = v6;
+            double* r0 = v7;
+            for (int c = 0; c < n; c++) r0[c] = r[c];
+            double rho = 0, alpha = 0, omega = 0;
+            int it = 0;
+            bool done = false;
+            do {
+                const double rhoOld = rho;
+                rho = 0.0;
+                for (int c = 0; c < n; c++) rho += r0[c] * r[c];
+                if (fabs(rho) < vSmall) break;
+                if (it == 0) {
+                    for (int c = 0; c < n; c++) p[c] = r[c];
+                } else {
+                    if (fabs(omega) < vSmall) break;
+                    const double beta = (rho / rhoOld) * (alpha / omega);
+                    for (int c = 0; c < n; c++) p[c] = r[c] + beta * (p[c] - omega * AyA[c]);
+                }
+                c_precondition(a, up, lo, rD, y, p);
+                c_amul(a, up, lo, dg, AyA, y);
+                double r0AyA = 0.0;
+                for (int c = 0; c < n; c++) r0AyA += r0[c] * AyA[c];
+                alpha = rho / r0AyA;
+                for (int c = 0; c < n; c++) s[c] = r[c] - alpha * AyA[c];
+                sm = 0.0;
+                for (int c = 0; c < n; c++) sm += fabs(s[c]);
+                fin = sm / nfac;
+                if (++it >= 0 && c_converged(fin, ini, a.tolerance, a.relTol)) {
+                    for (int c = 0; c < n; c++) x[c] += alpha * y[c];
+                    done = true;
+                    break;
+                }
+                c_precondition(a, up, lo, rD, z, s);
+                c_amul(a, up, lo, dg, t, z);
+                double tt = 0.0;
+                for (int c = 0; c < n; c++) tt += t[c] * t[c];
+                double ts = 0.0;
+                for (int c = 0; c < n; c++) ts += t[c] * s[c];
+                omega = ts / tt;
+                for (int c = 0; c < n; c++) {
+                    x[c] += alpha * y[c] + omega * z[c];
+                    r[c] = s[c] - omega * t[c];
+                }
+                sm = 0.0;
+                for (int c = 0; c < n; c++) sm += fabs(r[c]);
+                fin = sm / nfac;
+            } while (it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
+            (void)done;
+        }
+    }
+    for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = x[c];
+}
+
+static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
+    const int k = int(m->levels.size()) - 1;
+    DevLevel& D = DL(m, k);
+    MatLevel& M = m->levels[k];
+    if (ctx().nRanks > 1) throw CudaError("multi-rank GAMG coarsest solve not implemented yet");
+    m->coarsestWork.alloc(size_t(12) * D.nCells + size_t(2) * D.nFaces + 16);
+    CoarsestArgs a;
+    a.nCells = D.nCells;
+    a.nFaces = D.nFaces;
+    a.symmetric = m->symmetric ? 1 : 0;
+    a.lower = D.refLower.p;
+    a.upper = D.refUpper.p;
+    a.Uidx = D.Uidx.p;
+    a.Lidx = D.Lidx.p;
+    a.ipos = D.ipos.p;
+    a.diag = M.diag.p;
+    a.Uval = M.Uval();
+    a.Lval = M.Lval(D.nFaces);
+    a.source = M.src.p;
+    a.psi = M.corr.p;
+    a.work = m->coarsestWork.p;
+    a.tolerance = c.tolerance;
+    a.relTol = c.relTol;
+    a.maxIter = 1000;   // lduMatrix::solver::defaultMaxIter_
+    LAUNCH(k_coarsest_solve, 1, 32, a);
+}
+
+// GAMGSolver::scale (GAMGSolverScale.C:31-76)
+static void gamgScale(b200ls_matrix_s* m, int level, double* field, double* Acf, const double* source) {
+    Context& cx = ctx();
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    const int n = D.nCells;
+    opAmul(m, level, Acf, field);
+    LAUNCH(k_dot2, kReduceBlocks, kReduceThreads, scalar(m, S_NUM), source, Acf, field, n, cx.partials.p,
+           cx.ticket.p);
+    allReduce(scalar(m, S_NUM), 2);
+    LAUNCH(k_gamg_scale, gridStride(n), 256, field, source, Acf, M.diag.p, scalar(m, S_NUM), n);
+}
+
+static void restrictTo(b200ls_matrix_s* m, int fineLevel, double* coarse, const double* fine) {
+    DevLevel& F = DL(m, fineLevel);
+    DevLevel& C = DL(m, fineLevel + 1);
+    if (C.nCells) LAUNCH(k_restrict, gridRows(C.nCells), 256, coarse, fine, F.rPtr.p, F.rFine.p, C.nCells);
+}
+static void prolongTo(b200ls_matrix_s* m, int fineLevel, double* fine, const double* coarse) {
+    DevLevel& F = DL(m, fineLevel);
+    if (F.nCells) LAUNCH(k_prolong, gridRows(F.nCells), 256, fine, coarse, F.pMap.p, F.nCells);
+}
+
+// one V-cycle (GAMGSolverSolve.C:148-443).  My level k>0 is the reference's matrixLevels_[k-1];
+// coarseCorrFields[l] / coarseSources[l] live on level l+1 as levels[l+1].corr / .src.
+static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, double*& psiSpare,
+                   const double* source, double* Apsi, double* finestCorrection, double* finestResidual,
+                   bool scaleCorrection) {
+    const int nL = int(m->levels.size());
+    const int coarsest = nL - 2;   // reference coarsestLevel index into matrixLevels_
+    const int n0 = DL(m, 0).nCells;
+
+    restrictTo(m, 0, m->levels[1].src.p, finestResidual);
+    for (int l = 0; l < coarsest; l++) {
+        MatLevel& ML = m->levels[l + 1];
+        if (c.nPreSweeps) {
+            DevLevel& D = DL(m, l + 1);
+            B2_CUDA(cudaMemsetAsync(ML.corr.p, 0, sizeof(double) * D.nCells, S()));
+            ensureLevelScratch(m, l + 1);
+            double* corr = ML.corr.p;
+            double* spare = ML.tmpC.p;
+            if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) {
+                // the DIC/DILU smoother needs tmpB/tmpC itself: use the coarse Apsi scratch as spare
+            }
+            opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
+                     std::min(c.nPreSweeps + c.preSweepsLevelMultiplier * l, c.maxPreSweeps));
+            if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
+            double* ACf = ML.tmpB.p;
+            if (scaleCorrection && l < coarsest - 1) gamgScale(m, l + 1, ML.corr.p, ACf, ML.src.p);
+            opAmul(m, l + 1, ACf, ML.corr.p);
+            // coarseSources[l] -= ACf
+            LAUNCH(k_sub_inplace, gridStride(D.nCells), 256, ML.src.p, ACf, D.nCells);
+        }
+        restrictTo(m, l + 1, m->levels[l + 2].src.p, ML.src.p);
+    }
+
+    solveCoarsest(m, c);
+
+    for (int l = coarsest - 1; l >= 0; l--) {
+        DevLevel& D = DL(m, l + 1);
+        MatLevel& ML = m->levels[l + 1];
+        ensureLevelScratch(m, l + 1);
+        double* pre = nullptr;
+        if (c.nPreSweeps) {
+            // preSmoothedCoarseCorrField = coarseCorrFields[l]
+            ML.dWork.alloc(D.nCells);
+            pre = ML.dWork.p;
+            B2_CUDA(cudaMemcpyAsync(pre, ML.corr.p, sizeof(double) * D.nCells, cudaMemcpyDeviceToDevice, S()));
+        }
+        prolongTo(m, l + 1, ML.corr.p, m->levels[l + 2].corr.p);
+        if (scaleCorrection && l < coarsest - 1) gamgScale(m, l + 1, ML.corr.p, ML.tmpB.p, ML.src.p);
+        if (pre) LAUNCH(k_add_inplace, gridStride(D.nCells), 256, ML.corr.p, pre, D.nCells);
+        double* corr = ML.corr.p;
+        double* spare = ML.tmpC.p;
+        // GS swaps corr/spare; DIC smoothing uses tmpB/tmpC internally and leaves corr in place
+        if (c.precond == B200LS_GAUSS_SEIDEL) {
+            opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
+                     std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
+            if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
+        } else {
+            opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
+                     std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
+        }
+    }
+
+    prolongTo(m, 0, finestCorrection, m->levels[1].corr.p);
+    if (scaleCorrection) gamgScale(m, 0, finestCorrection, Apsi, finestResidual);
+    LAUNCH(k_add_inplace, gridStride(n0), 256, psi, finestCorrection, n0);
+    opSmooth(m, 0, c.precond, psi, psiSpare, source, c.nFinestSweeps);
+}
+
+static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, double*& psiSpare,
+                      const double* source, b200ls_perf* perf, cudaEvent_t evLoopStart) {
+    Context& cx = ctx();
+    if (m->levels.size() < 2) {
+        throw CudaError("No coarse levels created, either matrix too small for GAMG or minCellsPerProcessor too "
+                        "large (call b200ls_agglomerate first)");
+    }
+    const int n = DL(m, 0).nCells;
+    double* Apsi = m->vec("wA");
+    double* finestCorrection = m->vec("pA");
+    double* finestResidual = m->vec("rA");
+    const bool scaleCorrection = c.scaleCorrection < 0 ? m->symmetric : (c.scaleCorrection != 0);
+
+    // solver construction: coarse matrices (+ smoother factorisations) -- timed as setup
+    buildCoarseMatrices(m);
+    if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) {
+        for (int k = 0; k + 1 < int(m->levels.size()); k++) ensureFactor(m, k, c.precond);
+    }
+
+    opAmul(m, 0, Apsi, psi);
+    const double nf = normFactor(m, psi, source, Apsi, finestCorrection, globalCells(m));
+    perf->normFactor = nf;
+    LAUNCH(k_sub, gridStride(n), 256, finestResidual, source, Apsi, n);
+    reduce<RED_SUMMAG>(scalar(m, S_RES), finestResidual, nullptr, n);
+    allReduce(scalar(m, S_RES), 1);
+    readScalars(scalar(m, S_RES), 1);
+    perf->initialResidual = cx.pinned[0] / nf;
+    perf->finalResidual = perf->initialResidual;
+    perf->nIterations = 0;
+
+    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+        do {
+            vcycle(m, c, psi, psiSpare, source, Apsi, finestCorrection, finestResidual, scaleCorrection);
+            opAmul(m, 0, Apsi, psi);
+            LAUNCH(k_sub, gridStride(n), 256, finestResidual, source, Apsi, n);
+            reduce<RED_SUMMAG>(scalar(m, S_RES), finestResidual, nullptr, n);
+            allReduce(scalar(m, S_RES), 1);
+            readScalars(scalar(m, S_RES), 1);
+            perf->finalResidual = cx.pinned[0] / nf;
+            record(perf, c, perf->finalResidual);
+        } while ((++perf->nIterations < c.maxIter &&
+                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                 perf->nIterations < c.minIter);
+    }
+    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// entry
+// ------------------------------------------------------------------------------------------------------------
+
+void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, const double* sourceCell,
+              b200ls_perf* perf) {
+    if (!m->valuesSet) throw CudaError("b200ls_solve: matrix coefficients not set");
+    Context& cx = ctx();
+    const int n = DL(m, 0).nCells;
+    const int64_t launches0 = cx.launches;
+    memset(perf, 0, offsetof(b200ls_perf, history));
+
+    cudaEvent_t ev0, ev1, ev2;
+    B2_CUDA(cudaEventCreate(&ev0));
+    B2_CUDA(cudaEventCreate(&ev1));
+    B2_CUDA(cudaEventCreate(&ev2));
+    B2_CUDA(cudaEventRecord(ev0, S()));
+
+    // named vectors are looked up before taking raw pointers (std::map nodes are stable)
+    b200ls::Vec& vPsi = m->vecs["psi"];
+    b200ls::Vec& vSpare = m->vecs["psiSpare"];
+    m->vec("psi");
+    m->vec("psiSpare");
+    double* source = m->vec("source");
+    toPositions(m, 0, vPsi.buf.p, psiCell);
+    toPositions(m, 0, source, sourceCell);
+
+    try {
+        switch (c.solver) {
+            case B200LS_PCG:
+                if (!m->symmetric) throw CudaError("PCG requires a symmetric matrix");
+                solvePCG(m, c, vPsi.buf.p, source, perf, ev1);
+                break;
+            case B200LS_PBICGSTAB:
+                solvePBiCGStab(m, c, vPsi.buf.p, source, perf, ev1);
+                break;
+            case B200LS_GAMG:
+                solveGAMG(m, c, vPsi.buf.p, vSpare.buf.p, source, perf, ev1);
+                break;
+            case B200LS_SMOOTH_SOLVER:
+                solveSmooth(m, c, vPsi.buf.p, vSpare.buf.p, source, perf, ev1);
+                break;
+            default:
+                throw CudaError("unknown solver");
+        }
+        toCells(m, 0, psiCell, vPsi.buf.p);
+        B2_CUDA(cudaEventRecord(ev2, S()));
+        B2_CUDA(cudaStreamSynchronize(S()));
+        checkLaunch("solve");
+        checkSweepError();
+    } catch (...) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        cudaEventDestroy(ev2);
+        throw;
+    }
+    float msSetup = 0, msLoop = 0;
+    cudaEventElapsedTime(&msSetup, ev0, ev1);
+    cudaEventElapsedTime(&msLoop, ev1, ev2);
+    perf->setupMs = msSetup;
+    perf->solveMs = msLoop;
+    perf->kernelLaunches = cx.launches - launches0;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaEventDestroy(ev2);
+    (void)n;
+}
+
+}  // namespace b200ls

@@ -1,0 +1,65 @@
+// Matrix object (coefficients resident in HBM in the native layout) and the solver drivers.
+#pragma once
+
+#include "../../include/b200ls.h"
+#include "device.cuh"
+
+namespace b200ls {
+
+// Coefficients of one level in the native layout
+struct MatLevel {
+    DevBuf<double> diag;
+    DevBuf<double> vals;            // [Uval (nFaces) | Lval (nFaces)]
+    DevBuf<double> rD;              // DIC/DILU reciprocal diagonal
+    bool rDValid = false;
+    DevBuf<double> dWork;           // factorisation scratch (pre-reciprocal diagonal, sentinel protocol)
+    // interfaces: coefficients, send/recv buffers
+    std::vector<DevBuf<double>> bou, inn, sendBuf, recvBuf;
+    DevBuf<unsigned char> ifaceViews;   // IfaceView[nIfaces] on device
+    // level work vectors (GAMG): correction, source, scratch
+    DevBuf<double> corr, src, tmpA, tmpB, tmpC;
+    bool tmpASentinel = false;      // tmpA is known to be all-sentinel
+    double* Uval() { return vals.p; }
+    double* Lval(int nFaces) { return vals.p + nFaces; }
+};
+
+struct Vec {
+    DevBuf<double> buf;
+    double* p() { return buf.p; }
+};
+
+}  // namespace b200ls
+
+struct b200ls_matrix_s {
+    b200ls_mesh_s* mesh = nullptr;
+    int meshGeneration = -1;
+    bool symmetric = true;
+    bool valuesSet = false;
+    bool coarseValid = false;       // coarse-level matrices match the current coefficients
+    std::vector<b200ls::MatLevel> levels;
+    std::map<std::string, b200ls::Vec> vecs;     // named finest-level work vectors (position order)
+    b200ls::DevBuf<double> stageA, stageB;       // cell-order staging (H2D / D2H)
+    b200ls::DevBuf<double> scalars;              // device scalars of the Krylov loops
+    b200ls::DevBuf<double> coarsestWork;         // scratch of the single-thread coarsest solve
+    double* vec(const std::string& name);
+};
+
+namespace b200ls {
+
+void ensureDeviceMesh(b200ls_mesh_s* mesh);
+void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, const double* lower,
+               const double* const* bou, const double* const* inn);
+void opAmul(b200ls_matrix_s* m, int level, double* out, const double* x);
+void opResidual(b200ls_matrix_s* m, int level, double* out, const double* x, const double* b);
+void opSumA(b200ls_matrix_s* m, int level, double* out);
+void ensureFactor(b200ls_matrix_s* m, int level, int precond);
+void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA);
+void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*& spare, const double* source,
+              int nSweeps);
+void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, const double* sourceCell,
+              b200ls_perf* perf);
+void toPositions(b200ls_matrix_s* m, int level, double* outPos, const double* inCell);
+void toCells(b200ls_matrix_s* m, int level, double* outCell, const double* inPos);
+void checkSweepError();
+
+}  // namespace b200ls

@@ -444,7 +444,7 @@ int main(int argc, char* argv[])
     }
 
     // --- solves: entries "solve.<i>.dict", optional "solve.<i>.history" = k:
-    //     re-run with maxIter=1..k and store the final residual of each run
+    //     re-run with maxIter=1..k (same tolerances) and store the final residual of each run
     for (int i = 0; ; i++)
     {
         const std::string key = "solve." + std::to_string(i);
@@ -493,9 +493,9 @@ int main(int argc, char* argv[])
             for (label it = 1; it <= k; it++)
             {
                 dictionary dk(d);
+                // tolerance/relTol are kept: a GAMG coarsest solver inherits them and must
+                // still terminate.  Entries past convergence repeat the final residual.
                 dk.set("maxIter", it);
-                dk.set("tolerance", 0);
-                dk.set("relTol", 0);
                 scalarField psik(psi0);
                 solverPerformance pk = lduMatrix::solver::New
                 (

@@ -1,0 +1,76 @@
+"""Shared helpers of the parity tests."""
+from pathlib import Path
+
+import numpy as np
+
+from _pkg import load_pkg
+
+load_pkg()
+from b200ls import capi, cases, ldu_io  # noqa: E402
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+FIXTURES = sorted(p.stem for p in GOLDEN.glob("*.b2ls"))
+
+
+def load_fixture(name):
+    raw = ldu_io.read(str(GOLDEN / f"{name}.b2ls"))
+    inp = {k[3:]: v for k, v in raw.items() if k.startswith("in.")}
+    ref = {k[4:]: v for k, v in raw.items() if k.startswith("ref.")}
+    return inp, ref
+
+
+def system_from_entries(inp):
+    return cases.LduSystem(
+        n_cells=int(inp["nCells"][0]), lower=inp["lower"], upper=inp["upper"], diag=inp["diag"],
+        upper_coeffs=inp["upperCoeffs"], lower_coeffs=inp.get("lowerCoeffs"), source=inp.get("source"),
+        face_weights=inp.get("faceWeights"),
+    )
+
+
+def parse_dict(text):
+    """'solver PCG; preconditioner DIC; tolerance 1e-6;' -> {'solver': 'PCG', ...}"""
+    out = {}
+    for item in text.split(";"):
+        parts = item.split()
+        if len(parts) >= 2:
+            out[parts[0]] = parts[1]
+    return out
+
+
+_INT_KEYS = {"maxIter", "minIter", "nPreSweeps", "preSweepsLevelMultiplier", "maxPreSweeps", "nPostSweeps",
+             "postSweepsLevelMultiplier", "maxPostSweeps", "nFinestSweeps", "nSweeps"}
+_FLT_KEYS = {"tolerance", "relTol"}
+
+
+def controls_from_dict(text, **extra):
+    d = parse_dict(text)
+    kw = {}
+    for k, v in d.items():
+        if k in _INT_KEYS:
+            kw[k] = int(v)
+        elif k in _FLT_KEYS:
+            kw[k] = float(v)
+    kw.update(extra)
+    return capi.controls(solver=d["solver"], preconditioner=d.get("preconditioner"), smoother=d.get("smoother"), **kw)
+
+
+def solve_keys(inp):
+    i = 0
+    while f"solve.{i}.dict" in inp:
+        yield i, ldu_io.as_str(inp[f"solve.{i}.dict"])
+        i += 1
+
+
+def smooth_keys(inp):
+    i = 0
+    while f"smooth.{i}.dict" in inp:
+        yield i, parse_dict(ldu_io.as_str(inp[f"smooth.{i}.dict"]))["smoother"], int(inp[f"smooth.{i}.nSweeps"][0])
+        i += 1
+
+
+def max_rel_diff(a, b):
+    """max |a-b| / max|b| : the 'max relative difference' of north_star, scaled by the field magnitude."""
+    scale = np.max(np.abs(b))
+    if scale == 0:
+        return float(np.max(np.abs(a - b)))
+    return float(np.max(np.abs(a - b)) / scale)

@@ -1,0 +1,102 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference solver stack
+(oracle/_ref/ref_harness, built from /root/reference by oracle/build_ref.py) on the synthetic systems of
+openfoam-dev_b200/cases.py.  Run in the build container only (needs /root/reference to build oracle/_ref):
+
+    python tests/golden/make_goldens.py
+
+Each fixture <name>.b2ls holds the harness INPUT entries (prefix "in.") and its OUTPUT entries (prefix "ref.").
+One harness process per fixture (pairGAMGAgglomeration::forward_ is a process-global static).
+"""
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT / "tests"))
+from _pkg import load_pkg  # noqa: E402
+
+b200ls = load_pkg()
+from b200ls import cases, ldu_io  # noqa: E402
+
+
+def run_ref(entries):
+    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle/foam_env"), WM_PROJECT="OpenFOAM",
+               WM_PROJECT_VERSION="dev")
+    with tempfile.TemporaryDirectory() as td:
+        ldu_io.write(f"{td}/in.b2ls", entries)
+        r = subprocess.run([str(ROOT / "oracle/_ref/ref_harness"), f"{td}/in.b2ls", f"{td}/out.b2ls", f"{td}/case"],
+                           env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
+        return ldu_io.read(f"{td}/out.b2ls")
+
+
+SYM_SOLVES = [
+    ("solver PCG; preconditioner DIC; tolerance 1e-6; relTol 0.05;", 30),
+    ("solver PCG; preconditioner DIC; tolerance 1e-10; relTol 0;", 80),
+    ("solver PCG; preconditioner diagonal; tolerance 1e-8; relTol 0;", 0),
+    ("solver PCG; preconditioner none; tolerance 1e-6; relTol 0; maxIter 25;", 0),
+    ("solver PBiCGStab; preconditioner DIC; tolerance 1e-8; relTol 0;", 45),
+    ("solver GAMG; smoother GaussSeidel; tolerance 1e-8; relTol 0;", 25),
+    ("solver GAMG; smoother DIC; tolerance 1e-8; relTol 0;", 25),
+    ("solver GAMG; smoother GaussSeidel; tolerance 1e-6; relTol 0.01; nPreSweeps 1; nFinestSweeps 3;", 0),
+    ("solver smoothSolver; smoother GaussSeidel; nSweeps 2; tolerance 1e-3; relTol 0; maxIter 40;", 0),
+    ("solver smoothSolver; smoother DIC; nSweeps 1; tolerance 1e-3; relTol 0; maxIter 40;", 0),
+]
+
+ASYM_SOLVES = [
+    ("solver PBiCGStab; preconditioner DILU; tolerance 1e-10; relTol 0;", 30),
+    ("solver PBiCGStab; preconditioner DILU; tolerance 1e-6; relTol 0.1;", 0),
+    ("solver PBiCGStab; preconditioner diagonal; tolerance 1e-8; relTol 0;", 0),
+    ("solver GAMG; smoother GaussSeidel; tolerance 1e-8; relTol 0;", 20),
+    ("solver GAMG; smoother DILU; tolerance 1e-8; relTol 0;", 20),
+    ("solver smoothSolver; smoother GaussSeidel; nSweeps 1; tolerance 1e-6; relTol 0; maxIter 60;", 0),
+    ("solver smoothSolver; smoother DILU; nSweeps 2; tolerance 1e-6; relTol 0; maxIter 60;", 0),
+]
+
+
+def fixture(name, sys_, solves, smoothers, agglom=True):
+    e = cases.to_entries(sys_)
+    n = sys_.n_cells
+    e["x"] = np.cos(0.11 * np.arange(n)) + 0.25
+    for i, (d, hist) in enumerate(solves):
+        e[f"solve.{i}.dict"] = d
+        if hist:
+            e[f"solve.{i}.history"] = hist
+    for i, (d, ns) in enumerate(smoothers):
+        e[f"smooth.{i}.dict"] = d
+        e[f"smooth.{i}.nSweeps"] = ns
+    if agglom:
+        e["agglomerate.dict"] = "solver GAMG;"
+    out = run_ref(e)
+    merged = {f"in.{k}": v for k, v in e.items()}
+    merged.update({f"ref.{k}": v for k, v in out.items()})
+    ldu_io.write(str(HERE / f"{name}.b2ls"), merged)
+    its = [int(out[f"solve.{i}.perf"][2]) for i in range(len(solves))]
+    print(f"{name}: nCells={n} nFaces={sys_.n_faces} levels={int(out['agg.nLevels'][0]) if agglom else -1} iterations={its}")
+
+
+def main():
+    if not (ROOT / "oracle/_ref/ref_harness").exists():
+        sys.exit("oracle/_ref/ref_harness missing: run python oracle/build_ref.py first")
+    sym_sm = [("smoother GaussSeidel;", 1), ("smoother GaussSeidel;", 3), ("smoother DIC;", 2)]
+    asym_sm = [("smoother GaussSeidel;", 2), ("smoother DILU;", 2)]
+    # config 1: the cavity tutorial mesh, 20x20x1, uniform Laplacian (PCG+DIC as icoFoam/cavity ships it)
+    fixture("cavity_20x20x1", cases.cavity_laplacian(20, 20, 1), SYM_SOLVES, sym_sm)
+    fixture("block_7x5x3_rand", cases.cavity_laplacian(7, 5, 3, coeffs="random", rhs_kind="uniform"),
+            SYM_SOLVES, sym_sm)
+    fixture("block_16x16x16_rand", cases.cavity_laplacian(16, 16, 16, coeffs="random"), SYM_SOLVES, sym_sm)
+    fixture("block_24x24x24", cases.cavity_laplacian(24, 24, 24, rhs_kind="uniform"), SYM_SOLVES[1:2] + SYM_SOLVES[5:6],
+            sym_sm[:1], agglom=False)
+    fixture("convdiff_24x18x1", cases.convection_diffusion(24, 18, 1, dt_coeff=50.0), ASYM_SOLVES, asym_sm)
+    fixture("convdiff_9x8x7", cases.convection_diffusion(9, 8, 7, dt_coeff=50.0, rhs_kind="uniform"), ASYM_SOLVES, asym_sm)
+
+
+if __name__ == "__main__":
+    main()
