@@ -1,0 +1,164 @@
+"""CPU tests (no GPU): host-side integer data of libb200ls against the reference goldens (bit-exact), the C-ABI
+surface, the B2LS container and the decomposition helpers."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from _util import FIXTURES, capi, cases, ldu_io, load_fixture, system_from_entries
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "b200ls.h").read_text()
+    declared = set(re.findall(r"\b(b200ls_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200ls_mesh_s", "b200ls_matrix_s"}
+    lib = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200ls.h but not exported"
+    assert set(capi.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when no CUDA device is usable."""
+    if capi.device_available():
+        pytest.skip("a CUDA device is present")
+    s = cases.cavity_laplacian(4, 4, 1)
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    mat = capi.Matrix(mesh)
+    with pytest.raises(capi.B200Error, match="no CUDA device"):
+        mat.set(s.diag, s.upper_coeffs)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_addressing_bit_exact(name):
+    inp, ref = load_fixture(name)
+    s = system_from_entries(inp)
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    assert np.array_equal(mesh.get_i32(capi.LOSORT), ref["losort"])
+    assert np.array_equal(mesh.get_i32(capi.OWNER_START), ref["ownerStart"])
+    assert np.array_equal(mesh.get_i32(capi.LOSORT_START), ref["losortStart"])
+
+
+@pytest.mark.parametrize("name", [f for f in FIXTURES if f != "block_24x24x24"])
+def test_agglomeration_bit_exact(name):
+    inp, ref = load_fixture(name)
+    s = system_from_entries(inp)
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    n_coarse = mesh.agglomerate(s.face_weights, forward_start=1)
+    assert n_coarse == int(ref["agg.nLevels"][0])
+    assert mesh.n_levels == n_coarse + 1
+    for lev in range(n_coarse):
+        k = f"agg.{lev}."
+        assert np.array_equal(mesh.get_i32(capi.RESTRICT_ADDRESSING, lev), ref[k + "restrictAddressing"])
+        assert np.array_equal(mesh.get_i32(capi.FACE_RESTRICT_ADDRESSING, lev), ref[k + "faceRestrictAddressing"])
+        assert np.array_equal(mesh.get_i32(capi.FACE_FLIP_MAP, lev), ref[k + "faceFlipMap"].astype(np.int32))
+        assert np.array_equal(mesh.get_i32(capi.LOWER_ADDR, lev + 1), ref[k + "coarseLower"])
+        assert np.array_equal(mesh.get_i32(capi.UPPER_ADDR, lev + 1), ref[k + "coarseUpper"])
+        assert list(mesh.get_i32(capi.LEVEL_SIZES, lev + 1)) == list(ref[k + "sizes"])
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 3), (20, 20, 1), (9, 1, 1), (1, 1, 1)])
+def test_wavefronts_of_a_block(shape):
+    """Canonical wavefronts: on an nx*ny*nz block Lf = i+j+k and Lb mirrors it."""
+    nx, ny, nz = shape
+    lower, upper, _ = cases.block_addressing(nx, ny, nz)
+    n = nx * ny * nz
+    mesh = capi.Mesh(n, lower, upper)
+    c = np.arange(n)
+    i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+    for which_o, which_r, lev in ((capi.FWD_LEVEL_OFFSETS, capi.FWD_LEVEL_ROWS, i + j + k),
+                                  (capi.BWD_LEVEL_OFFSETS, capi.BWD_LEVEL_ROWS,
+                                   (nx - 1 - i) + (ny - 1 - j) + (nz - 1 - k))):
+        offs, rows = mesh.get_i32(which_o), mesh.get_i32(which_r)
+        assert offs.size - 1 == nx + ny + nz - 2
+        for q in range(offs.size - 1):
+            assert np.array_equal(rows[offs[q]:offs[q + 1]], c[lev == q])
+
+
+def test_wavefront_dependencies_general_mesh():
+    """Every row sits strictly after all of its dependencies, on an unstructured (agglomerated) level."""
+    s = cases.cavity_laplacian(11, 7, 5, coeffs="random")
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    mesh.agglomerate(s.face_weights)
+    for lev in range(mesh.n_levels):
+        lo, up = mesh.get_i32(capi.LOWER_ADDR, lev), mesh.get_i32(capi.UPPER_ADDR, lev)
+        n = int(mesh.get_i32(capi.LEVEL_SIZES, lev)[0])
+        for wo, wr, src, dst in ((capi.FWD_LEVEL_OFFSETS, capi.FWD_LEVEL_ROWS, lo, up),
+                                 (capi.BWD_LEVEL_OFFSETS, capi.BWD_LEVEL_ROWS, up, lo)):
+            offs, rows = mesh.get_i32(wo, lev), mesh.get_i32(wr, lev)
+            level_of = np.empty(n, dtype=np.int64)
+            for q in range(offs.size - 1):
+                level_of[rows[offs[q]:offs[q + 1]]] = q
+            assert sorted(rows.tolist()) == list(range(n))
+            assert np.all(level_of[dst] > level_of[src])
+            # tight: every row of level q>0 has a dependency in level q-1
+            need = np.zeros(n, dtype=np.int64)
+            np.maximum.at(need, dst, level_of[src] + 1)
+            assert np.array_equal(need, level_of)
+
+
+def test_invalid_addressing_is_rejected():
+    with pytest.raises(capi.B200Error, match="upper-triangular"):
+        capi.Mesh(4, [1, 0], [2, 3])
+    with pytest.raises(capi.B200Error, match="lower < upper"):
+        capi.Mesh(4, [2], [1])
+
+
+def test_b2ls_roundtrip(tmp_path):
+    e = {"a": np.arange(5, dtype=np.int32), "b": np.linspace(0, 1, 7), "s": "solver PCG;", "n": 3}
+    ldu_io.write(str(tmp_path / "x.b2ls"), e)
+    r = ldu_io.read(str(tmp_path / "x.b2ls"))
+    assert np.array_equal(r["a"], e["a"]) and np.array_equal(r["b"], e["b"])
+    assert ldu_io.as_str(r["s"]) == "solver PCG;" and int(r["n"][0]) == 3
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4, 8])
+def test_direct_subdomain_equals_general_decomposition(n_ranks):
+    from b200ls import decompose
+
+    split = decompose.simple_split(n_ranks)
+    nx, ny, nz = 4 * split[0], 3 * split[1], 2 * split[2]
+    glob = cases.cavity_laplacian(nx, ny, nz)
+    parts, maps = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), n_ranks)
+    for r in range(n_ranks):
+        d = decompose.cavity_subdomain(nx, ny, nz, split, r)
+        g = parts[r]
+        assert d.n_cells == g.n_cells
+        assert np.array_equal(d.lower, g.lower) and np.array_equal(d.upper, g.upper)
+        assert np.array_equal(d.diag, g.diag) and np.array_equal(d.upper_coeffs, g.upper_coeffs)
+        assert np.allclose(d.source, g.source, rtol=0, atol=0)
+        assert [i.neighb_rank for i in d.interfaces] == [i.neighb_rank for i in g.interfaces]
+        for a, b in zip(d.interfaces, g.interfaces):
+            assert np.array_equal(a.face_cells, b.face_cells) and np.array_equal(a.bou_coeffs, b.bou_coeffs)
+
+
+def test_decomposed_operator_equals_global_operator():
+    """numpy restatement of Amul with interfaces (lduMatrixATmul.C:34-92 + processorFvPatchScalarField.C:133-136)
+    on the decomposed systems reproduces the global Amul."""
+    from b200ls import decompose
+
+    glob = cases.convection_diffusion(6, 4, 4)
+    ranks = decompose.box_cell_ranks(6, 4, 4, (2, 2, 1))
+    parts, maps = decompose.decompose_system(glob, ranks, 4)
+    x = np.cos(0.3 * np.arange(glob.n_cells))
+
+    def amul(s, xl):
+        y = s.diag * xl
+        lo_c = s.upper_coeffs if s.lower_coeffs is None else s.lower_coeffs
+        np.add.at(y, s.upper, lo_c * xl[s.lower])
+        np.add.at(y, s.lower, s.upper_coeffs * xl[s.upper])
+        return y
+
+    yg = amul(glob, x)
+    for r, (s, m) in enumerate(zip(parts, maps)):
+        y = amul(s, x[m])
+        for itf in s.interfaces:
+            # the neighbour's patchInternalField in the same face order
+            other = parts[itf.neighb_rank]
+            back = [i for i in other.interfaces if i.neighb_rank == r][0]
+            recv = x[maps[itf.neighb_rank]][back.face_cells]
+            np.subtract.at(y, itf.face_cells, itf.bou_coeffs * recv)
+        assert np.allclose(y, yg[m], rtol=1e-14, atol=1e-14)
