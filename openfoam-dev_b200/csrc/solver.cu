@@ -413,7 +413,9 @@ static void ensureLevelScratch(b200ls_matrix_s* m, int level) {
 void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
-    if (M.rDValid) return;
+    const int kind = (precond == B200LS_DIAGONAL) ? B200LS_DIAGONAL : B200LS_DIC;   // DIC and DILU share rD
+    if (M.rDValid && M.rDKind == kind) return;
+    M.rDKind = kind;
     M.rD.alloc(D.nCells);
     if (precond == B200LS_DIAGONAL) {
         // rD = 1/diag (diagonalPreconditioner.C:59-62)

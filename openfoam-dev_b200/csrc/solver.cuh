@@ -12,6 +12,7 @@ struct MatLevel {
     DevBuf<double> vals;            // [Uval (nFaces) | Lval (nFaces)]
     DevBuf<double> rD;              // DIC/DILU reciprocal diagonal
     bool rDValid = false;
+    int rDKind = -1;                // which preconditioner rD belongs to (DIC/DILU vs diagonal)
     DevBuf<double> dWork;           // factorisation scratch (pre-reciprocal diagonal, sentinel protocol)
     // interfaces: coefficients, send/recv buffers
     std::vector<DevBuf<double>> bou, inn, sendBuf, recvBuf;

@@ -40,7 +40,7 @@ def run_ref(entries):
 SYM_SOLVES = [
     ("solver PCG; preconditioner DIC; tolerance 1e-6; relTol 0.05;", 30),
     ("solver PCG; preconditioner DIC; tolerance 1e-10; relTol 0;", 80),
-    ("solver PCG; preconditioner diagonal; tolerance 1e-8; relTol 0;", 0),
+    ("solver PCG; preconditioner diagonal; tolerance 1e-8; relTol 0; maxIter 40;", 40),
     ("solver PCG; preconditioner none; tolerance 1e-6; relTol 0; maxIter 25;", 0),
     ("solver PBiCGStab; preconditioner DIC; tolerance 1e-8; relTol 0;", 45),
     ("solver GAMG; smoother GaussSeidel; tolerance 1e-8; relTol 0;", 25),
@@ -53,7 +53,7 @@ SYM_SOLVES = [
 ASYM_SOLVES = [
     ("solver PBiCGStab; preconditioner DILU; tolerance 1e-10; relTol 0;", 30),
     ("solver PBiCGStab; preconditioner DILU; tolerance 1e-6; relTol 0.1;", 0),
-    ("solver PBiCGStab; preconditioner diagonal; tolerance 1e-8; relTol 0;", 0),
+    ("solver PBiCGStab; preconditioner diagonal; tolerance 1e-8; relTol 0; maxIter 15;", 15),
     ("solver GAMG; smoother GaussSeidel; tolerance 1e-8; relTol 0;", 20),
     ("solver GAMG; smoother DILU; tolerance 1e-8; relTol 0;", 20),
     ("solver smoothSolver; smoother GaussSeidel; nSweeps 1; tolerance 1e-6; relTol 0; maxIter 60;", 0),
