@@ -92,6 +92,12 @@ int b200ls_mesh_n_levels(b200ls_mesh_t mesh);   /* number of mesh levels incl. t
 int b200ls_agglomerate(b200ls_mesh_t mesh, const double* faceWeights,
                        int32_t minCellsPerProcessor, int32_t mergeLevels, int32_t forwardStart);
 
+/* Same, with the cell maps of every level supplied by the caller: restrictAddr[k] maps the cells of level k to
+ * the nCoarseCells[k] cells of level k+1 (GAMGAgglomeration::restrictAddressing(k) / nCells(k)).  The plugin uses
+ * this with the reference's own cached GAMGAgglomeration MeshObject (GAMGAgglomeration.C:349-400). */
+int b200ls_agglomerate_from_maps(b200ls_mesh_t mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
+                                 const int32_t* nCoarseCells);
+
 /* ---- matrix --------------------------------------------------------------------------------------------- */
 
 b200ls_matrix_t b200ls_matrix_create(b200ls_mesh_t mesh);

@@ -78,6 +78,25 @@ def build_ref(ref="/root/reference"):
     return harness
 
 
+def build_plugin(ref="/root/reference"):
+    """libB200LinearSolvers.so: the OpenFOAM plugin shim, compiled against the reference headers (build container
+    only; the built .so travels to the GPU box together with oracle/_ref/libOpenFOAM.so)."""
+    refdir = ROOT / "oracle" / "_ref"
+    if not (refdir / "lnInclude").exists() or not Path(ref, "src/OpenFOAM").exists():
+        return None
+    src = PKG / "plugin" / "B200Solvers.C"
+    out = PKG / "libB200LinearSolvers.so"
+    if _newer(out, [src, ROOT / "include" / "b200ls.h", LIB]):
+        return out
+    subprocess.check_call([
+        "g++", "-std=c++14", "-m64", "-Dlinux64", "-DWM_ARCH_OPTION=64", "-DWM_DP", "-DWM_LABEL_SIZE=32", "-O2",
+        "-DNoRepository", "-ftemplate-depth-256", "-fPIC", "-w", f"-I{refdir / 'lnInclude'}", f"-I{ROOT / 'include'}",
+        "-shared", str(src), "-o", str(out), f"-L{PKG}", "-lb200ls", f"-L{refdir}", "-lOpenFOAM",
+        "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../oracle/_ref",
+    ])
+    return out
+
+
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_oracle()

@@ -24,7 +24,7 @@ PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "Gauss
 EXPORTS = [
     "b200ls_init", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
     "b200ls_mesh_create", "b200ls_mesh_free", "b200ls_mesh_get_i32", "b200ls_mesh_n_levels",
-    "b200ls_agglomerate", "b200ls_matrix_create", "b200ls_matrix_free", "b200ls_matrix_set",
+    "b200ls_agglomerate", "b200ls_agglomerate_from_maps", "b200ls_matrix_create", "b200ls_matrix_free", "b200ls_matrix_set",
     "b200ls_amul", "b200ls_residual", "b200ls_sum_a", "b200ls_precondition", "b200ls_reciprocal_d",
     "b200ls_smooth", "b200ls_controls_default", "b200ls_solve", "b200ls_solve_dev", "b200ls_time_kernel",
 ]
@@ -77,6 +77,7 @@ def lib():
     L.b200ls_mesh_get_i32.argtypes = [p, C.c_int, C.c_int, C.POINTER(p), C.POINTER(i64)]
     L.b200ls_mesh_n_levels.argtypes = [p]
     L.b200ls_agglomerate.argtypes = [p, p, i32, i32, i32]
+    L.b200ls_agglomerate_from_maps.argtypes = [p, i32, p, p]
     L.b200ls_matrix_create.restype = p
     L.b200ls_matrix_create.argtypes = [p]
     L.b200ls_matrix_free.argtypes = [p]
@@ -189,6 +190,16 @@ class Mesh:
     def agglomerate(self, face_weights, min_cells_per_processor=10, merge_levels=1, forward_start=1):
         w = _f64(face_weights)
         n = lib().b200ls_agglomerate(self.h, _ptr(w), min_cells_per_processor, merge_levels, forward_start)
+        if n < 0:
+            raise B200Error(lib().b200ls_last_error().decode())
+        return n
+
+
+    def agglomerate_from_maps(self, restrict_maps):
+        maps = [_i32(m) for m in restrict_maps]
+        n_coarse = _i32([int(m.max()) + 1 for m in maps])
+        ptrs = (C.c_void_p * max(len(maps), 1))(*[m.ctypes.data for m in maps])
+        n = lib().b200ls_agglomerate_from_maps(self.h, len(maps), C.cast(ptrs, C.c_void_p), _ptr(n_coarse))
         if n < 0:
             raise B200Error(lib().b200ls_last_error().decode())
         return n

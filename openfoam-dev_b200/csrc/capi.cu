@@ -191,6 +191,18 @@ int b200ls_agglomerate(b200ls_mesh_t mesh, const double* faceWeights, int32_t mi
     return rc == 0 ? nCoarse : -1;
 }
 
+int b200ls_agglomerate_from_maps(b200ls_mesh_t mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
+                                 const int32_t* nCoarseCells) {
+    int n = -1;
+    int rc = guarded([&] {
+        if (!mesh) throw CudaError("null mesh");
+        n = agglomerateFromMaps(mesh->host, nCoarseLevels, restrictAddr, nCoarseCells);
+        mesh->dev.reset();
+        mesh->generation++;
+    });
+    return rc == 0 ? n : -1;
+}
+
 b200ls_matrix_t b200ls_matrix_create(b200ls_mesh_t mesh) {
     if (!mesh) {
         g_lastError = "null mesh";

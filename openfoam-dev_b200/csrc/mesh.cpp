@@ -403,12 +403,35 @@ void buildMaps(LevelHost& fine, const LevelHost& coarse) {
 
 }  // namespace
 
+// Append the coarse level defined by `map` (fine cell -> coarse cell) below the current coarsest level:
+// agglomerateLduAddressing + native layout + transfer maps.
+static void appendCoarseLevel(HostMesh& mesh, std::vector<int32_t> map, int32_t nCoarse) {
+    const size_t k = mesh.levels.size() - 1;
+    {
+        LevelHost& fine = mesh.levels[k];
+        if (int32_t(map.size()) != fine.nCells) throw std::runtime_error("restrict map size != fine level size");
+        for (int32_t v : map)
+            if (v < 0 || v >= nCoarse) throw std::runtime_error("restrict map entry out of range");
+        if (!fine.interfaces.empty()) {
+            throw std::runtime_error("agglomeration with processor interfaces is not supported yet");
+        }
+        fine.hasCoarse = true;
+        fine.nCoarseCells = nCoarse;
+        fine.restrictAddr = std::move(map);
+        fine.patchFaceRestrictAddr.assign(fine.interfaces.size(), {});
+    }
+    std::vector<int32_t> cLower, cUpper;
+    agglomerateAddressing(mesh.levels[k], cLower, cUpper);
+    mesh.levels.emplace_back();   // may move the storage: re-take references
+    LevelHost& fine = mesh.levels[k];
+    LevelHost& coarse = mesh.levels[k + 1];
+    buildLevel(coarse, nCoarse, int32_t(cLower.size()), cLower.data(), cUpper.data(), {});
+    buildMaps(fine, coarse);
+}
+
 int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
                 bool& forward) {
     if (mergeLevels != 1) throw std::runtime_error("mergeLevels != 1 is not supported");
-    if (mesh.nRanks != 1 && !mesh.levels[0].interfaces.empty()) {
-        // multi-rank agglomeration needs the neighbour restrictMap exchange; see capi multi-rank path
-    }
     mesh.levels.resize(1);
     mesh.levels[0].hasCoarse = false;
     mesh.agglomerated = false;
@@ -418,47 +441,41 @@ int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerPr
 
     int nCreated = 0;
     while (nCreated < maxLevels - 1) {
-        LevelHost& fine = mesh.levels[nCreated];
         int32_t nCoarse = -1;
-        std::vector<int32_t> map = pairAgglomerate(nCoarse, fine, w, forward);
+        std::vector<int32_t> map = pairAgglomerate(nCoarse, mesh.levels[nCreated], w, forward);
 
         // continueAgglomerating (single rank: global sums are local values)
         const int64_t totalCoarse = nCoarse;
-        const int64_t totalFine = fine.nCells;
+        const int64_t totalFine = mesh.levels[nCreated].nCells;
         if (totalCoarse < int64_t(mesh.nRanks) * minCellsPerProcessor || !(totalCoarse < totalFine)) break;
 
-        fine.hasCoarse = true;
-        fine.nCoarseCells = nCoarse;
-        fine.restrictAddr = std::move(map);
-
-        std::vector<int32_t> cLower, cUpper;
-        agglomerateAddressing(fine, cLower, cUpper);
-
-        // coarse interfaces: single-rank meshes have none
-        std::vector<HostInterface> coarseIfaces;
-        fine.patchFaceRestrictAddr.assign(fine.interfaces.size(), {});
-        if (!fine.interfaces.empty()) {
-            throw std::runtime_error("agglomeration with processor interfaces needs b200ls_agglomerate_parallel");
-        }
-
-        mesh.levels.emplace_back();
-        LevelHost& fineRef = mesh.levels[nCreated];   // emplace_back may have moved the storage
-        LevelHost& coarse = mesh.levels[nCreated + 1];
-        buildLevel(coarse, nCoarse, int32_t(cLower.size()), cLower.data(), cUpper.data(), std::move(coarseIfaces));
+        appendCoarseLevel(mesh, std::move(map), nCoarse);
 
         // restrictFaceField of the weights for the next level (sequential adds in fine-face order)
-        std::vector<double> cw(coarse.nFaces, 0.0);
-        for (int32_t f = 0; f < fineRef.nFaces; f++) {
-            const int32_t cf = fineRef.faceRestrictAddr[f];
+        const LevelHost& fine = mesh.levels[nCreated];
+        std::vector<double> cw(mesh.levels[nCreated + 1].nFaces, 0.0);
+        for (int32_t f = 0; f < fine.nFaces; f++) {
+            const int32_t cf = fine.faceRestrictAddr[f];
             if (cf >= 0) cw[cf] += w[f];
         }
         w.swap(cw);
-
-        buildMaps(fineRef, coarse);
         nCreated++;
     }
     mesh.agglomerated = true;
     return nCreated;
+}
+
+int agglomerateFromMaps(HostMesh& mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
+                        const int32_t* nCoarseCells) {
+    mesh.levels.resize(1);
+    mesh.levels[0].hasCoarse = false;
+    mesh.agglomerated = false;
+    for (int32_t k = 0; k < nCoarseLevels; k++) {
+        const int32_t nFine = mesh.levels[k].nCells;
+        appendCoarseLevel(mesh, std::vector<int32_t>(restrictAddr[k], restrictAddr[k] + nFine), nCoarseCells[k]);
+    }
+    mesh.agglomerated = true;
+    return nCoarseLevels;
 }
 
 }  // namespace b200ls

@@ -85,4 +85,9 @@ std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fin
 int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
                 bool& forward);
 
+// Levels supplied by the caller (the plugin passes GAMGAgglomeration::restrictAddressing(level) of the reference's
+// own cached agglomeration object); everything derived from them is rebuilt here.
+int agglomerateFromMaps(HostMesh& mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
+                        const int32_t* nCoarseCells);
+
 }  // namespace b200ls

@@ -1,0 +1,543 @@
+/*---------------------------------------------------------------------------*\
+  libB200LinearSolvers -- OpenFOAM-dev plugin: lduMatrix solvers running on a
+  B200 through libb200ls (include/b200ls.h).
+
+  Selected with only the fvSolution `solver` keyword and a controlDict `libs`
+  entry:
+
+      // system/controlDict
+      libs ("libB200LinearSolvers.so");
+
+      // system/fvSolution
+      p { solver B200PCG;  preconditioner DIC;  tolerance 1e-6; relTol 0.01; }
+      U { solver B200PBiCGStab; preconditioner DILU; tolerance 1e-5; relTol 0.1; }
+      p { solver B200GAMG; smoother GaussSeidel; tolerance 1e-6; relTol 0.01; }
+
+  Registration follows the reference's own pattern (PCG.C:34-35,
+  PBiCGStab.C:34-38, GAMGSolver.C:38-42): namespace-scope
+  lduMatrix::solver::add{sym,asym}MatrixConstructorToTable<T> objects insert
+  T::typeName -> T::New into the run-time selection tables when the library is
+  dlopen'ed by Time (db/Time/Time.C:403 -> dlLibraryTable::open).
+
+  This file holds no arithmetic: it marshals the lduMatrix the solver was
+  constructed with (lduMatrix.H:187-195) into the C-ABI and the returned
+  b200ls_perf into a solverPerformance.  Everything persistent lives in a
+  process-level cache keyed on the lduAddressing object, because OpenFOAM
+  constructs a new solver for every solve (fvScalarMatrix.C:162-170).
+\*---------------------------------------------------------------------------*/
+
+#include "lduMatrix.H"
+#include "processorLduInterface.H"
+#include "GAMGAgglomeration.H"
+#include "addToRunTimeSelectionTable.H"
+#include "Pstream.H"
+#include "OSspecific.H"
+
+#include "b200ls.h"
+
+#include <map>
+#include <vector>
+#include <cstdlib>
+
+namespace Foam
+{
+
+// ---------------------------------------------------------------------------
+// process-level state
+// ---------------------------------------------------------------------------
+
+namespace B200
+{
+
+struct cacheEntry
+{
+    b200ls_mesh_t mesh;
+    b200ls_matrix_t matrix;
+    label nCells;
+    label nFaces;
+    bool agglomerated;
+
+    cacheEntry()
+    :
+        mesh(nullptr),
+        matrix(nullptr),
+        nCells(-1),
+        nFaces(-1),
+        agglomerated(false)
+    {}
+};
+
+static std::map<const lduAddressing*, cacheEntry> cache_;
+static bool initialised_ = false;
+
+
+static void check(const int rc, const char* what)
+{
+    if (rc != 0)
+    {
+        FatalErrorInFunction
+            << what << " failed: " << b200ls_last_error()
+            << exit(FatalError);
+    }
+}
+
+
+//- One process per GPU: device = local rank modulo visible devices unless
+//  B200LS_DEVICE is set.  In parallel the NCCL id is created on the master
+//  and scattered through Pstream.
+static void init()
+{
+    if (initialised_) return;
+
+    int device = 0;
+    if (const char* s = getenv("B200LS_DEVICE"))
+    {
+        device = atoi(s);
+    }
+    else if (const char* s = getenv("OMPI_COMM_WORLD_LOCAL_RANK"))
+    {
+        device = atoi(s);
+    }
+    else if (const char* s = getenv("MPI_LOCALRANKID"))
+    {
+        device = atoi(s);
+    }
+
+    if (Pstream::parRun())
+    {
+        List<char> id(128, '\0');
+        if (Pstream::master())
+        {
+            check(b200ls_nccl_unique_id(id.begin()), "b200ls_nccl_unique_id");
+        }
+        Pstream::scatter(id);
+        check
+        (
+            b200ls_init(device, id.begin(), Pstream::myProcNo(), Pstream::nProcs()),
+            "b200ls_init"
+        );
+    }
+    else
+    {
+        check(b200ls_init(device, nullptr, 0, 1), "b200ls_init");
+    }
+
+    initialised_ = true;
+}
+
+
+static int preconditionerId(const word& name)
+{
+    if (name == "DIC") return B200LS_DIC;
+    if (name == "DILU") return B200LS_DILU;
+    if (name == "diagonal") return B200LS_DIAGONAL;
+    if (name == "none") return B200LS_NONE;
+    if (name == "GaussSeidel") return B200LS_GAUSS_SEIDEL;
+
+    FatalErrorInFunction
+        << "preconditioner/smoother " << name
+        << " is not provided by libB200LinearSolvers."
+        << " Valid: DIC DILU diagonal none (preconditioners),"
+        << " GaussSeidel DIC DILU (smoothers)"
+        << exit(FatalError);
+    return -1;
+}
+
+} // End namespace B200
+
+
+// ---------------------------------------------------------------------------
+// common base: marshalling
+// ---------------------------------------------------------------------------
+
+class B200SolverBase
+:
+    public lduMatrix::solver
+{
+protected:
+
+    //- Mesh/matrix handles for this solver's addressing (created on demand)
+    B200::cacheEntry& entry() const
+    {
+        B200::init();
+
+        const lduAddressing& addr = matrix_.lduAddr();
+        B200::cacheEntry& e = B200::cache_[&addr];
+
+        const label nCells = addr.size();
+        const label nFaces = addr.lowerAddr().size();
+
+        if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces))
+        {
+            // mesh changed under the same address: rebuild
+            b200ls_matrix_free(e.matrix);
+            b200ls_mesh_free(e.mesh);
+            e = B200::cacheEntry();
+        }
+
+        if (!e.mesh)
+        {
+            std::vector<int32_t> sizes, nbr;
+            std::vector<const int32_t*> faceCells;
+
+            forAll(interfaces_, patchi)
+            {
+                if (interfaces_.set(patchi))
+                {
+                    const lduInterface& li = interfaces_[patchi].interface();
+                    if (!isA<processorLduInterface>(li))
+                    {
+                        FatalErrorInFunction
+                            << "coupled patch " << patchi << " of type "
+                            << li.type() << " is not a processor interface:"
+                            << " only processor patches are supported"
+                            << exit(FatalError);
+                    }
+                    const labelUList& fc = li.faceCells();
+                    sizes.push_back(fc.size());
+                    faceCells.push_back(fc.begin());
+                    nbr.push_back
+                    (
+                        refCast<const processorLduInterface>(li).neighbProcNo()
+                    );
+                }
+            }
+
+            e.mesh = b200ls_mesh_create
+            (
+                nCells,
+                nFaces,
+                addr.lowerAddr().begin(),
+                addr.upperAddr().begin(),
+                sizes.size(),
+                sizes.data(),
+                faceCells.data(),
+                nbr.data()
+            );
+            if (!e.mesh)
+            {
+                FatalErrorInFunction
+                    << "b200ls_mesh_create failed: " << b200ls_last_error()
+                    << exit(FatalError);
+            }
+            e.matrix = b200ls_matrix_create(e.mesh);
+            e.nCells = nCells;
+            e.nFaces = nFaces;
+        }
+
+        return e;
+    }
+
+    //- Upload the coefficients this solver object was constructed with
+    void upload(B200::cacheEntry& e) const
+    {
+        std::vector<const double*> bou, inn;
+        forAll(interfaces_, patchi)
+        {
+            if (interfaces_.set(patchi))
+            {
+                bou.push_back(interfaceBouCoeffs_[patchi].begin());
+                inn.push_back(interfaceIntCoeffs_[patchi].begin());
+            }
+        }
+
+        B200::check
+        (
+            b200ls_matrix_set
+            (
+                e.matrix,
+                matrix_.diag().begin(),
+                matrix_.upper().begin(),
+                matrix_.asymmetric() ? matrix_.lower().begin() : nullptr,
+                bou.data(),
+                inn.data()
+            ),
+            "b200ls_matrix_set"
+        );
+    }
+
+    //- Run the solve and translate the result
+    solverPerformance run
+    (
+        const word& solverName,
+        b200ls_controls& c,
+        scalarField& psi,
+        const scalarField& source
+    ) const
+    {
+        B200::cacheEntry& e = entry();
+        upload(e);
+
+        c.tolerance = tolerance_;
+        c.relTol = relTol_;
+        c.maxIter = maxIter_;
+        c.minIter = minIter_;
+
+        b200ls_perf* perf = new b200ls_perf;
+        B200::check
+        (
+            b200ls_solve(e.matrix, &c, psi.begin(), source.begin(), perf),
+            "b200ls_solve"
+        );
+
+        solverPerformance solverPerf(solverName, fieldName_);
+        solverPerf.initialResidual() = perf->initialResidual;
+        solverPerf.finalResidual() = perf->finalResidual;
+        solverPerf.nIterations() = perf->nIterations;
+        solverPerf.checkConvergence(tolerance_, relTol_);
+        if (perf->singular)
+        {
+            solverPerf.checkSingularity(0);
+        }
+        delete perf;
+
+        return solverPerf;
+    }
+
+
+public:
+
+    B200SolverBase
+    (
+        const word& fieldName,
+        const lduMatrix& matrix,
+        const Field<Field<scalar>>& interfaceBouCoeffs,
+        const Field<Field<scalar>>& interfaceIntCoeffs,
+        const lduInterfaceFieldPtrsList& interfaces,
+        const dictionary& solverControls
+    )
+    :
+        lduMatrix::solver
+        (
+            fieldName,
+            matrix,
+            interfaceBouCoeffs,
+            interfaceIntCoeffs,
+            interfaces,
+            solverControls
+        )
+    {}
+
+    virtual ~B200SolverBase()
+    {}
+};
+
+
+// ---------------------------------------------------------------------------
+// B200PCG  (drop-in for PCG, solvers/PCG/PCG.C)
+// ---------------------------------------------------------------------------
+
+class B200PCG
+:
+    public B200SolverBase
+{
+public:
+
+    TypeName("B200PCG");
+
+    using B200SolverBase::B200SolverBase;
+
+    virtual solverPerformance solve
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt = 0
+    ) const
+    {
+        const word precon(lduMatrix::preconditioner::getName(controlDict_));
+        b200ls_controls c;
+        b200ls_controls_default(&c);
+        c.solver = B200LS_PCG;
+        c.precond = B200::preconditionerId(precon);
+        return run(precon + "PCG", c, psi, source);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// B200PBiCGStab  (drop-in for PBiCGStab, solvers/PBiCGStab/PBiCGStab.C)
+// ---------------------------------------------------------------------------
+
+class B200PBiCGStab
+:
+    public B200SolverBase
+{
+public:
+
+    TypeName("B200PBiCGStab");
+
+    using B200SolverBase::B200SolverBase;
+
+    virtual solverPerformance solve
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt = 0
+    ) const
+    {
+        const word precon(lduMatrix::preconditioner::getName(controlDict_));
+        b200ls_controls c;
+        b200ls_controls_default(&c);
+        c.solver = B200LS_PBICGSTAB;
+        c.precond = B200::preconditionerId(precon);
+        return run(precon + "PBiCGStab", c, psi, source);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// B200smoothSolver  (drop-in for smoothSolver)
+// ---------------------------------------------------------------------------
+
+class B200smoothSolver
+:
+    public B200SolverBase
+{
+public:
+
+    TypeName("B200smoothSolver");
+
+    using B200SolverBase::B200SolverBase;
+
+    virtual solverPerformance solve
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt = 0
+    ) const
+    {
+        b200ls_controls c;
+        b200ls_controls_default(&c);
+        c.solver = B200LS_SMOOTH_SOLVER;
+        c.precond = B200::preconditionerId(word(controlDict_.lookup("smoother")));
+        c.nSweeps = controlDict_.lookupOrDefault<label>("nSweeps", 1);
+        return run("smoothSolver", c, psi, source);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// B200GAMG  (drop-in for GAMG, solvers/GAMG/GAMGSolver*.C)
+//
+// The agglomeration is the reference's own cached MeshObject
+// (GAMGAgglomeration::New, GAMGAgglomeration.C:349-400: faceAreaPair by default);
+// only its restrictAddressing per level crosses the C-ABI, everything derived is
+// rebuilt (and checked bit-exact against the reference) inside libb200ls.
+// ---------------------------------------------------------------------------
+
+class B200GAMG
+:
+    public B200SolverBase
+{
+public:
+
+    TypeName("B200GAMG");
+
+    using B200SolverBase::B200SolverBase;
+
+    virtual solverPerformance solve
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt = 0
+    ) const
+    {
+        B200::cacheEntry& e = entry();
+
+        if (!e.agglomerated)
+        {
+            const GAMGAgglomeration& agg =
+                GAMGAgglomeration::New(matrix_, controlDict_);
+
+            std::vector<const int32_t*> maps;
+            std::vector<int32_t> nCoarse;
+            for (label lev = 0; lev < agg.size(); lev++)
+            {
+                maps.push_back(agg.restrictAddressing(lev).begin());
+                nCoarse.push_back(agg.nCells(lev));
+            }
+            if
+            (
+                b200ls_agglomerate_from_maps
+                (
+                    e.mesh,
+                    maps.size(),
+                    maps.data(),
+                    nCoarse.data()
+                ) < 0
+            )
+            {
+                FatalErrorInFunction
+                    << "b200ls_agglomerate_from_maps failed: "
+                    << b200ls_last_error() << exit(FatalError);
+            }
+            e.agglomerated = true;
+        }
+
+        b200ls_controls c;
+        b200ls_controls_default(&c);
+        c.solver = B200LS_GAMG;
+        c.precond = B200::preconditionerId(word(controlDict_.lookup("smoother")));
+
+        // GAMGSolver::readControls (GAMGSolver.C:348-371)
+        c.nPreSweeps = controlDict_.lookupOrDefault<label>("nPreSweeps", 0);
+        c.preSweepsLevelMultiplier =
+            controlDict_.lookupOrDefault<label>("preSweepsLevelMultiplier", 1);
+        c.maxPreSweeps = controlDict_.lookupOrDefault<label>("maxPreSweeps", 4);
+        c.nPostSweeps = controlDict_.lookupOrDefault<label>("nPostSweeps", 2);
+        c.postSweepsLevelMultiplier =
+            controlDict_.lookupOrDefault<label>("postSweepsLevelMultiplier", 1);
+        c.maxPostSweeps = controlDict_.lookupOrDefault<label>("maxPostSweeps", 4);
+        c.nFinestSweeps = controlDict_.lookupOrDefault<label>("nFinestSweeps", 2);
+        c.scaleCorrection =
+            controlDict_.lookupOrDefault<Switch>
+            (
+                "scaleCorrection",
+                matrix_.symmetric()
+            );
+
+        if (controlDict_.lookupOrDefault<Switch>("interpolateCorrection", false))
+        {
+            FatalErrorInFunction
+                << "interpolateCorrection is not supported by B200GAMG"
+                << exit(FatalError);
+        }
+        if (controlDict_.lookupOrDefault<Switch>("directSolveCoarsest", false))
+        {
+            FatalErrorInFunction
+                << "directSolveCoarsest is not supported by B200GAMG"
+                << exit(FatalError);
+        }
+
+        return run("GAMG", c, psi, source);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
+// run-time selection
+// ---------------------------------------------------------------------------
+
+defineTypeNameAndDebug(B200PCG, 0);
+lduMatrix::solver::addsymMatrixConstructorToTable<B200PCG>
+    addB200PCGSymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200PBiCGStab, 0);
+lduMatrix::solver::addsymMatrixConstructorToTable<B200PBiCGStab>
+    addB200PBiCGStabSymMatrixConstructorToTable_;
+lduMatrix::solver::addasymMatrixConstructorToTable<B200PBiCGStab>
+    addB200PBiCGStabAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200smoothSolver, 0);
+lduMatrix::solver::addsymMatrixConstructorToTable<B200smoothSolver>
+    addB200smoothSolverSymMatrixConstructorToTable_;
+lduMatrix::solver::addasymMatrixConstructorToTable<B200smoothSolver>
+    addB200smoothSolverAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200GAMG, 0);
+lduMatrix::solver::addsymMatrixConstructorToTable<B200GAMG>
+    addB200GAMGSymMatrixConstructorToTable_;
+lduMatrix::solver::addasymMatrixConstructorToTable<B200GAMG>
+    addB200GAMGAsymMatrixConstructorToTable_;
+
+} // End namespace Foam

@@ -1,0 +1,51 @@
+"""Drop-in test: the UNMODIFIED reference (oracle/_ref/ref_harness -> lduMatrix::solver::New) loads
+libB200LinearSolvers.so through its own `libs` mechanism (dlLibraryTable) and selects B200PCG / B200PBiCGStab /
+B200GAMG / B200smoothSolver by name from its run-time selection tables -- exactly what a case does with
+`libs ("libB200LinearSolvers.so");` in controlDict and `solver B200PCG;` in fvSolution.  Results are compared with
+the reference's own solvers on the same matrix (the golden fixtures)."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from _util import FIXTURES, ldu_io, load_fixture, max_rel_diff, solve_keys
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+HARNESS = ROOT / "oracle/_ref/ref_harness"
+PLUGIN = ROOT / "openfoam-dev_b200/libB200LinearSolvers.so"
+
+
+@pytest.mark.parametrize("name", ["cavity_20x20x1", "block_16x16x16_rand", "convdiff_9x8x7"])
+def test_reference_selects_b200_solvers_by_name(name, tmp_path):
+    if not HARNESS.exists() or not PLUGIN.exists():
+        pytest.skip("oracle/_ref or the plugin was not built (needs /root/reference at build time)")
+    inp, ref = load_fixture(name)
+    e = {k: v for k, v in inp.items() if not k.startswith(("solve.", "smooth.", "agglomerate", "x"))}
+    e["libs"] = f'"{PLUGIN}"'
+    texts = []
+    for i, text in solve_keys(inp):
+        t = text.replace("solver PCG", "solver B200PCG").replace("solver PBiCGStab", "solver B200PBiCGStab")
+        t = t.replace("solver GAMG", "solver B200GAMG").replace("solver smoothSolver", "solver B200smoothSolver")
+        e[f"solve.{i}.dict"] = t
+        texts.append(t)
+    ldu_io.write(str(tmp_path / "in.b2ls"), e)
+    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle/foam_env"), WM_PROJECT="OpenFOAM",
+               WM_PROJECT_VERSION="dev")
+    r = subprocess.run([str(HARNESS), str(tmp_path / "in.b2ls"), str(tmp_path / "out.b2ls"), str(tmp_path / "case")],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = ldu_io.read(str(tmp_path / "out.b2ls"))
+    for i, t in enumerate(texts):
+        got, want = out[f"solve.{i}.perf"], ref[f"solve.{i}.perf"]
+        ctx = (name, t, got[:3], want[:3])
+        assert ldu_io.as_str(out[f"solve.{i}.solverName"]) == ldu_io.as_str(ref[f"solve.{i}.solverName"]), ctx
+        assert abs(got[2] - want[2]) <= 1, ctx
+        assert abs(got[0] - want[0]) <= 1e-9 * abs(want[0]), ctx
+        if got[2] == want[2]:
+            assert abs(got[1] - want[1]) <= 1e-9 * abs(want[0]), ctx
+            assert max_rel_diff(out[f"solve.{i}.psi"], ref[f"solve.{i}.psi"]) <= 1e-9, ctx
+            assert got[3] == want[3], ctx

@@ -162,3 +162,18 @@ def test_decomposed_operator_equals_global_operator():
             recv = x[maps[itf.neighb_rank]][back.face_cells]
             np.subtract.at(y, itf.face_cells, itf.bou_coeffs * recv)
         assert np.allclose(y, yg[m], rtol=1e-14, atol=1e-14)
+
+
+def test_agglomerate_from_reference_maps():
+    """Levels rebuilt from the reference's restrictAddressing alone reproduce its face maps and coarse addressing."""
+    inp, ref = load_fixture("block_16x16x16_rand")
+    s = system_from_entries(inp)
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    n = int(ref["agg.nLevels"][0])
+    assert mesh.agglomerate_from_maps([ref[f"agg.{k}.restrictAddressing"] for k in range(n)]) == n
+    for lev in range(n):
+        k = f"agg.{lev}."
+        assert np.array_equal(mesh.get_i32(capi.FACE_RESTRICT_ADDRESSING, lev), ref[k + "faceRestrictAddressing"])
+        assert np.array_equal(mesh.get_i32(capi.FACE_FLIP_MAP, lev), ref[k + "faceFlipMap"].astype(np.int32))
+        assert np.array_equal(mesh.get_i32(capi.LOWER_ADDR, lev + 1), ref[k + "coarseLower"])
+        assert np.array_equal(mesh.get_i32(capi.UPPER_ADDR, lev + 1), ref[k + "coarseUpper"])
