@@ -1,0 +1,92 @@
+"""Worker of tests/test_gpu_multi.py: one rank per GPU under torch.distributed.run."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _pkg import load_pkg  # noqa: E402
+
+load_pkg()
+from b200ls import capi, cases, decompose  # noqa: E402
+
+
+def dense(sys_):
+    a = np.diag(sys_.diag.copy())
+    lo_c = sys_.upper_coeffs if sys_.lower_coeffs is None else sys_.lower_coeffs
+    a[sys_.upper, sys_.lower] += lo_c
+    a[sys_.lower, sys_.upper] += sys_.upper_coeffs
+    return a
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    capi.init(local, bytes(buf.cpu().numpy().tobytes()), rank, world)
+
+    split = decompose.simple_split(world)
+    nx, ny, nz = 8 * split[0], 6 * split[1], 5 * split[2]
+    ok = True
+    for kind in ("sym", "asym"):
+        glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if kind == "sym" else \
+            cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
+        parts, maps = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), world)
+        part, cells = parts[rank], maps[rank]
+        mesh, mat = capi.from_system(part)
+        A = dense(glob)
+        x = np.cos(0.3 * np.arange(glob.n_cells))
+
+        def gather(local_vec):
+            t = torch.zeros(glob.n_cells, dtype=torch.float64, device="cuda")
+            t[torch.from_numpy(cells).cuda()] = torch.from_numpy(local_vec).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+        y = gather(mat.amul(x[cells]))
+        err = np.max(np.abs(y - A @ x)) / np.max(np.abs(A @ x))
+        r = gather(mat.residual(x[cells], glob.source[cells]))
+        err_r = np.max(np.abs(r - (glob.source - A @ x))) / np.max(np.abs(glob.source))
+        ok &= err < 1e-14 and err_r < 1e-14
+        if rank == 0:
+            print(f"{kind}: amul rel err {err:.2e} residual rel err {err_r:.2e}", flush=True)
+
+        exact = np.linalg.solve(A, glob.source)
+        combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
+        if kind == "asym":   # Gauss-Seidel alone converges far too slowly on the Laplacian to pin a solution
+            combos.append(("smoothSolver", "GaussSeidel"))
+        for solver, pre in combos:
+            kw = dict(tolerance=1e-13, relTol=0.0, maxIter=2000)
+            ctl = capi.controls(solver, preconditioner=pre, **kw) if solver != "smoothSolver" else \
+                capi.controls(solver, smoother=pre, nSweeps=4, **kw)
+            psi, perf = mat.solve(ctl, part.source)
+            full = gather(psi)
+            e = np.max(np.abs(full - exact)) / np.max(np.abs(exact))
+            its = torch.tensor([perf.nIterations], device="cuda")
+            lo, hi = its.clone(), its.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            good = e < 1e-9 and int(lo) == int(hi) and perf.converged
+            ok &= bool(good)
+            if rank == 0:
+                print(f"{kind}: {solver}+{pre}: iterations {perf.nIterations} solution rel err {e:.2e} "
+                      f"converged {perf.converged} {'OK' if good else 'FAIL'}", flush=True)
+        mat.close()
+        mesh.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_OK" if int(flag) else "MGPU_FAIL", flush=True)
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
