@@ -109,7 +109,7 @@ def run_reference_sample(sys_, iters):
 
     harness = ROOT / "oracle/_ref/ref_harness"
     if not harness.exists():
-        return None
+        return None      # callers fall back to the C port of the oracle
     e = cases.to_entries(sys_)
     e.pop("faceWeights", None)
     e["solve.0.dict"] = f"solver PCG; preconditioner DIC; tolerance 0; relTol 0; maxIter {iters};"

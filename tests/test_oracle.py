@@ -1,0 +1,76 @@
+"""Pins the C oracle (oracle/ldu_oracle.c) against outputs of the unmodified reference (tests/golden/*.b2ls).
+The oracle restates the reference's sequential face loops and summation order, so everything -- including Krylov
+histories and iteration counts -- must agree bit for bit (both are compiled without FMA contraction)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from _util import FIXTURES, ldu_io, load_fixture, parse_dict, smooth_keys, solve_keys, system_from_entries
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+import ldu_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=FIXTURES)
+def fx(request):
+    inp, ref = load_fixture(request.param)
+    s = system_from_entries(inp)
+    return request.param, inp, ref, s, orc.System(s)
+
+
+def test_operators(fx):
+    name, inp, ref, s, S = fx
+    assert np.array_equal(orc.amul(S, inp["x"]), ref["Amul"])
+    assert np.array_equal(orc.residual(S, inp["x"], s.source), ref["residual"])
+    assert np.array_equal(orc.sum_a(S), ref["sumA"])
+    assert np.array_equal(orc.losort(S), ref["losort"])
+
+
+def test_preconditioners(fx):
+    name, inp, ref, s, S = fx
+    kind = "DIC" if s.symmetric else "DILU"
+    assert np.array_equal(orc.reciprocal_d(S), ref[f"{kind}_rD"])
+    assert np.array_equal(orc.precondition(S, kind, inp["x"]), ref["precondition"])
+
+
+def test_smoothers(fx):
+    name, inp, ref, s, S = fx
+    for i, kind, n_sweeps in smooth_keys(inp):
+        assert np.array_equal(orc.smooth(S, kind, inp["x"], s.source, n_sweeps), ref[f"smooth.{i}.psi"]), (name, kind)
+
+
+def test_agglomeration(fx):
+    name, inp, ref, s, S = fx
+    if "agg.nLevels" not in ref:
+        pytest.skip("fixture without agglomeration dump")
+    levels = orc.agglomeration(S)
+    assert len(levels) == int(ref["agg.nLevels"][0])
+    for k, (ra, fra, ff, cl, cu) in enumerate(levels):
+        p = f"agg.{k}."
+        assert np.array_equal(ra, ref[p + "restrictAddressing"])
+        assert np.array_equal(fra, ref[p + "faceRestrictAddressing"])
+        assert np.array_equal(ff, ref[p + "faceFlipMap"].astype(np.int32))
+        assert np.array_equal(cl, ref[p + "coarseLower"]) and np.array_equal(cu, ref[p + "coarseUpper"])
+
+
+def test_solvers_bit_exact(fx):
+    name, inp, ref, s, S = fx
+    for i, text in solve_keys(inp):
+        d = parse_dict(text)
+        kw = {k: (float(v) if k in ("tolerance", "relTol") else int(v)) for k, v in d.items()
+              if k not in ("solver", "preconditioner", "smoother")}
+        ctl = orc.controls(precond=d.get("preconditioner") or d.get("smoother"), **kw)
+        psi, perf = orc.solve(S, d["solver"], ctl, s.source)
+        rperf = ref[f"solve.{i}.perf"]
+        ctx = (name, text, perf["nIterations"], rperf[2], perf["finalResidual"], rperf[1])
+        assert perf["nIterations"] == int(rperf[2]), ctx
+        assert perf["initialResidual"] == rperf[0], ctx
+        assert perf["finalResidual"] == rperf[1], ctx
+        assert perf["converged"] == bool(rperf[3]), ctx
+        assert np.array_equal(psi, ref[f"solve.{i}.psi"]), ctx
+        hkey = f"solve.{i}.historyResiduals"
+        if hkey in ref:
+            n = min(len(perf["history"]), len(ref[hkey]), int(rperf[2]))
+            assert np.array_equal(perf["history"][:n], ref[hkey][:n]), ctx
