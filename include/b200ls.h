@@ -51,6 +51,16 @@ const char* b200ls_last_error(void);
 /* 1 if a CUDA device is usable by this process, else 0 (no error is recorded). */
 int b200ls_device_available(void);
 
+/* Optional host-side communicator for the once-per-mesh agglomeration of a DECOMPOSED mesh: the neighbour
+ * exchange of restrictMap over each processor patch (GAMGAgglomerateLduAddressing.C:268-283) and the global sums of
+ * continueAgglomerating (GAMGAgglomeration.C:211-229).  exchange(): send[i] (sizes[i] labels) goes to rank nbr[i],
+ * recv[i] receives as many from it.  Without it (default) the library uses NCCL on small staging buffers.
+ * Pass NULL callbacks to unset. */
+typedef void (*b200ls_exchange_fn)(int32_t nIfaces, const int32_t* nbr, const int32_t* sizes,
+                                   const int32_t* const* send, int32_t* const* recv);
+typedef int64_t (*b200ls_sum_fn)(int64_t localValue);
+int b200ls_set_host_comm(int32_t rank, int32_t nRanks, b200ls_exchange_fn exchange, b200ls_sum_fn sum);
+
 /* ---- mesh (cached per lduAddressing by the caller) ---------------------------------------------- */
 
 /* Host analysis only (no device work): losort/ownerStart/losortStart, forward/backward wavefronts,
@@ -82,7 +92,14 @@ enum b200ls_i32_which {
  * RESTRICT_ADDRESSING / FACE_RESTRICT_ADDRESSING / FACE_FLIP_MAP at `level` map level -> level+1,
  * as in the reference.  The pointer stays valid until the mesh is freed or re-agglomerated. */
 int b200ls_mesh_get_i32(b200ls_mesh_t mesh, int which, int level, const int32_t** data, int64_t* n);
-int b200ls_mesh_n_levels(b200ls_mesh_t mesh);   /* number of mesh levels incl. the finest */
+int b200ls_mesh_n_levels(b200ls_mesh_t mesh);
+
+enum b200ls_iface_i32_which {
+    B200LS_IFACE_FACE_CELLS = 0,               /* lduInterface::faceCells() of coupled patch `iface` at `level`   */
+    B200LS_IFACE_FACE_RESTRICT_ADDRESSING = 1  /* GAMGInterface::faceRestrictAddressing(): level -> level+1       */
+};
+int b200ls_mesh_get_iface_i32(b200ls_mesh_t mesh, int which, int level, int iface, const int32_t** data,
+                              int64_t* n);   /* number of mesh levels incl. the finest */
 
 /* Pair agglomeration with the given finest-level face weights (faceAreaPair passes
  * mag(cmptMultiply(Sf/sqrt(magSf), (1 1.01 1.02)))).  minCellsPerProcessor: reference default 10

@@ -22,8 +22,8 @@ SOLVERS = {"PCG": PCG, "PBiCGStab": PBICGSTAB, "GAMG": GAMG, "smoothSolver": SMO
 PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "GaussSeidel": GAUSS_SEIDEL}
 
 EXPORTS = [
-    "b200ls_init", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
-    "b200ls_mesh_create", "b200ls_mesh_free", "b200ls_mesh_get_i32", "b200ls_mesh_n_levels",
+    "b200ls_init", "b200ls_set_host_comm", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
+    "b200ls_mesh_create", "b200ls_mesh_free", "b200ls_mesh_get_i32", "b200ls_mesh_get_iface_i32", "b200ls_mesh_n_levels",
     "b200ls_agglomerate", "b200ls_agglomerate_from_maps", "b200ls_matrix_create", "b200ls_matrix_free", "b200ls_matrix_set",
     "b200ls_amul", "b200ls_residual", "b200ls_sum_a", "b200ls_precondition", "b200ls_reciprocal_d",
     "b200ls_smooth", "b200ls_controls_default", "b200ls_solve", "b200ls_solve_dev", "b200ls_time_kernel",
@@ -76,6 +76,7 @@ def lib():
     L.b200ls_mesh_free.argtypes = [p]
     L.b200ls_mesh_get_i32.argtypes = [p, C.c_int, C.c_int, C.POINTER(p), C.POINTER(i64)]
     L.b200ls_mesh_n_levels.argtypes = [p]
+    L.b200ls_mesh_get_iface_i32.argtypes = [p, C.c_int, C.c_int, C.c_int, C.POINTER(p), C.POINTER(i64)]
     L.b200ls_agglomerate.argtypes = [p, p, i32, i32, i32]
     L.b200ls_agglomerate_from_maps.argtypes = [p, i32, p, p]
     L.b200ls_matrix_create.restype = p
@@ -111,6 +112,29 @@ def _f64(a):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+EXCHANGE_FN = C.CFUNCTYPE(None, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                          C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)))
+SUM_FN = C.CFUNCTYPE(C.c_int64, C.c_int64)
+_host_comm_refs = []
+
+
+def set_host_comm(rank, n_ranks, exchange, total):
+    """exchange(nbr: list[int], send: list[np.ndarray]) -> list[np.ndarray]; total(v: int) -> int (global sum)."""
+
+    def _ex(n, nbr, sizes, send, recv):
+        nb = [nbr[i] for i in range(n)]
+        snd = [np.ctypeslib.as_array(send[i], shape=(sizes[i],)).copy() if sizes[i] else np.zeros(0, np.int32)
+               for i in range(n)]
+        got = exchange(nb, snd)
+        for i in range(n):
+            if sizes[i]:
+                np.ctypeslib.as_array(recv[i], shape=(sizes[i],))[:] = got[i]
+
+    ex_c, sum_c = EXCHANGE_FN(_ex), SUM_FN(lambda v: int(total(int(v))))
+    _host_comm_refs[:] = [ex_c, sum_c]
+    lib().b200ls_set_host_comm(rank, n_ranks, ex_c, sum_c)
 
 
 def device_available():
@@ -182,6 +206,14 @@ class Mesh:
             return np.zeros(0, dtype=np.int32)
         arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int32)), shape=(n.value,))
         return arr.copy()
+
+    def get_iface_i32(self, which, level, iface):
+        data = C.c_void_p()
+        n = C.c_int64()
+        _check(lib().b200ls_mesh_get_iface_i32(self.h, which, level, iface, C.byref(data), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=np.int32)
+        return np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int32)), shape=(n.value,)).copy()
 
     @property
     def n_levels(self):

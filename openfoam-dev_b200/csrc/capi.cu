@@ -61,6 +61,77 @@ void d2h(double* host, const double* dev, int n) {
     B2_CUDA(cudaStreamSynchronize(ctx().stream));
 }
 
+// ---- host-side communicator for multi-rank agglomeration ---------------------------------------------------
+// Either caller-supplied callbacks (b200ls_set_host_comm: Pstream in the plugin, torch.distributed/gloo in the
+// CPU tests) or NCCL on small staging buffers.
+typedef void (*exchange_cb_t)(int32_t nIfaces, const int32_t* nbr, const int32_t* sizes, const int32_t* const* send,
+                              int32_t* const* recv);
+typedef int64_t (*sum_cb_t)(int64_t);
+exchange_cb_t g_exchangeCb = nullptr;
+sum_cb_t g_sumCb = nullptr;
+int g_hostRank = 0, g_hostRanks = 1;
+bool g_hostCommSet = false;
+
+HostComm makeHostComm() {
+    HostComm hc;
+    if (g_hostCommSet) {
+        hc.exchange = [](const std::vector<int32_t>& nbr, const std::vector<std::vector<int32_t>>& send,
+                         std::vector<std::vector<int32_t>>& recv) {
+            std::vector<int32_t> sizes(nbr.size());
+            std::vector<const int32_t*> sp(nbr.size());
+            std::vector<int32_t*> rp(nbr.size());
+            for (size_t i = 0; i < nbr.size(); i++) {
+                sizes[i] = int32_t(send[i].size());
+                sp[i] = send[i].data();
+                rp[i] = recv[i].data();
+            }
+            g_exchangeCb(int32_t(nbr.size()), nbr.data(), sizes.data(), sp.data(), rp.data());
+        };
+        hc.sum = [](int64_t v) { return g_sumCb(v); };
+        return hc;
+    }
+    hc.exchange = [](const std::vector<int32_t>& nbr, const std::vector<std::vector<int32_t>>& send,
+                     std::vector<std::vector<int32_t>>& recv) {
+        Context& c = ctx();
+        ensureInit();
+        if (!c.comm) throw CudaError("multi-rank agglomeration needs b200ls_init with nRanks > 1");
+        std::vector<DevBuf<int>> ds(nbr.size()), dr(nbr.size());
+        for (size_t i = 0; i < nbr.size(); i++) {
+            ds[i].upload(std::vector<int>(send[i].begin(), send[i].end()), c.stream);
+            dr[i].alloc(send[i].size());
+        }
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        c.nccl.GroupStart();
+        for (size_t i = 0; i < nbr.size(); i++) {
+            c.nccl.Send(ds[i].p, send[i].size(), ncclInt32, nbr[i], c.comm, c.stream);
+            c.nccl.Recv(dr[i].p, send[i].size(), ncclInt32, nbr[i], c.comm, c.stream);
+        }
+        int r = c.nccl.GroupEnd();
+        if (r != 0) throw CudaError(std::string("nccl restrictMap exchange: ") + c.nccl.GetErrorString((ncclResult_t)r));
+        for (size_t i = 0; i < nbr.size(); i++) {
+            if (!send[i].empty())
+                B2_CUDA(cudaMemcpyAsync(recv[i].data(), dr[i].p, sizeof(int32_t) * send[i].size(),
+                                        cudaMemcpyDeviceToHost, c.stream));
+        }
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+    };
+    hc.sum = [](int64_t v) {
+        Context& c = ctx();
+        ensureInit();
+        if (!c.comm) throw CudaError("multi-rank agglomeration needs b200ls_init with nRanks > 1");
+        DevBuf<long long> d;
+        d.alloc(1);
+        long long h = v;
+        B2_CUDA(cudaMemcpyAsync(d.p, &h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
+        int r = c.nccl.AllReduce(d.p, d.p, 1, ncclInt64, ncclSum, c.comm, c.stream);
+        if (r != 0) throw CudaError("ncclAllReduce(int64) failed");
+        B2_CUDA(cudaMemcpyAsync(&h, d.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        return int64_t(h);
+    };
+    return hc;
+}
+
 void requireValues(b200ls_matrix_t m) {
     if (!m || !m->valuesSet) throw CudaError("matrix coefficients not set (call b200ls_matrix_set)");
 }
@@ -118,6 +189,15 @@ void b200ls_finalize(void) {
     }
 }
 
+int b200ls_set_host_comm(int32_t rank, int32_t nRanks, exchange_cb_t exchange, sum_cb_t sum) {
+    g_exchangeCb = exchange;
+    g_sumCb = sum;
+    g_hostRank = rank;
+    g_hostRanks = nRanks;
+    g_hostCommSet = (exchange != nullptr && sum != nullptr);
+    return 0;
+}
+
 b200ls_mesh_t b200ls_mesh_create(int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
                                  int32_t nInterfaces, const int32_t* ifaceSizes,
                                  const int32_t* const* ifaceFaceCells, const int32_t* ifaceNeighbRank) {
@@ -130,8 +210,8 @@ b200ls_mesh_t b200ls_mesh_create(int32_t nCells, int32_t nFaces, const int32_t* 
         }
         std::unique_ptr<b200ls_mesh_s> m(new b200ls_mesh_s);
         m->host.levels.resize(1);
-        m->host.nRanks = ctx().nRanks;
-        m->host.rank = ctx().rank;
+        m->host.nRanks = g_hostCommSet ? g_hostRanks : ctx().nRanks;
+        m->host.rank = g_hostCommSet ? g_hostRank : ctx().rank;
         buildLevel(m->host.levels[0], nCells, nFaces, lower, upper, std::move(ifs));
         mesh = m.release();
     });
@@ -177,13 +257,36 @@ int b200ls_mesh_get_i32(b200ls_mesh_t mesh, int which, int level, const int32_t*
     });
 }
 
+int b200ls_mesh_get_iface_i32(b200ls_mesh_t mesh, int which, int level, int iface, const int32_t** data,
+                              int64_t* n) {
+    return guarded([&] {
+        if (!mesh) throw CudaError("null mesh");
+        if (level < 0 || level >= int(mesh->host.levels.size())) throw CudaError("level out of range");
+        LevelHost& L = mesh->host.levels[level];
+        if (iface < 0 || iface >= int(L.interfaces.size())) throw CudaError("interface out of range");
+        const std::vector<int32_t>* v = nullptr;
+        if (which == B200LS_IFACE_FACE_CELLS) {
+            v = &L.interfaces[iface].faceCells;
+        } else if (which == B200LS_IFACE_FACE_RESTRICT_ADDRESSING) {
+            if (!L.hasCoarse) throw CudaError("level has no coarser level");
+            v = &L.patchFaceRestrictAddr[iface];
+        } else {
+            throw CudaError("unknown interface array id");
+        }
+        *data = v->data();
+        *n = int64_t(v->size());
+    });
+}
+
 int b200ls_agglomerate(b200ls_mesh_t mesh, const double* faceWeights, int32_t minCellsPerProcessor,
                        int32_t mergeLevels, int32_t forwardStart) {
     int nCoarse = -1;
     int rc = guarded([&] {
         if (!mesh) throw CudaError("null mesh");
         bool fwd = forwardStart < 0 ? g_forward : (forwardStart != 0);
-        nCoarse = agglomerate(mesh->host, faceWeights, minCellsPerProcessor, mergeLevels, fwd);
+        HostComm hc = makeHostComm();
+        nCoarse = agglomerate(mesh->host, faceWeights, minCellsPerProcessor, mergeLevels, fwd,
+                              mesh->host.nRanks > 1 ? &hc : nullptr);
         g_forward = fwd;
         mesh->dev.reset();
         mesh->generation++;
@@ -196,7 +299,9 @@ int b200ls_agglomerate_from_maps(b200ls_mesh_t mesh, int32_t nCoarseLevels, cons
     int n = -1;
     int rc = guarded([&] {
         if (!mesh) throw CudaError("null mesh");
-        n = agglomerateFromMaps(mesh->host, nCoarseLevels, restrictAddr, nCoarseCells);
+        HostComm hc = makeHostComm();
+        n = agglomerateFromMaps(mesh->host, nCoarseLevels, restrictAddr, nCoarseCells,
+                                mesh->host.nRanks > 1 ? &hc : nullptr);
         mesh->dev.reset();
         mesh->generation++;
     });

@@ -13,6 +13,7 @@
 #include <limits>
 #include <numeric>
 #include <stdexcept>
+#include <unordered_map>
 
 namespace b200ls {
 
@@ -403,34 +404,78 @@ void buildMaps(LevelHost& fine, const LevelHost& coarse) {
 
 }  // namespace
 
+// Coarse processor interfaces (processorGAMGInterface ctor, processorGAMGInterface.C:53-140): coarse patch faces
+// are the distinct (local coarse cell, neighbour coarse cell) pairs in first-seen order; the pair is ordered
+// (master, slave) by rank so both sides number the coarse faces identically.
+static void agglomerateInterfaces(LevelHost& fine, std::vector<HostInterface>& coarseIfaces, int myRank,
+                                  const HostComm* comm) {
+    const size_t nI = fine.interfaces.size();
+    fine.patchFaceRestrictAddr.assign(nI, {});
+    coarseIfaces.assign(nI, {});
+    if (nI == 0) return;
+    if (!comm || !comm->exchange) throw std::runtime_error("agglomerating processor interfaces needs a communicator");
+    std::vector<int32_t> nbr(nI);
+    std::vector<std::vector<int32_t>> send(nI), recv(nI);
+    for (size_t i = 0; i < nI; i++) {
+        const auto& fc = fine.interfaces[i].faceCells;
+        nbr[i] = fine.interfaces[i].neighbRank;
+        send[i].resize(fc.size());
+        for (size_t k = 0; k < fc.size(); k++) send[i][k] = fine.restrictAddr[fc[k]];   // interfaceInternalField
+        recv[i].assign(fc.size(), -1);
+    }
+    comm->exchange(nbr, send, recv);
+    for (size_t i = 0; i < nI; i++) {
+        const bool master = myRank < nbr[i];
+        std::unordered_map<uint64_t, int32_t> seen;
+        seen.reserve(send[i].size() * 2);
+        HostInterface& ci = coarseIfaces[i];
+        ci.neighbRank = nbr[i];
+        auto& pr = fine.patchFaceRestrictAddr[i];
+        pr.resize(send[i].size());
+        for (size_t k = 0; k < send[i].size(); k++) {
+            const uint32_t a = uint32_t(master ? send[i][k] : recv[i][k]);
+            const uint32_t b = uint32_t(master ? recv[i][k] : send[i][k]);
+            const uint64_t key = (uint64_t(a) << 32) | b;
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                const int32_t cf = int32_t(ci.faceCells.size());
+                seen.emplace(key, cf);
+                ci.faceCells.push_back(send[i][k]);
+                pr[k] = cf;
+            } else {
+                pr[k] = it->second;
+            }
+        }
+    }
+}
+
 // Append the coarse level defined by `map` (fine cell -> coarse cell) below the current coarsest level:
-// agglomerateLduAddressing + native layout + transfer maps.
-static void appendCoarseLevel(HostMesh& mesh, std::vector<int32_t> map, int32_t nCoarse) {
+// agglomerateLduAddressing + coarse interfaces + native layout + transfer maps.
+static void appendCoarseLevel(HostMesh& mesh, std::vector<int32_t> map, int32_t nCoarse, const HostComm* comm) {
     const size_t k = mesh.levels.size() - 1;
+    std::vector<HostInterface> coarseIfaces;
     {
         LevelHost& fine = mesh.levels[k];
         if (int32_t(map.size()) != fine.nCells) throw std::runtime_error("restrict map size != fine level size");
         for (int32_t v : map)
             if (v < 0 || v >= nCoarse) throw std::runtime_error("restrict map entry out of range");
-        if (!fine.interfaces.empty()) {
-            throw std::runtime_error("agglomeration with processor interfaces is not supported yet");
-        }
         fine.hasCoarse = true;
         fine.nCoarseCells = nCoarse;
         fine.restrictAddr = std::move(map);
-        fine.patchFaceRestrictAddr.assign(fine.interfaces.size(), {});
+        agglomerateInterfaces(fine, coarseIfaces, mesh.rank, comm);
     }
     std::vector<int32_t> cLower, cUpper;
     agglomerateAddressing(mesh.levels[k], cLower, cUpper);
     mesh.levels.emplace_back();   // may move the storage: re-take references
     LevelHost& fine = mesh.levels[k];
     LevelHost& coarse = mesh.levels[k + 1];
-    buildLevel(coarse, nCoarse, int32_t(cLower.size()), cLower.data(), cUpper.data(), {});
+    buildLevel(coarse, nCoarse, int32_t(cLower.size()), cLower.data(), cUpper.data(), std::move(coarseIfaces));
     buildMaps(fine, coarse);
 }
 
 int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
-                bool& forward) {
+                bool& forward, const HostComm* comm) {
+    if (mesh.nRanks > 1 && (!comm || !comm->sum)) throw std::runtime_error("multi-rank agglomeration needs a communicator");
     if (mergeLevels != 1) throw std::runtime_error("mergeLevels != 1 is not supported");
     mesh.levels.resize(1);
     mesh.levels[0].hasCoarse = false;
@@ -444,12 +489,12 @@ int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerPr
         int32_t nCoarse = -1;
         std::vector<int32_t> map = pairAgglomerate(nCoarse, mesh.levels[nCreated], w, forward);
 
-        // continueAgglomerating (single rank: global sums are local values)
-        const int64_t totalCoarse = nCoarse;
-        const int64_t totalFine = mesh.levels[nCreated].nCells;
+        // continueAgglomerating: global sums over ranks
+        const int64_t totalCoarse = mesh.nRanks > 1 ? comm->sum(nCoarse) : nCoarse;
+        const int64_t totalFine = mesh.nRanks > 1 ? comm->sum(mesh.levels[nCreated].nCells) : mesh.levels[nCreated].nCells;
         if (totalCoarse < int64_t(mesh.nRanks) * minCellsPerProcessor || !(totalCoarse < totalFine)) break;
 
-        appendCoarseLevel(mesh, std::move(map), nCoarse);
+        appendCoarseLevel(mesh, std::move(map), nCoarse, comm);
 
         // restrictFaceField of the weights for the next level (sequential adds in fine-face order)
         const LevelHost& fine = mesh.levels[nCreated];
@@ -466,13 +511,13 @@ int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerPr
 }
 
 int agglomerateFromMaps(HostMesh& mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
-                        const int32_t* nCoarseCells) {
+                        const int32_t* nCoarseCells, const HostComm* comm) {
     mesh.levels.resize(1);
     mesh.levels[0].hasCoarse = false;
     mesh.agglomerated = false;
     for (int32_t k = 0; k < nCoarseLevels; k++) {
         const int32_t nFine = mesh.levels[k].nCells;
-        appendCoarseLevel(mesh, std::vector<int32_t>(restrictAddr[k], restrictAddr[k] + nFine), nCoarseCells[k]);
+        appendCoarseLevel(mesh, std::vector<int32_t>(restrictAddr[k], restrictAddr[k] + nFine), nCoarseCells[k], comm);
     }
     mesh.agglomerated = true;
     return nCoarseLevels;

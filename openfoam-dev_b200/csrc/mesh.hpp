@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -65,6 +66,16 @@ struct LevelHost {
     AgglomMaps maps;
 };
 
+// Host-side communication needed while agglomerating a decomposed mesh (once per mesh): the neighbour exchange
+// of restrictMap over every processor patch (GAMGAgglomerateLduAddressing.C:268-283,
+// processorGAMGInterface.C:195-214) and the global sums of continueAgglomerating (GAMGAgglomeration.C:211-229).
+struct HostComm {
+    // send[i] goes to nbr[i]; recv[i] (same length) comes from nbr[i]; patches in this rank's patch order
+    std::function<void(const std::vector<int32_t>& nbr, const std::vector<std::vector<int32_t>>& send,
+                       std::vector<std::vector<int32_t>>& recv)> exchange;
+    std::function<int64_t(int64_t)> sum;
+};
+
 struct HostMesh {
     std::vector<LevelHost> levels;      // [0] = finest
     bool agglomerated = false;
@@ -83,11 +94,11 @@ std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fin
 // Whole level loop of pairGAMGAgglomeration::agglomerate(mesh, weights) (pairGAMGAgglomerate.C:31-118)
 // with continueAgglomerating (GAMGAgglomeration.C:205-230).  Returns number of coarse levels.
 int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
-                bool& forward);
+                bool& forward, const HostComm* comm = nullptr);
 
 // Levels supplied by the caller (the plugin passes GAMGAgglomeration::restrictAddressing(level) of the reference's
 // own cached agglomeration object); everything derived from them is rebuilt here.
 int agglomerateFromMaps(HostMesh& mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
-                        const int32_t* nCoarseCells);
+                        const int32_t* nCoarseCells, const HostComm* comm = nullptr);
 
 }  // namespace b200ls

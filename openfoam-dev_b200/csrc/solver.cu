@@ -570,12 +570,12 @@ static double* scalar(b200ls_matrix_s* m, int i) {
 }
 
 // normFactor (lduMatrixSolver.C:174-197). tmp is clobbered.
-static double normFactor(b200ls_matrix_s* m, const double* psi, const double* source, const double* Apsi,
+static double normFactor(b200ls_matrix_s* m, int lv, const double* psi, const double* source, const double* Apsi,
                          double* tmp, int64_t nGlobalCells) {
     Context& c = ctx();
-    DevLevel& D = DL(m, 0);
+    DevLevel& D = DL(m, lv);
     const int n = D.nCells;
-    opSumA(m, 0, tmp);
+    opSumA(m, lv, tmp);
     reduce<RED_SUM>(scalar(m, S_SUMPSI), psi, nullptr, n);
     allReduce(scalar(m, S_SUMPSI), 1);
     LAUNCH(k_norm_factor, kReduceBlocks, kReduceThreads, scalar(m, S_NORM), Apsi, source, tmp, scalar(m, S_SUMPSI),
@@ -590,9 +590,18 @@ static bool converged(double finalRes, double initRes, double tol, double relTol
     return finalRes < tol || (relTol > 1e-20 && finalRes < relTol * initRes);
 }
 
-static int64_t globalCells(b200ls_matrix_s* m) {
+// named work vector of a level (level 0 vectors are the solver's finest-level vectors)
+static double* lvec(b200ls_matrix_s* m, int lv, const char* name) {
+    if (lv == 0) return m->vec(name);
+    Vec& v = m->vecs[std::string(name) + "@" + std::to_string(lv)];
+    const size_t n = DL(m, lv).nCells;
+    if (v.buf.n != n || !v.buf.p) v.buf.alloc(n);
+    return v.buf.p;
+}
+
+static int64_t globalCells(b200ls_matrix_s* m, int lv = 0) {
     Context& c = ctx();
-    const int64_t n = DL(m, 0).nCells;
+    const int64_t n = DL(m, lv).nCells;
     if (c.nRanks == 1) return n;
     double* s = scalar(m, S_NUM);
     const double h = double(n);
@@ -613,16 +622,16 @@ static void record(b200ls_perf* perf, const b200ls_controls& c, double r) {
 // PCG (PCG.C:65-193)
 // ------------------------------------------------------------------------------------------------------------
 
-static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, const double* source,
+static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, double* psi, const double* source,
                      b200ls_perf* perf, cudaEvent_t evLoopStart) {
     Context& cx = ctx();
-    const int n = DL(m, 0).nCells;
-    double* pA = m->vec("pA");
-    double* wA = m->vec("wA");
-    double* rA = m->vec("rA");
+    const int n = DL(m, lv).nCells;
+    double* pA = lvec(m, lv, "pA");
+    double* wA = lvec(m, lv, "wA");
+    double* rA = lvec(m, lv, "rA");
 
-    opAmulAndResidual(m, 0, wA, rA, psi, source);
-    const double nf = normFactor(m, psi, source, wA, pA, globalCells(m));
+    opAmulAndResidual(m, lv, wA, rA, psi, source);
+    const double nf = normFactor(m, lv, psi, source, wA, pA, globalCells(m, lv));
     perf->normFactor = nf;
     reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
     allReduce(scalar(m, S_RES), 1);
@@ -631,18 +640,18 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, 
     perf->finalResidual = perf->initialResidual;
     perf->nIterations = 0;
 
-    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
     if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
-        ensureFactor(m, 0, c.precond);
+        ensureFactor(m, lv, c.precond);
         do {
             const int cur = S_WARA0 + (perf->nIterations & 1);
             const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
-            opPrecondition(m, 0, c.precond, wA, rA);
+            opPrecondition(m, lv, c.precond, wA, rA);
             reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
             allReduce(scalar(m, cur), 1);
             LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
                    perf->nIterations == 0 ? 1 : 0, n);
-            opAmul(m, 0, wA, pA);
+            opAmul(m, lv, wA, pA);
             reduce<RED_DOT>(scalar(m, S_WAPA), wA, pA, n);
             allReduce(scalar(m, S_WAPA), 1);
             // singularity test needs wApA on the host before psi is touched (PCG.C:165)
@@ -668,16 +677,16 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, 
 // PBiCGStab (PBiCGStab.C:68-254)
 // ------------------------------------------------------------------------------------------------------------
 
-static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, double* psi, const double* source,
+static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv, double* psi, const double* source,
                            b200ls_perf* perf, cudaEvent_t evLoopStart) {
     Context& cx = ctx();
-    const int n = DL(m, 0).nCells;
-    double* pA = m->vec("pA");
-    double* yA = m->vec("yA");
-    double* rA = m->vec("rA");
+    const int n = DL(m, lv).nCells;
+    double* pA = lvec(m, lv, "pA");
+    double* yA = lvec(m, lv, "yA");
+    double* rA = lvec(m, lv, "rA");
 
-    opAmulAndResidual(m, 0, yA, rA, psi, source);
-    const double nf = normFactor(m, psi, source, yA, pA, globalCells(m));
+    opAmulAndResidual(m, lv, yA, rA, psi, source);
+    const double nf = normFactor(m, lv, psi, source, yA, pA, globalCells(m, lv));
     perf->normFactor = nf;
     reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
     allReduce(scalar(m, S_RES), 1);
@@ -686,15 +695,15 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, double*
     perf->finalResidual = perf->initialResidual;
     perf->nIterations = 0;
 
-    B2_CUDA(cudaEventRecord(evLoopStart, S()));
+    if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
     if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
-        double* AyA = m->vec("AyA");
-        double* sA = m->vec("sA");
-        double* zA = m->vec("zA");
-        double* tA = m->vec("tA");
-        double* rA0 = m->vec("rA0");
+        double* AyA = lvec(m, lv, "AyA");
+        double* sA = lvec(m, lv, "sA");
+        double* zA = lvec(m, lv, "zA");
+        double* tA = lvec(m, lv, "tA");
+        double* rA0 = lvec(m, lv, "rA0");
         B2_CUDA(cudaMemcpyAsync(rA0, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
-        ensureFactor(m, 0, c.precond);
+        ensureFactor(m, lv, c.precond);
         double omega = 0;
         do {
             const int cur = S_RHO0 + (perf->nIterations & 1);
@@ -712,8 +721,8 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, double*
             }
             LAUNCH(k_bicg_update_p, gridStride(n), 256, pA, rA, AyA, m->scalars.p, cur, old, S_ALPHA, S_OMEGA,
                    perf->nIterations == 0 ? 1 : 0, n);
-            opPrecondition(m, 0, c.precond, yA, pA);
-            opAmul(m, 0, AyA, yA);
+            opPrecondition(m, lv, c.precond, yA, pA);
+            opAmul(m, lv, AyA, yA);
             reduce<RED_DOT>(scalar(m, S_RA0AYA), rA0, AyA, n);
             allReduce(scalar(m, S_RA0AYA), 1);
             LAUNCH(k_bicg_update_s, kReduceBlocks, kReduceThreads, sA, rA, AyA, scalar(m, cur), scalar(m, S_RA0AYA),
@@ -728,8 +737,8 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, double*
                 perf->converged = 1;
                 return;
             }
-            opPrecondition(m, 0, c.precond, zA, sA);
-            opAmul(m, 0, tA, zA);
+            opPrecondition(m, lv, c.precond, zA, sA);
+            opAmul(m, lv, tA, zA);
             // tAsA and tAtA in one pass (and one 2-element allreduce)
             LAUNCH(k_dot2, kReduceBlocks, kReduceThreads, scalar(m, S_TASA), sA, tA, tA, n, cx.partials.p,
                    cx.ticket.p);
@@ -769,7 +778,7 @@ static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& p
     double* tmp = m->vec("pA");
     double* rA = m->vec("rA");
     opAmulAndResidual(m, 0, Apsi, rA, psi, source);
-    const double nf = normFactor(m, psi, source, Apsi, tmp, globalCells(m));
+    const double nf = normFactor(m, 0, psi, source, Apsi, tmp, globalCells(m));
     perf->normFactor = nf;
     reduce<RED_SUMMAG>(scalar(m, S_RES), rA, nullptr, n);
     allReduce(scalar(m, S_RES), 1);
@@ -1037,7 +1046,24 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
     const int k = int(m->levels.size()) - 1;
     DevLevel& D = DL(m, k);
     MatLevel& M = m->levels[k];
-    if (ctx().nRanks > 1) throw CudaError("multi-rank GAMG coarsest solve not implemented yet");
+    if (ctx().nRanks > 1) {
+        // distributed coarsest level: the regular PCG+DIC / PBiCGStab+DILU on that level with the parent's
+        // tolerance and relTol, zero initial guess (GAMGSolver.C:286-319, GAMGSolverSolve.C:538-545)
+        b200ls_controls cc;
+        memset(&cc, 0, sizeof(cc));
+        cc.tolerance = c.tolerance;
+        cc.relTol = c.relTol;
+        cc.maxIter = 1000;
+        cc.minIter = 0;
+        cc.precond = m->symmetric ? B200LS_DIC : B200LS_DILU;
+        static b200ls_perf cperf;
+        memset(&cperf, 0, offsetof(b200ls_perf, history));
+        B2_CUDA(cudaMemsetAsync(M.corr.p, 0, sizeof(double) * D.nCells, S()));
+        M.rDValid = M.rDValid && true;
+        if (m->symmetric) solvePCG(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
+        else solvePBiCGStab(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
+        return;
+    }
     m->coarsestWork.alloc(size_t(12) * D.nCells + size_t(2) * D.nFaces + 16);
     CoarsestArgs a;
     a.nCells = D.nCells;
@@ -1171,7 +1197,7 @@ static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi
     }
 
     opAmul(m, 0, Apsi, psi);
-    const double nf = normFactor(m, psi, source, Apsi, finestCorrection, globalCells(m));
+    const double nf = normFactor(m, 0, psi, source, Apsi, finestCorrection, globalCells(m));
     perf->normFactor = nf;
     LAUNCH(k_sub, gridStride(n), 256, finestResidual, source, Apsi, n);
     reduce<RED_SUMMAG>(scalar(m, S_RES), finestResidual, nullptr, n);
@@ -1230,10 +1256,10 @@ void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, con
         switch (c.solver) {
             case B200LS_PCG:
                 if (!m->symmetric) throw CudaError("PCG requires a symmetric matrix");
-                solvePCG(m, c, vPsi.buf.p, source, perf, ev1);
+                solvePCG(m, c, 0, vPsi.buf.p, source, perf, ev1);
                 break;
             case B200LS_PBICGSTAB:
-                solvePBiCGStab(m, c, vPsi.buf.p, source, perf, ev1);
+                solvePBiCGStab(m, c, 0, vPsi.buf.p, source, perf, ev1);
                 break;
             case B200LS_GAMG:
                 solveGAMG(m, c, vPsi.buf.p, vSpare.buf.p, source, perf, ev1);

@@ -33,7 +33,7 @@ def main():
     capi.init(local, bytes(buf.cpu().numpy().tobytes()), rank, world)
 
     split = decompose.simple_split(world)
-    nx, ny, nz = 8 * split[0], 6 * split[1], 5 * split[2]
+    nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
     ok = True
     for kind in ("sym", "asym"):
         glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if kind == "sym" else \
@@ -41,6 +41,9 @@ def main():
         parts, maps = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), world)
         part, cells = parts[rank], maps[rank]
         mesh, mat = capi.from_system(part)
+        n_coarse = mesh.agglomerate(part.face_weights)      # restrictMap exchange + global stop criterion over NCCL
+        mat.set(part.diag, part.upper_coeffs, part.lower_coeffs, [i.bou_coeffs for i in part.interfaces],
+                [i.int_coeffs for i in part.interfaces])
         A = dense(glob)
         x = np.cos(0.3 * np.arange(glob.n_cells))
 
@@ -60,12 +63,17 @@ def main():
 
         exact = np.linalg.solve(A, glob.source)
         combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
+        combos += [("GAMG", "GaussSeidel"), ("GAMG", "DIC" if kind == "sym" else "DILU")]
         if kind == "asym":   # Gauss-Seidel alone converges far too slowly on the Laplacian to pin a solution
             combos.append(("smoothSolver", "GaussSeidel"))
         for solver, pre in combos:
             kw = dict(tolerance=1e-13, relTol=0.0, maxIter=2000)
-            ctl = capi.controls(solver, preconditioner=pre, **kw) if solver != "smoothSolver" else \
-                capi.controls(solver, smoother=pre, nSweeps=4, **kw)
+            if solver == "smoothSolver":
+                ctl = capi.controls(solver, smoother=pre, nSweeps=4, **kw)
+            elif solver == "GAMG":
+                ctl = capi.controls(solver, smoother=pre, **kw)
+            else:
+                ctl = capi.controls(solver, preconditioner=pre, **kw)
             psi, perf = mat.solve(ctl, part.source)
             full = gather(psi)
             e = np.max(np.abs(full - exact)) / np.max(np.abs(exact))
