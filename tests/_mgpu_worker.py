@@ -57,7 +57,7 @@ def main():
         err = np.max(np.abs(y - A @ x)) / np.max(np.abs(A @ x))
         r = gather(mat.residual(x[cells], glob.source[cells]))
         err_r = np.max(np.abs(r - (glob.source - A @ x))) / np.max(np.abs(glob.source))
-        ok &= err < 1e-14 and err_r < 1e-14
+        ok &= err < 1e-13 and err_r < 1e-13   # vs a dense numpy matvec (different summation order)
         if rank == 0:
             print(f"{kind}: amul rel err {err:.2e} residual rel err {err_r:.2e}", flush=True)
 
