@@ -106,6 +106,8 @@ struct DevLevel {
     int nCells = 0, nFaces = 0;
     DevBuf<int> perm, ipos;
     DevBuf<int> Lptr, Lcol, Lface, Uptr, Ucol, Uface, LtoU;
+    DevBuf<unsigned char> Lslot;    // slot of each L entry inside its owner's U row (symmetric SpMV); empty if > 255
+    bool hasLslot = false;
     DevBuf<int2> fwdTasks, bwdTasks;
     DevBuf<int> bwdPos;
     int nFwdTasks = 0, nBwdTasks = 0;

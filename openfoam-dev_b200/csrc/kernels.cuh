@@ -118,6 +118,40 @@ k_spmv(double* __restrict__ out, double* __restrict__ out2, const double* __rest
     if (MODE == SPMV_AMUL_AND_RESIDUAL) out2[p] = b[p] - acc;
 }
 
+// Symmetric matrices: the neighbour-side coefficient of row p for neighbour q is the owner-side coefficient that
+// row q stores for p, so it is gathered from Uval[Uptr[q] + slot] (L2 hit: row q streamed it a wavefront earlier)
+// instead of being read from a duplicated Lval array: 83 B/row of DRAM traffic instead of 104 on a hex mesh.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_spmv_sym(double* __restrict__ out, double* __restrict__ out2, const double* __restrict__ x,
+           const double* __restrict__ b, const double* __restrict__ diag, const int* __restrict__ Lptr,
+           const int* __restrict__ Lcol, const unsigned char* __restrict__ Lslot, const int* __restrict__ Uptr,
+           const int* __restrict__ Ucol, const double* __restrict__ Uval, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int l0 = Lptr[p], l1 = Lptr[p + 1];
+    const int u0 = Uptr[p], u1 = Uptr[p + 1];
+    double acc;
+    if (MODE == SPMV_RESIDUAL) {
+        acc = b[p] - diag[p] * x[p];
+        for (int j = l0; j < l1; j++) {
+            const int q = Lcol[j];
+            acc -= Uval[Uptr[q] + Lslot[j]] * x[q];
+        }
+        for (int j = u0; j < u1; j++) acc -= Uval[j] * x[Ucol[j]];
+        out[p] = acc;
+        return;
+    }
+    acc = diag[p] * x[p];
+    for (int j = l0; j < l1; j++) {
+        const int q = Lcol[j];
+        acc += Uval[Uptr[q] + Lslot[j]] * x[q];
+    }
+    for (int j = u0; j < u1; j++) acc += Uval[j] * x[Ucol[j]];
+    out[p] = acc;
+    if (MODE == SPMV_AMUL_AND_RESIDUAL) out2[p] = b[p] - acc;
+}
+
 // Coupled-interface epilogue: result[faceCells[i]] -= coeffs[i]*recv[i] in (patch, face) order
 // (processorFvPatchScalarField.C:133-136).  One thread per boundary row.  sign = +1 for Amul, -1 when the
 // caller negated the coefficients (residual, GaussSeidel).

@@ -135,7 +135,17 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         std::vector<int32_t> ltou(H.nFaces);
         for (int32_t j = 0; j < H.nFaces; j++) ltou[j] = H.Uidx[H.Lface[j]];
         D.LtoU.upload(ltou, s);
-        B2_CUDA(cudaStreamSynchronize(s));   // ltou is a temporary
+        // slot of the matching entry inside the owner's U row
+        std::vector<unsigned char> slot(H.nFaces);
+        bool fits = true;
+        for (int32_t j = 0; j < H.nFaces && fits; j++) {
+            const int32_t d = ltou[j] - H.Uptr[H.Lcol[j]];
+            if (d < 0 || d > 255) fits = false;
+            else slot[j] = (unsigned char)d;
+        }
+        D.hasLslot = fits && H.nFaces > 0;
+        if (D.hasLslot) D.Lslot.upload(slot, s);
+        B2_CUDA(cudaStreamSynchronize(s));   // ltou/slot are temporaries
     }
     static_assert(sizeof(SweepTask) == sizeof(int2), "task layout");
     D.nFwdTasks = int(H.fwdTasks.size());
@@ -349,6 +359,12 @@ static void spmv(b200ls_matrix_s* m, int level, double* out, double* out2, const
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     if (D.nCells == 0) return;
+    static const bool noSym = getenv("B200LS_NO_SYM_SPMV") != nullptr;
+    if (MODE != SPMV_SUMA && m->symmetric && D.hasLslot && !noSym) {
+        LAUNCH(k_spmv_sym<MODE>, gridRows(D.nCells), 256, out, out2, x, b, M.diag.p, D.Lptr.p, D.Lcol.p, D.Lslot.p,
+               D.Uptr.p, D.Ucol.p, M.Uval(), D.nCells);
+        return;
+    }
     LAUNCH(k_spmv<MODE>, gridRows(D.nCells), 256, out, out2, x, b, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
            D.Uptr.p, D.Ucol.p, M.Uval(), D.nCells);
 }

@@ -1,0 +1,85 @@
+// prototype: 2-level tasks -- owned rows of level L recompute their level L-1 dependencies redundantly and only
+// wait for rows >= 2 levels back: halves the dependency chain of the sweep.
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include "../openfoam-dev_b200/csrc/kernels.cuh"
+#include "../openfoam-dev_b200/csrc/mesh.hpp"
+using namespace b200ls;
+struct Task2 { int start, count, d1off, d1cnt; };
+struct Args { const Task2* tasks; int nTasks; const int* d1; const int* ptr; const int* col; const double* val; const double* rD; const double* in; double* out; int* err; };
+__device__ __forceinline__ int find_local(const int* s, int n, int key){ int lo=0, hi=n; while(lo<hi){int mid=(lo+hi)>>1; int v=s[mid]; if(v<key) lo=mid+1; else hi=mid;} return (lo<n && s[lo]==key)? lo : -1; }
+template<int MINB> __global__ void __launch_bounds__(256, MINB) k2(Args a){
+    __shared__ int sD1[8][32]; __shared__ double sVal[8][32];
+    const int wpb=blockDim.x>>5, nW=gridDim.x*wpb, lane=threadIdx.x&31, w=threadIdx.x>>5;
+    for(int t=blockIdx.x*wpb+w; t<a.nTasks; t+=nW){
+        const Task2 T=a.tasks[t];
+        const int rowA = lane<T.d1cnt ? a.d1[T.d1off+lane] : -1;
+        sD1[w][lane]=rowA; __syncwarp();
+        int nA=0,cA[4]; double vA[4],wA[4],rdA=0,accA=0;
+        if(rowA>=0){ rdA=a.rD[rowA]; accA=rdA*a.in[rowA]; const int j0=a.ptr[rowA]; nA=a.ptr[rowA+1]-j0;
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nA){cA[k]=a.col[j0+k]; vA[k]=a.val[j0+k];}
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nA) wA[k]=ld_l2(a.out+cA[k]); }
+        const int rowB = lane<T.count ? T.start+lane : -1;
+        int nB=0,cB[4],loc[4]; double vB[4],wB[4],rdB=0,accB=0;
+        if(rowB>=0){ rdB=a.rD[rowB]; accB=rdB*a.in[rowB]; const int j0=a.ptr[rowB]; nB=a.ptr[rowB+1]-j0;
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nB){cB[k]=a.col[j0+k]; vB[k]=a.val[j0+k]; loc[k]=find_local(sD1[w],T.d1cnt,cB[k]);}
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nB && loc[k]<0) wB[k]=ld_l2(a.out+cB[k]); }
+        // pass A
+        if(rowA>=0){ unsigned spins=0; while(true){ bool pend=false;
+#pragma unroll
+                for(int k=0;k<4;k++) if(k<nA&&is_sentinel(wA[k])) pend=true;
+                if(!pend) break; if(++spins>kMaxSpins){*a.err=1;break;}
+#pragma unroll
+                for(int k=0;k<4;k++) if(k<nA&&is_sentinel(wA[k])) wA[k]=ld_l2(a.out+cA[k]); }
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nA) accA -= (rdA*vA[k])*wA[k];
+            sVal[w][lane]=accA; }
+        __syncwarp();
+        if(rowB>=0){ unsigned spins=0; while(true){ bool pend=false;
+#pragma unroll
+                for(int k=0;k<4;k++) if(k<nB&&loc[k]<0&&is_sentinel(wB[k])) pend=true;
+                if(!pend) break; if(++spins>kMaxSpins){*a.err=1;break;}
+#pragma unroll
+                for(int k=0;k<4;k++) if(k<nB&&loc[k]<0&&is_sentinel(wB[k])) wB[k]=ld_l2(a.out+cB[k]); }
+#pragma unroll
+            for(int k=0;k<4;k++) if(k<nB) accB -= (rdB*vB[k])*(loc[k]>=0 ? sVal[w][loc[k]] : wB[k]);
+            st_l2(a.out+rowB, accB); }
+        __syncwarp();
+    }
+}
+int main(int argc,char**argv){
+  int N=argc>1?atoi(argv[1]):128; int bpsm=argc>2?atoi(argv[2]):4; int maxOwned=argc>3?atoi(argv[3]):32;
+  std::vector<int32_t> lo,up;
+  for(int k=0;k<N;k++)for(int j=0;j<N;j++)for(int i=0;i<N;i++){int c=i+N*(j+N*k); if(i<N-1){lo.push_back(c);up.push_back(c+1);} if(j<N-1){lo.push_back(c);up.push_back(c+N);} if(k<N-1){lo.push_back(c);up.push_back(c+N*N);}}
+  LevelHost L; buildLevel(L,N*N*N,(int)lo.size(),lo.data(),up.data(),{});
+  int n=L.nCells,nF=L.nFaces; int nLev=L.fwdOffsets.size()-1;
+  std::vector<int> levOf(n); for(int k=0;k<nLev;k++) for(int p=L.fwdOffsets[k];p<L.fwdOffsets[k+1];p++) levOf[p]=k;
+  // build 2-level tasks
+  std::vector<Task2> tasks; std::vector<int> d1;
+  for(int k=0;k<nLev;k++){ int p=L.fwdOffsets[k], e=L.fwdOffsets[k+1];
+    while(p<e){ std::vector<int> set; int cnt=0; int q=p;
+      while(q<e && cnt<maxOwned){ std::vector<int> add; for(int j=L.Lptr[q];j<L.Lptr[q+1];j++){int d=L.Lcol[j]; if(levOf[d]==k-1 && !std::binary_search(set.begin(),set.end(),d) && std::find(add.begin(),add.end(),d)==add.end()) add.push_back(d);} 
+        if(set.size()+add.size()>32) break; for(int d:add) set.insert(std::upper_bound(set.begin(),set.end(),d),d); cnt++; q++; }
+      if(cnt==0){ // single row with >32 deps at L-1: no recompute
+        tasks.push_back({p,1,(int)d1.size(),0}); p++; continue; }
+      tasks.push_back({p,cnt,(int)d1.size(),(int)set.size()}); for(int d:set) d1.push_back(d); p=q; } }
+  int nT=tasks.size(); printf("N %d levels %d tasks %d (rows/task %.1f) d1 total %zu (%.2f per row)\n",N,nLev,nT,(double)n/nT,d1.size(),(double)d1.size()/n);
+  int *Lptr,*Lcol,*dd1; double *Lval,*rD,*in,*out; Task2* dtasks; int* err;
+  cudaMalloc(&Lptr,(n+1)*4);cudaMalloc(&Lcol,nF*4);cudaMalloc(&Lval,nF*8);cudaMalloc(&rD,n*8);cudaMalloc(&in,n*8);cudaMalloc(&out,n*8);cudaMalloc(&dtasks,nT*sizeof(Task2));cudaMalloc(&err,4);cudaMalloc(&dd1,d1.size()*4+4);
+  cudaMemcpy(Lptr,L.Lptr.data(),(n+1)*4,cudaMemcpyHostToDevice);cudaMemcpy(Lcol,L.Lcol.data(),nF*4,cudaMemcpyHostToDevice);cudaMemcpy(dtasks,tasks.data(),nT*sizeof(Task2),cudaMemcpyHostToDevice);cudaMemcpy(dd1,d1.data(),d1.size()*4,cudaMemcpyHostToDevice);
+  std::vector<double> v(nF),d(n),b(n); for(int i=0;i<nF;i++) v[i]=-0.1-0.001*(i%7); for(int i=0;i<n;i++){d[i]=0.5+0.01*(i%5); b[i]=1.0+0.1*(i%3);} 
+  cudaMemcpy(Lval,v.data(),nF*8,cudaMemcpyHostToDevice);cudaMemcpy(rD,d.data(),n*8,cudaMemcpyHostToDevice);cudaMemcpy(in,b.data(),n*8,cudaMemcpyHostToDevice);cudaMemset(err,0,4);
+  Args a{dtasks,nT,dd1,Lptr,Lcol,Lval,rD,in,out,err};
+  int blocks=std::min(148*bpsm,(nT+7)/8); float best=1e9;
+  for(int rep=0;rep<5;rep++){ k_fill_sentinel<<<1024,256>>>(out,n); cudaEvent_t e0,e1;cudaEventCreate(&e0);cudaEventCreate(&e1);cudaEventRecord(e0); void* args[]={&a};
+    cudaLaunchCooperativeKernel(bpsm>=6?(void*)k2<6>:bpsm>=4?(void*)k2<4>:(void*)k2<2>,dim3(blocks),dim3(256),args,0,0); cudaEventRecord(e1);cudaEventSynchronize(e1);float ms;cudaEventElapsedTime(&ms,e0,e1); if(rep>0) best=std::min(best,ms);} 
+  printf("k2 blocks %d maxOwned %d: best %.3f ms (%s)\n",blocks,maxOwned,best,cudaGetErrorString(cudaGetLastError()));
+  std::vector<double> ho(n),ref(n); cudaMemcpy(ho.data(),out,n*8,cudaMemcpyDeviceToHost);
+  for(int p=0;p<n;p++){ double acc=d[p]*b[p]; for(int j=L.Lptr[p];j<L.Lptr[p+1];j++) acc-=(d[p]*v[j])*ref[L.Lcol[j]]; ref[p]=acc; }
+  int bad=0; for(int p=0;p<n;p++) if(ho[p]!=ref[p]) bad++; int h; cudaMemcpy(&h,err,4,cudaMemcpyDeviceToHost); printf("mismatches %d err %d\n",bad,h);
+  return 0;}
