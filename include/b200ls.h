@@ -130,7 +130,11 @@ int b200ls_sum_a(b200ls_matrix_t m, double* sumA);
 
 enum b200ls_solver { B200LS_PCG = 0, B200LS_PBICGSTAB = 1, B200LS_GAMG = 2, B200LS_SMOOTH_SOLVER = 3 };
 enum b200ls_precond {            /* preconditioner (Krylov) or smoother (GAMG / smoothSolver) */
-    B200LS_NONE = 0, B200LS_DIAGONAL = 1, B200LS_DIC = 2, B200LS_DILU = 3, B200LS_GAUSS_SEIDEL = 4
+    B200LS_NONE = 0, B200LS_DIAGONAL = 1, B200LS_DIC = 2, B200LS_DILU = 3, B200LS_GAUSS_SEIDEL = 4,
+    B200LS_SYM_GAUSS_SEIDEL = 5,    /* smoothers/symGaussSeidel/symGaussSeidelSmoother.C:66-217                  */
+    B200LS_DIC_GAUSS_SEIDEL = 6,    /* smoothers/DICGaussSeidel/DICGaussSeidelSmoother.C:79-89                   */
+    B200LS_DILU_GAUSS_SEIDEL = 7,   /* smoothers/DILUGaussSeidel/DILUGaussSeidelSmoother.C                       */
+    B200LS_GAMG_PRECOND = 8         /* preconditioners/GAMGPreconditioner/GAMGPreconditioner.C:81-148            */
 };
 
 int b200ls_precondition(b200ls_matrix_t m, int precond, const double* rA, double* wA);
@@ -156,6 +160,12 @@ typedef struct b200ls_controls {
     int32_t scaleCorrection;        /* [-1 = matrix.symmetric()] 0/1 */
     int32_t nSweeps;                /* smoothSolver [1] */
     int32_t recordHistory;          /* store the residual after every iteration in perf.history */
+    /* preconditioner GAMG (sub-dictionary `preconditioner { preconditioner GAMG; smoother ...; nVcycles 2; }`):
+     * the V-cycle controls above apply to it, plus: */
+    int32_t precSmoother;           /* enum b200ls_precond: smoother of the preconditioning V-cycles [GaussSeidel] */
+    int32_t nVcycles;               /* [2] */
+    double  precTolerance;          /* tolerance / relTol of the sub-dictionary: inherited by its coarsest solver */
+    double  precRelTol;
 } b200ls_controls;
 
 void b200ls_controls_default(b200ls_controls* c);

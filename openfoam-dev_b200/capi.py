@@ -16,10 +16,12 @@ RESTRICT_ADDRESSING, FACE_RESTRICT_ADDRESSING, FACE_FLIP_MAP = 7, 8, 9
 LOWER_ADDR, UPPER_ADDR, LEVEL_SIZES = 10, 11, 12
 # enum b200ls_solver / b200ls_precond
 PCG, PBICGSTAB, GAMG, SMOOTH_SOLVER = 0, 1, 2, 3
-NONE, DIAGONAL, DIC, DILU, GAUSS_SEIDEL = 0, 1, 2, 3, 4
+NONE, DIAGONAL, DIC, DILU, GAUSS_SEIDEL, SYM_GAUSS_SEIDEL, DIC_GAUSS_SEIDEL, DILU_GAUSS_SEIDEL, GAMG_PRECOND = range(9)
 
 SOLVERS = {"PCG": PCG, "PBiCGStab": PBICGSTAB, "GAMG": GAMG, "smoothSolver": SMOOTH_SOLVER}
-PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "GaussSeidel": GAUSS_SEIDEL}
+PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "GaussSeidel": GAUSS_SEIDEL,
+            "symGaussSeidel": SYM_GAUSS_SEIDEL, "DICGaussSeidel": DIC_GAUSS_SEIDEL,
+            "DILUGaussSeidel": DILU_GAUSS_SEIDEL, "GAMG": GAMG_PRECOND}
 
 EXPORTS = [
     "b200ls_init", "b200ls_set_host_comm", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
@@ -38,7 +40,8 @@ class Controls(C.Structure):
         ("nPreSweeps", C.c_int32), ("preSweepsLevelMultiplier", C.c_int32), ("maxPreSweeps", C.c_int32),
         ("nPostSweeps", C.c_int32), ("postSweepsLevelMultiplier", C.c_int32), ("maxPostSweeps", C.c_int32),
         ("nFinestSweeps", C.c_int32), ("scaleCorrection", C.c_int32), ("nSweeps", C.c_int32),
-        ("recordHistory", C.c_int32),
+        ("recordHistory", C.c_int32), ("precSmoother", C.c_int32), ("nVcycles", C.c_int32),
+        ("precTolerance", C.c_double), ("precRelTol", C.c_double),
     ]
 
 
@@ -165,6 +168,8 @@ def controls(solver="PCG", preconditioner=None, smoother=None, **kw):
     for k, v in kw.items():
         if not hasattr(c, k):
             raise KeyError(k)
+        if k == "precSmoother" and isinstance(v, str):
+            v = PRECONDS[v]
         setattr(c, k, v)
     return c
 

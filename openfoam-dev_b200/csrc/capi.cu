@@ -416,10 +416,7 @@ int b200ls_smooth(b200ls_matrix_t m, int smoother, double* psi, const double* so
         toPositions(m, 0, vPsi.buf.p, m->stageA.p);
         h2d(m->stageA.p, source, n);
         toPositions(m, 0, b, m->stageA.p);
-        if (smoother == B200LS_DIC || smoother == B200LS_DILU) {
-            m->levels[0].rDValid = false;
-            ensureFactor(m, 0, smoother);
-        }
+        m->levels[0].rDValid = false;
         opSmooth(m, 0, smoother, vPsi.buf.p, vSpare.buf.p, b, nSweeps);
         toCells(m, 0, m->stageA.p, vPsi.buf.p);
         d2h(psi, m->stageA.p, n);
@@ -445,6 +442,10 @@ void b200ls_controls_default(b200ls_controls* c) {
     c->scaleCorrection = -1;
     c->nSweeps = 1;
     c->recordHistory = 0;
+    c->precSmoother = B200LS_GAUSS_SEIDEL;
+    c->nVcycles = 2;
+    c->precTolerance = 1e-6;
+    c->precRelTol = 0;
 }
 
 int b200ls_solve_dev(b200ls_matrix_t m, const b200ls_controls* c, double* psi_dev, const double* source_dev,

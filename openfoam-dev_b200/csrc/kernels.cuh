@@ -400,6 +400,32 @@ __global__ void __launch_bounds__(256) k_gs_sweep(SweepArgs a) {
     }
 }
 
+// Reverse half of symGaussSeidel (symGaussSeidelSmoother.C:178-205) in gather form.  After the forward loop
+// bPrime[c] = b'[c] - sum_{nbr faces asc} lower[f]*psi_fwd[l]; the reverse loop then subtracts the owner side with
+// the already reverse-updated upper neighbours:
+//   psi_rev[c] = ( b'[c] - sum_{nbr faces asc} lower[f]*psi_fwd[l] - sum_{own faces asc} upper[f]*psi_rev[u] ) / diag[c]
+// ptr/col/val = U triangle (polled, rows in backward-wavefront order), ptr2/col2/val2 = L triangle read from `old`
+// (the forward result).
+__global__ void __launch_bounds__(256) k_gs_sweep_rev(SweepArgs a) {
+    const double sent = sentinel();
+    SWEEP_TASK_LOOP(a) {
+        const int2 next = SWEEP_NEXT_TASK(a);
+        if (lane < task.y) {
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
+            const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
+            const int k0 = a.ptr2[p], k1 = a.ptr2[p + 1];
+            const double dg = a.diag[p];
+            double acc = a.in[p];
+            for (int k = k0; k < k1; k++) acc -= a.val2[k] * a.old[a.col2[k]];
+            acc = gather_deps<false, false>(acc, 1.0, j0, j1, a.col, a.val, a.out, a.err);
+            st_l2(a.out + p, acc / dg);
+            if (a.clear) a.clear[p] = sent;
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Reductions: per-thread grid-stride partial -> warp shuffle -> shared memory -> one partial per block; the
 // last block to finish (atomic ticket) folds the partials in a fixed order.  Deterministic for a fixed grid.

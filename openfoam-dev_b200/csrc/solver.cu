@@ -520,7 +520,7 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
     const int n = D.nCells;
     if (n == 0) return;
     ensureLevelScratch(m, level);
-    if (smoother == B200LS_GAUSS_SEIDEL) {
+    if (smoother == B200LS_GAUSS_SEIDEL || smoother == B200LS_SYM_GAUSS_SEIDEL) {
         for (int sweep = 0; sweep < nSweeps; sweep++) {
             const double* bPrime = source;
             if (D.nIfaces) {
@@ -545,17 +545,44 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
             a.old = psi;
             a.out = spare;
             launchSweep(k_gs_sweep, a);
-            std::swap(psi, spare);
+            if (smoother == B200LS_GAUSS_SEIDEL) {
+                std::swap(psi, spare);
+                continue;
+            }
+            // symGaussSeidel: reverse loop over the forward result (symGaussSeidelSmoother.C:178-205)
+            fillSentinel(psi, n);
+            SweepArgs r{};
+            r.tasks = D.bwdTasks.p;
+            r.nTasks = D.nBwdTasks;
+            r.rowOf = D.bwdPos.p;
+            r.ptr = D.Uptr.p;
+            r.col = D.Ucol.p;
+            r.val = M.Uval();
+            r.ptr2 = D.Lptr.p;
+            r.col2 = D.Lcol.p;
+            r.val2 = M.Lval(D.nFaces);
+            r.diag = M.diag.p;
+            r.in = bPrime;
+            r.old = spare;
+            r.out = psi;
+            launchSweep(k_gs_sweep_rev, r);
         }
         return;
     }
     if (smoother == B200LS_DIC || smoother == B200LS_DILU) {
         // DICSmoother.C:84-115 / DILUSmoother.C: rA = residual ; rA = M^-1 rA ; psi += rA
+        ensureFactor(m, level, smoother);
         for (int sweep = 0; sweep < nSweeps; sweep++) {
             opResidual(m, level, M.tmpB.p, psi, source);
             opPrecondition(m, level, smoother, M.tmpC.p, M.tmpB.p);
             LAUNCH(k_add_inplace, gridStride(n), 256, psi, M.tmpC.p, n);
         }
+        return;
+    }
+    if (smoother == B200LS_DIC_GAUSS_SEIDEL || smoother == B200LS_DILU_GAUSS_SEIDEL) {
+        // DICGaussSeidelSmoother.C:79-89: nSweeps of DIC (DILU) followed by nSweeps of Gauss-Seidel
+        opSmooth(m, level, smoother == B200LS_DIC_GAUSS_SEIDEL ? B200LS_DIC : B200LS_DILU, psi, spare, source, nSweeps);
+        opSmooth(m, level, B200LS_GAUSS_SEIDEL, psi, spare, source, nSweeps);
         return;
     }
     throw CudaError("unknown smoother");
@@ -634,6 +661,25 @@ static void record(b200ls_perf* perf, const b200ls_controls& c, double r) {
     if (c.recordHistory && perf->nHistory < B200LS_MAX_HISTORY) perf->history[perf->nHistory++] = r;
 }
 
+// preconditioner dispatch of the Krylov solvers: DIC/DILU/diagonal/none per level, or GAMG V-cycles (finest level)
+static void gamgPrecondition(b200ls_matrix_s* m, const b200ls_controls& c, double* wA, const double* rA);
+static void buildCoarseMatrices(b200ls_matrix_s* m);
+
+static void preparePrecond(b200ls_matrix_s* m, const b200ls_controls& c, int lv) {
+    if (c.precond == B200LS_GAMG_PRECOND) {
+        if (lv != 0) throw CudaError("GAMG preconditioning is only available on the finest level");
+        if (m->levels.size() < 2) throw CudaError("preconditioner GAMG needs an agglomerated mesh");
+        buildCoarseMatrices(m);
+        return;
+    }
+    ensureFactor(m, lv, c.precond);
+}
+
+static void applyPrecond(b200ls_matrix_s* m, const b200ls_controls& c, int lv, double* wA, const double* rA) {
+    if (c.precond == B200LS_GAMG_PRECOND) gamgPrecondition(m, c, wA, rA);
+    else opPrecondition(m, lv, c.precond, wA, rA);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // PCG (PCG.C:65-193)
 // ------------------------------------------------------------------------------------------------------------
@@ -658,11 +704,11 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
 
     if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
     if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
-        ensureFactor(m, lv, c.precond);
+        preparePrecond(m, c, lv);
         do {
             const int cur = S_WARA0 + (perf->nIterations & 1);
             const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
-            opPrecondition(m, lv, c.precond, wA, rA);
+            applyPrecond(m, c, lv, wA, rA);
             reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
             allReduce(scalar(m, cur), 1);
             LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
@@ -719,7 +765,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
         double* tA = lvec(m, lv, "tA");
         double* rA0 = lvec(m, lv, "rA0");
         B2_CUDA(cudaMemcpyAsync(rA0, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
-        ensureFactor(m, lv, c.precond);
+        preparePrecond(m, c, lv);
         double omega = 0;
         do {
             const int cur = S_RHO0 + (perf->nIterations & 1);
@@ -737,7 +783,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
             }
             LAUNCH(k_bicg_update_p, gridStride(n), 256, pA, rA, AyA, m->scalars.p, cur, old, S_ALPHA, S_OMEGA,
                    perf->nIterations == 0 ? 1 : 0, n);
-            opPrecondition(m, lv, c.precond, yA, pA);
+            applyPrecond(m, c, lv, yA, pA);
             opAmul(m, lv, AyA, yA);
             reduce<RED_DOT>(scalar(m, S_RA0AYA), rA0, AyA, n);
             allReduce(scalar(m, S_RA0AYA), 1);
@@ -753,7 +799,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
                 perf->converged = 1;
                 return;
             }
-            opPrecondition(m, lv, c.precond, zA, sA);
+            applyPrecond(m, c, lv, zA, sA);
             opAmul(m, lv, tA, zA);
             // tAsA and tAtA in one pass (and one 2-element allreduce)
             LAUNCH(k_dot2, kReduceBlocks, kReduceThreads, scalar(m, S_TASA), sA, tA, tA, n, cx.partials.p,
@@ -785,7 +831,6 @@ static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& p
     perf->nIterations = 0;
     if (c.nSweeps < 0) {
         B2_CUDA(cudaEventRecord(evLoopStart, S()));
-        if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) ensureFactor(m, 0, c.precond);
         opSmooth(m, 0, c.precond, psi, spare, source, -c.nSweeps);
         perf->nIterations -= c.nSweeps;
         return;
@@ -803,7 +848,6 @@ static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& p
     perf->finalResidual = perf->initialResidual;
     B2_CUDA(cudaEventRecord(evLoopStart, S()));
     if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
-        if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) ensureFactor(m, 0, c.precond);
         do {
             opSmooth(m, 0, c.precond, psi, spare, source, c.nSweeps);
             opResidual(m, 0, rA, psi, source);
@@ -1176,21 +1220,45 @@ static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, d
         if (pre) LAUNCH(k_add_inplace, gridStride(D.nCells), 256, ML.corr.p, pre, D.nCells);
         double* corr = ML.corr.p;
         double* spare = ML.tmpC.p;
-        // GS swaps corr/spare; DIC smoothing uses tmpB/tmpC internally and leaves corr in place
-        if (c.precond == B200LS_GAUSS_SEIDEL) {
-            opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
-                     std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
-            if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
-        } else {
-            opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
-                     std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
-        }
+        // Gauss-Seidel sweeps swap corr/spare; the other smoothers leave corr in place
+        opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
+                 std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
+        if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
     }
 
     prolongTo(m, 0, finestCorrection, m->levels[1].corr.p);
     if (scaleCorrection) gamgScale(m, 0, finestCorrection, Apsi, finestResidual);
     LAUNCH(k_add_inplace, gridStride(n0), 256, psi, finestCorrection, n0);
     opSmooth(m, 0, c.precond, psi, psiSpare, source, c.nFinestSweeps);
+}
+
+// GAMGPreconditioner::precondition (GAMGPreconditioner.C:81-148): nVcycles V-cycles on A wA = rA from wA = 0
+static void gamgPrecondition(b200ls_matrix_s* m, const b200ls_controls& c, double* wA, const double* rA) {
+    const int n = DL(m, 0).nCells;
+    b200ls_controls g = c;
+    g.precond = c.precSmoother;
+    g.tolerance = c.precTolerance;       // inherited by the coarsest-level solver
+    g.relTol = c.precRelTol;
+    const bool scaleCorrection = g.scaleCorrection < 0 ? m->symmetric : (g.scaleCorrection != 0);
+    double* AwA = m->vec("gAwA");
+    double* finestCorrection = m->vec("gCorr");
+    double* finestResidual = m->vec("gRes");
+    double* psi = wA;
+    double* spare = m->vec("gSpare");
+    B2_CUDA(cudaMemsetAsync(psi, 0, sizeof(double) * n, S()));
+    B2_CUDA(cudaMemcpyAsync(finestResidual, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+    for (int cycle = 0; cycle < g.nVcycles; cycle++) {
+        vcycle(m, g, psi, spare, rA, AwA, finestCorrection, finestResidual, scaleCorrection);
+        if (cycle < g.nVcycles - 1) {
+            opAmul(m, 0, AwA, psi);
+            LAUNCH(k_sub, gridStride(n), 256, finestResidual, rA, AwA, n);
+        }
+    }
+    if (psi != wA) {
+        // Gauss-Seidel sweeps ping-pong between the two buffers: bring the result home
+        B2_CUDA(cudaMemcpyAsync(wA, psi, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+        // keep the named scratch vector pointing at its own storage (psi/spare were only swapped locally)
+    }
 }
 
 static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, double*& psiSpare,
@@ -1208,9 +1276,7 @@ static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi
 
     // solver construction: coarse matrices (+ smoother factorisations) -- timed as setup
     buildCoarseMatrices(m);
-    if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) {
-        for (int k = 0; k + 1 < int(m->levels.size()); k++) ensureFactor(m, k, c.precond);
-    }
+    // (DIC/DILU smoothers factorise lazily inside opSmooth, once per level per solve)
 
     opAmul(m, 0, Apsi, psi);
     const double nf = normFactor(m, 0, psi, source, Apsi, finestCorrection, globalCells(m));

@@ -133,12 +133,17 @@ static int preconditionerId(const word& name)
     if (name == "diagonal") return B200LS_DIAGONAL;
     if (name == "none") return B200LS_NONE;
     if (name == "GaussSeidel") return B200LS_GAUSS_SEIDEL;
+    if (name == "symGaussSeidel") return B200LS_SYM_GAUSS_SEIDEL;
+    if (name == "DICGaussSeidel") return B200LS_DIC_GAUSS_SEIDEL;
+    if (name == "DILUGaussSeidel") return B200LS_DILU_GAUSS_SEIDEL;
+    if (name == "GAMG") return B200LS_GAMG_PRECOND;
 
     FatalErrorInFunction
         << "preconditioner/smoother " << name
         << " is not provided by libB200LinearSolvers."
-        << " Valid: DIC DILU diagonal none (preconditioners),"
-        << " GaussSeidel DIC DILU (smoothers)"
+        << " Valid: DIC DILU diagonal none GAMG (preconditioners),"
+        << " GaussSeidel symGaussSeidel DIC DILU DICGaussSeidel"
+        << " DILUGaussSeidel (smoothers)"
         << exit(FatalError);
     return -1;
 }
@@ -256,6 +261,94 @@ protected:
         );
     }
 
+    //- Hand the reference's cached agglomeration (GAMGAgglomeration::New,
+    //  GAMGAgglomeration.C:349-400) to the library, once per mesh
+    void ensureAgglomeration(B200::cacheEntry& e, const dictionary& dict) const
+    {
+        if (e.agglomerated) return;
+
+        const GAMGAgglomeration& agg = GAMGAgglomeration::New(matrix_, dict);
+
+        std::vector<const int32_t*> maps;
+        std::vector<int32_t> nCoarse;
+        for (label lev = 0; lev < agg.size(); lev++)
+        {
+            maps.push_back(agg.restrictAddressing(lev).begin());
+            nCoarse.push_back(agg.nCells(lev));
+        }
+        if
+        (
+            b200ls_agglomerate_from_maps
+            (
+                e.mesh,
+                maps.size(),
+                maps.data(),
+                nCoarse.data()
+            ) < 0
+        )
+        {
+            FatalErrorInFunction
+                << "b200ls_agglomerate_from_maps failed: "
+                << b200ls_last_error() << exit(FatalError);
+        }
+        e.agglomerated = true;
+    }
+
+    //- GAMGSolver::readControls (GAMGSolver.C:348-371)
+    void readGAMGControls(b200ls_controls& c, const dictionary& dict) const
+    {
+        c.nPreSweeps = dict.lookupOrDefault<label>("nPreSweeps", 0);
+        c.preSweepsLevelMultiplier =
+            dict.lookupOrDefault<label>("preSweepsLevelMultiplier", 1);
+        c.maxPreSweeps = dict.lookupOrDefault<label>("maxPreSweeps", 4);
+        c.nPostSweeps = dict.lookupOrDefault<label>("nPostSweeps", 2);
+        c.postSweepsLevelMultiplier =
+            dict.lookupOrDefault<label>("postSweepsLevelMultiplier", 1);
+        c.maxPostSweeps = dict.lookupOrDefault<label>("maxPostSweeps", 4);
+        c.nFinestSweeps = dict.lookupOrDefault<label>("nFinestSweeps", 2);
+        c.scaleCorrection =
+            dict.lookupOrDefault<Switch>("scaleCorrection", matrix_.symmetric());
+
+        if (dict.lookupOrDefault<Switch>("interpolateCorrection", false))
+        {
+            FatalErrorInFunction
+                << "interpolateCorrection is not supported by libB200LinearSolvers"
+                << exit(FatalError);
+        }
+        if (dict.lookupOrDefault<Switch>("directSolveCoarsest", false))
+        {
+            FatalErrorInFunction
+                << "directSolveCoarsest is not supported by libB200LinearSolvers"
+                << exit(FatalError);
+        }
+    }
+
+    //- Preconditioner entry of a Krylov solver: a word, or a sub-dictionary
+    //  (lduMatrixPreconditioner.C:40-59); preconditioner GAMG takes its V-cycle
+    //  controls from the sub-dictionary (GAMGPreconditioner.C:47-79)
+    word readPreconditioner(b200ls_controls& c) const
+    {
+        const word precon(lduMatrix::preconditioner::getName(controlDict_));
+        c.precond = B200::preconditionerId(precon);
+
+        if (c.precond == B200LS_GAMG_PRECOND)
+        {
+            const Foam::entry& pe =
+                controlDict_.lookupEntry("preconditioner", false, false);
+            const dictionary& pd = pe.isDict() ? pe.dict() : controlDict_;
+
+            ensureAgglomeration(entry(), pd);
+            readGAMGControls(c, pd);
+            c.precSmoother =
+                B200::preconditionerId(word(pd.lookup("smoother")));
+            c.nVcycles = pd.lookupOrDefault<label>("nVcycles", 2);
+            c.precTolerance = pd.lookupOrDefault<scalar>("tolerance", 1e-6);
+            c.precRelTol = pd.lookupOrDefault<scalar>("relTol", 0);
+        }
+
+        return precon;
+    }
+
     //- Run the solve and translate the result
     solverPerformance run
     (
@@ -344,11 +437,10 @@ public:
         const direction cmpt = 0
     ) const
     {
-        const word precon(lduMatrix::preconditioner::getName(controlDict_));
         b200ls_controls c;
         b200ls_controls_default(&c);
         c.solver = B200LS_PCG;
-        c.precond = B200::preconditionerId(precon);
+        const word precon(readPreconditioner(c));
         return run(precon + "PCG", c, psi, source);
     }
 };
@@ -375,11 +467,10 @@ public:
         const direction cmpt = 0
     ) const
     {
-        const word precon(lduMatrix::preconditioner::getName(controlDict_));
         b200ls_controls c;
         b200ls_controls_default(&c);
         c.solver = B200LS_PBICGSTAB;
-        c.precond = B200::preconditionerId(precon);
+        const word precon(readPreconditioner(c));
         return run(precon + "PBiCGStab", c, psi, source);
     }
 };
@@ -442,72 +533,13 @@ public:
         const direction cmpt = 0
     ) const
     {
-        B200::cacheEntry& e = entry();
-
-        if (!e.agglomerated)
-        {
-            const GAMGAgglomeration& agg =
-                GAMGAgglomeration::New(matrix_, controlDict_);
-
-            std::vector<const int32_t*> maps;
-            std::vector<int32_t> nCoarse;
-            for (label lev = 0; lev < agg.size(); lev++)
-            {
-                maps.push_back(agg.restrictAddressing(lev).begin());
-                nCoarse.push_back(agg.nCells(lev));
-            }
-            if
-            (
-                b200ls_agglomerate_from_maps
-                (
-                    e.mesh,
-                    maps.size(),
-                    maps.data(),
-                    nCoarse.data()
-                ) < 0
-            )
-            {
-                FatalErrorInFunction
-                    << "b200ls_agglomerate_from_maps failed: "
-                    << b200ls_last_error() << exit(FatalError);
-            }
-            e.agglomerated = true;
-        }
+        ensureAgglomeration(entry(), controlDict_);
 
         b200ls_controls c;
         b200ls_controls_default(&c);
         c.solver = B200LS_GAMG;
         c.precond = B200::preconditionerId(word(controlDict_.lookup("smoother")));
-
-        // GAMGSolver::readControls (GAMGSolver.C:348-371)
-        c.nPreSweeps = controlDict_.lookupOrDefault<label>("nPreSweeps", 0);
-        c.preSweepsLevelMultiplier =
-            controlDict_.lookupOrDefault<label>("preSweepsLevelMultiplier", 1);
-        c.maxPreSweeps = controlDict_.lookupOrDefault<label>("maxPreSweeps", 4);
-        c.nPostSweeps = controlDict_.lookupOrDefault<label>("nPostSweeps", 2);
-        c.postSweepsLevelMultiplier =
-            controlDict_.lookupOrDefault<label>("postSweepsLevelMultiplier", 1);
-        c.maxPostSweeps = controlDict_.lookupOrDefault<label>("maxPostSweeps", 4);
-        c.nFinestSweeps = controlDict_.lookupOrDefault<label>("nFinestSweeps", 2);
-        c.scaleCorrection =
-            controlDict_.lookupOrDefault<Switch>
-            (
-                "scaleCorrection",
-                matrix_.symmetric()
-            );
-
-        if (controlDict_.lookupOrDefault<Switch>("interpolateCorrection", false))
-        {
-            FatalErrorInFunction
-                << "interpolateCorrection is not supported by B200GAMG"
-                << exit(FatalError);
-        }
-        if (controlDict_.lookupOrDefault<Switch>("directSolveCoarsest", false))
-        {
-            FatalErrorInFunction
-                << "directSolveCoarsest is not supported by B200GAMG"
-                << exit(FatalError);
-        }
+        readGAMGControls(c, controlDict_);
 
         return run("GAMG", c, psi, source);
     }

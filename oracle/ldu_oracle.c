@@ -32,6 +32,9 @@ typedef struct {
     int32_t nSweeps;
     int32_t nPreSweeps, preSweepsLevelMultiplier, maxPreSweeps;
     int32_t nPostSweeps, postSweepsLevelMultiplier, maxPostSweeps, nFinestSweeps, scaleCorrection;
+    int32_t precSmoother, nVcycles;   /* preconditioner GAMG (kind 8): smoother and cycles of the V-cycles */
+    double precTolerance, precRelTol; /* ... and the tolerances its coarsest-level solver inherits */
+    void* hierarchy;               /* hierarchy_t* for preconditioner GAMG */
 } ctl_t;
 
 static const double VSMALL = 2.2250738585072014e-308; /* vSmall, primitives/Scalar/doubleScalar/doubleScalar.H:57 */
@@ -131,6 +134,35 @@ static int32_t* make_owner_start(const ldu_t* A) {
 
 void oracle_smooth(const ldu_t* A, int kind, double* psi, const double* source, int nSweeps) {
     const int n = A->nCells;
+    if (kind == 6 || kind == 7) {                          /* DICGaussSeidel / DILUGaussSeidel: DICGaussSeidelSmoother.C:79-89 */
+        oracle_smooth(A, kind == 6 ? 2 : 3, psi, source, nSweeps);
+        oracle_smooth(A, 4, psi, source, nSweeps);
+        return;
+    }
+    if (kind == 5) {                                       /* symGaussSeidelSmoother.C:125-206 */
+        int32_t* os = make_owner_start(A);
+        double* bPrime = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        for (int sweep = 0; sweep < nSweeps; sweep++) {
+            memcpy(bPrime, source, sizeof(double) * (size_t)n);
+            for (int c = 0; c < n; c++) {
+                double psii = bPrime[c];
+                for (int f = os[c]; f < os[c + 1]; f++) psii -= A->upper[f] * psi[A->u[f]];
+                psii /= A->diag[c];
+                for (int f = os[c]; f < os[c + 1]; f++) bPrime[A->u[f]] -= A->lower[f] * psii;
+                psi[c] = psii;
+            }
+            for (int c = n - 1; c >= 0; c--) {
+                double psii = bPrime[c];
+                for (int f = os[c]; f < os[c + 1]; f++) psii -= A->upper[f] * psi[A->u[f]];
+                psii /= A->diag[c];
+                for (int f = os[c]; f < os[c + 1]; f++) bPrime[A->u[f]] -= A->lower[f] * psii;
+                psi[c] = psii;
+            }
+        }
+        free(bPrime);
+        free(os);
+        return;
+    }
     if (kind == 4) {
         int32_t* os = make_owner_start(A);
         double* bPrime = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
@@ -197,6 +229,13 @@ static void record(perf_t* p) {
     if (p->nHistory < 4096) p->history[p->nHistory++] = p->finalResidual;
 }
 
+static void gamg_precondition(const ctl_t* c, const double* rA, double* wA);
+
+static void apply_precond(const ldu_t* A, const ctl_t* c, const double* rD, const double* rA, double* wA) {
+    if (c->precond == 8) gamg_precondition(c, rA, wA);
+    else oracle_precondition(A, c->precond, rD, rA, wA);
+}
+
 /* ---- PCG (solvers/PCG/PCG.C:65-193) ---- */
 
 void oracle_pcg(const ldu_t* A, const ctl_t* c, double* psi, const double* source, perf_t* perf) {
@@ -215,7 +254,7 @@ void oracle_pcg(const ldu_t* A, const ctl_t* c, double* psi, const double* sourc
         make_rD(A, c->precond, rD);
         do {
             wArAold = wArA;
-            oracle_precondition(A, c->precond, rD, rA, wA);
+            apply_precond(A, c, rD, rA, wA);
             wArA = sum_prod(wA, rA, n);
             if (perf->nIterations == 0) {
                 for (int i = 0; i < n; i++) pA[i] = wA[i];
@@ -278,7 +317,7 @@ void oracle_pbicgstab(const ldu_t* A, const ctl_t* c, double* psi, const double*
                 const double beta = (rA0rA / rA0rAold) * (alpha / omega);
                 for (int i = 0; i < n; i++) pA[i] = rA[i] + beta * (pA[i] - omega * AyA[i]);
             }
-            oracle_precondition(A, c->precond, rD, pA, yA);
+            apply_precond(A, c, rD, pA, yA);
             oracle_amul(A, yA, AyA);
             const double rA0AyA = sum_prod(rA0, AyA, n);
             alpha = rA0rA / rA0AyA;
@@ -291,7 +330,7 @@ void oracle_pbicgstab(const ldu_t* A, const ctl_t* c, double* psi, const double*
                 free(pA);
                 return;
             }
-            oracle_precondition(A, c->precond, rD, sA, zA);
+            apply_precond(A, c, rD, sA, zA);
             oracle_amul(A, zA, tA);
             double tAtA = 0;
             for (int i = 0; i < n; i++) tAtA += tA[i] * tA[i];
@@ -576,13 +615,102 @@ static void gamg_scale(const level_t* L, double* field, double* Acf, const doubl
     for (int i = 0; i < L->nCells; i++) field[i] = sf * field[i] + (source[i] - sf * Acf[i]) / L->diag[i];
 }
 
+/* one V-cycle (GAMGSolverSolve.C:148-443) */
+static void gamg_vcycle(hierarchy_t* H, const ctl_t* c, double* psi, const double* source, double* Apsi,
+                        double* finestCorrection, double* finestResidual, double* scratch) {
+    const level_t* L0 = &H->lev[0];
+    const int n = L0->nCells;
+    const int coarsest = H->nLevels - 2;                   /* index into the reference's matrixLevels_ */
+    const int scale = c->scaleCorrection < 0 ? H->symmetric : c->scaleCorrection;
+    ldu_t A0 = as_ldu(L0);
+    ctl_t cc = *c;                                         /* coarsest solver: same tolerance/relTol, defaults else */
+    cc.maxIter = 1000;
+    cc.minIter = 0;
+    cc.precond = H->symmetric ? 2 : 3;
+    restrict_field(H->lev[1].src, finestResidual, L0->restrictAddr, n, H->lev[1].nCells);
+    for (int l = 0; l < coarsest; l++) {
+        level_t* L = &H->lev[l + 1];
+        if (c->nPreSweeps) {
+            ldu_t A = as_ldu(L);
+            for (int i = 0; i < L->nCells; i++) L->corr[i] = 0;
+            int ns = c->nPreSweeps + c->preSweepsLevelMultiplier * l;
+            if (ns > c->maxPreSweeps) ns = c->maxPreSweeps;
+            oracle_smooth(&A, c->precond, L->corr, L->src, ns);
+            if (scale && l < coarsest - 1) gamg_scale(L, L->corr, scratch, L->src);
+            oracle_amul(&A, L->corr, scratch);
+            for (int i = 0; i < L->nCells; i++) L->src[i] -= scratch[i];
+        }
+        restrict_field(H->lev[l + 2].src, L->src, L->restrictAddr, L->nCells, H->lev[l + 2].nCells);
+    }
+    {   /* solveCoarsestLevel */
+        level_t* L = &H->lev[coarsest + 1];
+        ldu_t A = as_ldu(L);
+        perf_t cp;
+        for (int i = 0; i < L->nCells; i++) L->corr[i] = 0;
+        if (L->nFaces == 0) {
+            for (int i = 0; i < L->nCells; i++) L->corr[i] = L->src[i] / L->diag[i];
+        } else if (H->symmetric) {
+            oracle_pcg(&A, &cc, L->corr, L->src, &cp);
+        } else {
+            oracle_pbicgstab(&A, &cc, L->corr, L->src, &cp);
+        }
+    }
+    for (int l = coarsest - 1; l >= 0; l--) {
+        level_t* L = &H->lev[l + 1];
+        ldu_t A = as_ldu(L);
+        double* pre = NULL;
+        if (c->nPreSweeps) {
+            pre = malloc(sizeof(double) * (size_t)L->nCells);
+            memcpy(pre, L->corr, sizeof(double) * (size_t)L->nCells);
+        }
+        for (int i = 0; i < L->nCells; i++) L->corr[i] = H->lev[l + 2].corr[L->restrictAddr[i]];
+        if (scale && l < coarsest - 1) gamg_scale(L, L->corr, scratch, L->src);
+        if (pre) {
+            for (int i = 0; i < L->nCells; i++) L->corr[i] += pre[i];
+            free(pre);
+        }
+        int ns = c->nPostSweeps + c->postSweepsLevelMultiplier * l;
+        if (ns > c->maxPostSweeps) ns = c->maxPostSweeps;
+        oracle_smooth(&A, c->precond, L->corr, L->src, ns);
+    }
+    for (int i = 0; i < n; i++) finestCorrection[i] = H->lev[1].corr[L0->restrictAddr[i]];
+    if (scale) gamg_scale(L0, finestCorrection, Apsi, finestResidual);
+    for (int i = 0; i < n; i++) psi[i] += finestCorrection[i];
+    oracle_smooth(&A0, c->precond, psi, source, c->nFinestSweeps);
+}
+
+void oracle_gamg_set_matrix(hierarchy_t* H, const double* diag, const double* upper, const double* lower) {
+    gamg_set_matrix(H, diag, upper, lower);
+}
+
+/* GAMGPreconditioner::precondition (preconditioners/GAMGPreconditioner/GAMGPreconditioner.C:81-148) */
+static void gamg_precondition(const ctl_t* c, const double* rA, double* wA) {
+    hierarchy_t* H = (hierarchy_t*)c->hierarchy;
+    const int n = H->lev[0].nCells;
+    ldu_t A0 = as_ldu(&H->lev[0]);
+    ctl_t g = *c;
+    g.precond = c->precSmoother;
+    g.tolerance = c->precTolerance;
+    g.relTol = c->precRelTol;
+    double* AwA = malloc(sizeof(double) * (size_t)n * 4);
+    double *finestCorrection = AwA + n, *finestResidual = finestCorrection + n, *scratch = finestResidual + n;
+    for (int i = 0; i < n; i++) { wA[i] = 0.0; finestResidual[i] = rA[i]; }
+    for (int cycle = 0; cycle < g.nVcycles; cycle++) {
+        gamg_vcycle(H, &g, wA, rA, AwA, finestCorrection, finestResidual, scratch);
+        if (cycle < g.nVcycles - 1) {
+            oracle_amul(&A0, wA, AwA);
+            for (int i = 0; i < n; i++) finestResidual[i] = rA[i] - AwA[i];
+        }
+    }
+    free(AwA);
+}
+
+/* GAMGSolver::solve (GAMGSolverSolve.C:31-145) */
 void oracle_gamg_solve(hierarchy_t* H, const double* diag, const double* upper, const double* lower,
                        const ctl_t* c, double* psi, const double* source, perf_t* perf) {
     gamg_set_matrix(H, diag, upper, lower);
     const level_t* L0 = &H->lev[0];
     const int n = L0->nCells;
-    const int coarsest = H->nLevels - 2;                   /* index into the reference's matrixLevels_ */
-    const int scale = c->scaleCorrection < 0 ? H->symmetric : c->scaleCorrection;
     ldu_t A0 = as_ldu(L0);
     double* Apsi = malloc(sizeof(double) * (size_t)n * 4);
     double *finestCorrection = Apsi + n, *finestResidual = finestCorrection + n, *scratch = finestResidual + n;
@@ -593,64 +721,9 @@ void oracle_gamg_solve(hierarchy_t* H, const double* diag, const double* upper, 
     for (int i = 0; i < n; i++) finestResidual[i] = source[i] - Apsi[i];
     perf->initialResidual = sum_mag(finestResidual, n) / nf;
     perf->finalResidual = perf->initialResidual;
-    ctl_t cc = *c;                                         /* coarsest solver: same tolerance/relTol, defaults else */
-    cc.maxIter = 1000;
-    cc.minIter = 0;
-    cc.precond = H->symmetric ? 2 : 3;
     if (c->minIter > 0 || !converged(perf, c->tolerance, c->relTol)) {
         do {
-            /* ---- Vcycle ---- */
-            restrict_field(H->lev[1].src, finestResidual, L0->restrictAddr, n, H->lev[1].nCells);
-            for (int l = 0; l < coarsest; l++) {
-                level_t* L = &H->lev[l + 1];
-                if (c->nPreSweeps) {
-                    ldu_t A = as_ldu(L);
-                    for (int i = 0; i < L->nCells; i++) L->corr[i] = 0;
-                    int ns = c->nPreSweeps + c->preSweepsLevelMultiplier * l;
-                    if (ns > c->maxPreSweeps) ns = c->maxPreSweeps;
-                    oracle_smooth(&A, c->precond, L->corr, L->src, ns);
-                    if (scale && l < coarsest - 1) gamg_scale(L, L->corr, scratch, L->src);
-                    oracle_amul(&A, L->corr, scratch);
-                    for (int i = 0; i < L->nCells; i++) L->src[i] -= scratch[i];
-                }
-                restrict_field(H->lev[l + 2].src, L->src, L->restrictAddr, L->nCells, H->lev[l + 2].nCells);
-            }
-            {   /* solveCoarsestLevel */
-                level_t* L = &H->lev[coarsest + 1];
-                ldu_t A = as_ldu(L);
-                perf_t cp;
-                for (int i = 0; i < L->nCells; i++) L->corr[i] = 0;
-                if (L->nFaces == 0) {
-                    for (int i = 0; i < L->nCells; i++) L->corr[i] = L->src[i] / L->diag[i];
-                } else if (H->symmetric) {
-                    oracle_pcg(&A, &cc, L->corr, L->src, &cp);
-                } else {
-                    oracle_pbicgstab(&A, &cc, L->corr, L->src, &cp);
-                }
-            }
-            for (int l = coarsest - 1; l >= 0; l--) {
-                level_t* L = &H->lev[l + 1];
-                ldu_t A = as_ldu(L);
-                double* pre = NULL;
-                if (c->nPreSweeps) {
-                    pre = malloc(sizeof(double) * (size_t)L->nCells);
-                    memcpy(pre, L->corr, sizeof(double) * (size_t)L->nCells);
-                }
-                for (int i = 0; i < L->nCells; i++) L->corr[i] = H->lev[l + 2].corr[L->restrictAddr[i]];
-                if (scale && l < coarsest - 1) gamg_scale(L, L->corr, scratch, L->src);
-                if (pre) {
-                    for (int i = 0; i < L->nCells; i++) L->corr[i] += pre[i];
-                    free(pre);
-                }
-                int ns = c->nPostSweeps + c->postSweepsLevelMultiplier * l;
-                if (ns > c->maxPostSweeps) ns = c->maxPostSweeps;
-                oracle_smooth(&A, c->precond, L->corr, L->src, ns);
-            }
-            for (int i = 0; i < n; i++) finestCorrection[i] = H->lev[1].corr[L0->restrictAddr[i]];
-            if (scale) gamg_scale(L0, finestCorrection, Apsi, finestResidual);
-            for (int i = 0; i < n; i++) psi[i] += finestCorrection[i];
-            oracle_smooth(&A0, c->precond, psi, source, c->nFinestSweeps);
-            /* ---- residual ---- */
+            gamg_vcycle(H, c, psi, source, Apsi, finestCorrection, finestResidual, scratch);
             oracle_amul(&A0, psi, Apsi);
             for (int i = 0; i < n; i++) finestResidual[i] = source[i] - Apsi[i];
             perf->finalResidual = sum_mag(finestResidual, n) / nf;

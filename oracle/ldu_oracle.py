@@ -7,7 +7,8 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libldu_oracle.so"
-PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2, "DILU": 3, "GaussSeidel": 4}
+PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2, "DILU": 3, "GaussSeidel": 4, "symGaussSeidel": 5,
+            "DICGaussSeidel": 6, "DILUGaussSeidel": 7, "GAMG": 8}
 
 
 class Ldu(C.Structure):
@@ -26,7 +27,8 @@ class Ctl(C.Structure):
                 ("precond", C.c_int32), ("nSweeps", C.c_int32), ("nPreSweeps", C.c_int32),
                 ("preSweepsLevelMultiplier", C.c_int32), ("maxPreSweeps", C.c_int32), ("nPostSweeps", C.c_int32),
                 ("postSweepsLevelMultiplier", C.c_int32), ("maxPostSweeps", C.c_int32), ("nFinestSweeps", C.c_int32),
-                ("scaleCorrection", C.c_int32)]
+                ("scaleCorrection", C.c_int32), ("precSmoother", C.c_int32), ("nVcycles", C.c_int32),
+                ("precTolerance", C.c_double), ("precRelTol", C.c_double), ("hierarchy", C.c_void_p)]
 
 
 _lib = None
@@ -47,6 +49,7 @@ def lib():
         _lib.oracle_gamg_solve.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.POINTER(Ctl), C.c_void_p, C.c_void_p,
                                                                              C.POINTER(Perf)]
         _lib.oracle_gamg_free.argtypes = [C.c_void_p]
+        _lib.oracle_gamg_set_matrix.argtypes = [C.c_void_p] * 4
     return _lib
 
 
@@ -71,9 +74,11 @@ class System:
 
 def controls(precond="DIC", tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, nSweeps=1, nPreSweeps=0,
              preSweepsLevelMultiplier=1, maxPreSweeps=4, nPostSweeps=2, postSweepsLevelMultiplier=1, maxPostSweeps=4,
-             nFinestSweeps=2, scaleCorrection=-1):
+             nFinestSweeps=2, scaleCorrection=-1, precSmoother="GaussSeidel", nVcycles=2, precTolerance=1e-6,
+             precRelTol=0.0):
     return Ctl(tolerance, relTol, maxIter, minIter, PRECONDS[precond], nSweeps, nPreSweeps, preSweepsLevelMultiplier,
-               maxPreSweeps, nPostSweeps, postSweepsLevelMultiplier, maxPostSweeps, nFinestSweeps, scaleCorrection)
+               maxPreSweeps, nPostSweeps, postSweepsLevelMultiplier, maxPostSweeps, nFinestSweeps, scaleCorrection,
+               PRECONDS[precSmoother], nVcycles, precTolerance, precRelTol, None)
 
 
 def amul(S, x):
@@ -143,7 +148,18 @@ def solve(S, solver, ctl, source, psi0=None):
     else:
         fn = {"PCG": lib().oracle_pcg, "PBiCGStab": lib().oracle_pbicgstab,
               "smoothSolver": lib().oracle_smooth_solver}[solver]
-        fn(C.byref(S.c), C.byref(ctl), _p(x), _p(b), C.byref(p))
+        H = None
+        if ctl.precond == PRECONDS["GAMG"]:     # preconditioner GAMG: build the hierarchy + coarse matrices first
+            H = lib().oracle_gamg_build(S.n, S.l.size, _p(S.l), _p(S.u), _p(np.ascontiguousarray(S.face_weights)),
+                                        10, 1)
+            lib().oracle_gamg_set_matrix(H, _p(S.diag), _p(S.upper), None if S.symmetric else _p(S.lower))
+            ctl.hierarchy = H
+        try:
+            fn(C.byref(S.c), C.byref(ctl), _p(x), _p(b), C.byref(p))
+        finally:
+            if H:
+                lib().oracle_gamg_free(H)
+                ctl.hierarchy = None
     return x, _perf(p)
 
 

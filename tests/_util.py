@@ -28,12 +28,22 @@ def system_from_entries(inp):
 
 
 def parse_dict(text):
-    """'solver PCG; preconditioner DIC; tolerance 1e-6;' -> {'solver': 'PCG', ...}"""
+    """'solver PCG; preconditioner DIC; tolerance 1e-6;' -> {'solver': 'PCG', ...}.  A sub-dictionary
+    'preconditioner { preconditioner GAMG; smoother GaussSeidel; ... }' becomes out['preconditioner'] = {...}."""
     out = {}
+    sub = None
+    if "{" in text:
+        head, rest = text.split("{", 1)
+        body, tail = rest.split("}", 1)
+        key = head.split(";")[-1].split()[0]
+        sub = (key, parse_dict(body))
+        text = ";".join(head.split(";")[:-1]) + ";" + tail
     for item in text.split(";"):
         parts = item.split()
         if len(parts) >= 2:
             out[parts[0]] = parts[1]
+    if sub:
+        out[sub[0]] = sub[1]
     return out
 
 
@@ -50,8 +60,20 @@ def controls_from_dict(text, **extra):
             kw[k] = int(v)
         elif k in _FLT_KEYS:
             kw[k] = float(v)
+    pre = d.get("preconditioner")
+    if isinstance(pre, dict):
+        # preconditioner GAMG: V-cycle controls come from the sub-dictionary (GAMGPreconditioner.C:47-62)
+        sub = pre
+        pre = sub["preconditioner"]
+        kw["precSmoother"] = sub.get("smoother", "GaussSeidel")
+        kw["nVcycles"] = int(sub.get("nVcycles", 2))
+        kw["precTolerance"] = float(sub.get("tolerance", 1e-6))
+        kw["precRelTol"] = float(sub.get("relTol", 0))
+        for k, v in sub.items():
+            if k in _INT_KEYS and k not in ("maxIter", "minIter", "nSweeps"):
+                kw[k] = int(v)
     kw.update(extra)
-    return capi.controls(solver=d["solver"], preconditioner=d.get("preconditioner"), smoother=d.get("smoother"), **kw)
+    return capi.controls(solver=d["solver"], preconditioner=pre, smoother=d.get("smoother"), **kw)
 
 
 def solve_keys(inp):

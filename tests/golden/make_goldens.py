@@ -48,6 +48,11 @@ SYM_SOLVES = [
     ("solver GAMG; smoother GaussSeidel; tolerance 1e-6; relTol 0.01; nPreSweeps 1; nFinestSweeps 3;", 0),
     ("solver smoothSolver; smoother GaussSeidel; nSweeps 2; tolerance 1e-3; relTol 0; maxIter 40;", 0),
     ("solver smoothSolver; smoother DIC; nSweeps 1; tolerance 1e-3; relTol 0; maxIter 40;", 0),
+    ("solver smoothSolver; smoother symGaussSeidel; nSweeps 1; tolerance 1e-3; relTol 0; maxIter 30;", 0),
+    ("solver GAMG; smoother DICGaussSeidel; tolerance 1e-8; relTol 0;", 0),
+    ("solver GAMG; smoother symGaussSeidel; tolerance 1e-8; relTol 0;", 0),
+    ("solver PCG; preconditioner { preconditioner GAMG; smoother GaussSeidel; nVcycles 2; tolerance 1e-5; "
+     "relTol 0; } tolerance 1e-9; relTol 0;", 12),
 ]
 
 ASYM_SOLVES = [
@@ -58,6 +63,10 @@ ASYM_SOLVES = [
     ("solver GAMG; smoother DILU; tolerance 1e-8; relTol 0;", 20),
     ("solver smoothSolver; smoother GaussSeidel; nSweeps 1; tolerance 1e-6; relTol 0; maxIter 60;", 0),
     ("solver smoothSolver; smoother DILU; nSweeps 2; tolerance 1e-6; relTol 0; maxIter 60;", 0),
+    ("solver smoothSolver; smoother symGaussSeidel; nSweeps 2; tolerance 1e-6; relTol 0; maxIter 60;", 0),
+    ("solver GAMG; smoother DILUGaussSeidel; tolerance 1e-8; relTol 0;", 0),
+    ("solver PBiCGStab; preconditioner { preconditioner GAMG; smoother GaussSeidel; nVcycles 1; tolerance 1e-5; "
+     "relTol 0; } tolerance 1e-9; relTol 0;", 8),
 ]
 
 
@@ -85,8 +94,10 @@ def fixture(name, sys_, solves, smoothers, agglom=True):
 def main():
     if not (ROOT / "oracle/_ref/ref_harness").exists():
         sys.exit("oracle/_ref/ref_harness missing: run python oracle/build_ref.py first")
-    sym_sm = [("smoother GaussSeidel;", 1), ("smoother GaussSeidel;", 3), ("smoother DIC;", 2)]
-    asym_sm = [("smoother GaussSeidel;", 2), ("smoother DILU;", 2)]
+    sym_sm = [("smoother GaussSeidel;", 1), ("smoother GaussSeidel;", 3), ("smoother DIC;", 2),
+              ("smoother symGaussSeidel;", 2), ("smoother DICGaussSeidel;", 1)]
+    asym_sm = [("smoother GaussSeidel;", 2), ("smoother DILU;", 2), ("smoother symGaussSeidel;", 1),
+               ("smoother DILUGaussSeidel;", 2)]
     # config 1: the cavity tutorial mesh, 20x20x1, uniform Laplacian (PCG+DIC as icoFoam/cavity ships it)
     fixture("cavity_20x20x1", cases.cavity_laplacian(20, 20, 1), SYM_SOLVES, sym_sm)
     fixture("block_7x5x3_rand", cases.cavity_laplacian(7, 5, 3, coeffs="random", rhs_kind="uniform"),

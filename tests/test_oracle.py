@@ -61,7 +61,12 @@ def test_solvers_bit_exact(fx):
         d = parse_dict(text)
         kw = {k: (float(v) if k in ("tolerance", "relTol") else int(v)) for k, v in d.items()
               if k not in ("solver", "preconditioner", "smoother")}
-        ctl = orc.controls(precond=d.get("preconditioner") or d.get("smoother"), **kw)
+        pre = d.get("preconditioner") or d.get("smoother")
+        if isinstance(pre, dict):
+            sub, pre = pre, pre["preconditioner"]
+            kw.update(precSmoother=sub.get("smoother", "GaussSeidel"), nVcycles=int(sub.get("nVcycles", 2)),
+                      precTolerance=float(sub.get("tolerance", 1e-6)), precRelTol=float(sub.get("relTol", 0)))
+        ctl = orc.controls(precond=pre, **kw)
         psi, perf = orc.solve(S, d["solver"], ctl, s.source)
         rperf = ref[f"solve.{i}.perf"]
         ctx = (name, text, perf["nIterations"], rperf[2], perf["finalResidual"], rperf[1])
