@@ -146,6 +146,34 @@ def convection_diffusion(nx, ny, nz=1, nu=0.01, dt_coeff=0.5, seed=20261017, rhs
     )
 
 
+def random_graph(n_cells, avg_degree=5, symmetric=True, seed=20261017, max_span=None):
+    """Unstructured stand-in: a random upper-triangular-ordered LDU graph (every cell owns a few faces to random
+    higher-numbered cells within `max_span`), random coefficients, strictly diagonally dominant.  Exercises rows
+    with many neighbours, irregular wavefronts and irregular agglomeration."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    span = max_span or max(8, n_cells // 6)
+    lower, upper = [], []
+    for c in range(n_cells - 1):
+        k = min(n_cells - 1 - c, rng.integers(1, 2 * avg_degree // 2 + 2))
+        hi = min(n_cells, c + 1 + span)
+        nb = np.unique(rng.integers(c + 1, hi, size=k))
+        if c + 1 not in nb and rng.random() < 0.7:
+            nb = np.unique(np.append(nb, c + 1))      # keep the graph connected-ish
+        lower.extend([c] * nb.size)
+        upper.extend(nb.tolist())
+    lower = np.array(lower, dtype=np.int32)
+    upper = np.array(upper, dtype=np.int32)
+    nf = lower.size
+    up = -(0.5 + rng.random(nf))
+    lo = None if symmetric else -(0.5 + rng.random(nf))
+    diag = np.zeros(n_cells)
+    np.add.at(diag, lower, np.abs(up))
+    np.add.at(diag, upper, np.abs(up if lo is None else lo))
+    diag = diag * (1.0 + 0.05 * rng.random(n_cells)) + 0.01
+    return LduSystem(n_cells=n_cells, lower=lower, upper=upper, diag=diag, upper_coeffs=up, lower_coeffs=lo,
+                     source=rng.uniform(-1.0, 1.0, n_cells), face_weights=0.5 + rng.random(nf))
+
+
 def to_entries(sys_: LduSystem):
     """B2LS entries understood by oracle/ref_harness.C and the C oracle."""
     e = {

@@ -81,6 +81,61 @@ __global__ void k_div(double* __restrict__ out, const double* __restrict__ x, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// grid-wide reduction helper (used by the reductions below and by the fused sweep / SpMV epilogues)
+// ------------------------------------------------------------------------------------------------------------
+
+static constexpr int kReduceBlocks = 592;    // 4 per SM on 148 SMs
+static constexpr int kReduceThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-level sum of up to 2 values; returns true in the single thread that holds the grid totals.
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials,
+                                            unsigned int* __restrict__ ticket) {
+    __shared__ double sm[NV][kReduceThreads / 32];
+    __shared__ bool isLast;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) sm[k][w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = lane < (blockDim.x >> 5) ? sm[k][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) partials[k * gridDim.x + blockIdx.x] = s;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return false;
+    __threadfence();
+    // fixed-order fold of the block partials by warp 0
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = 0.0;
+            for (int i = lane; i < gridDim.x; i += 32) s += ld_l2(partials + k * gridDim.x + i);
+            v[k] = warp_sum(s);
+        }
+        return lane == 0;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // SpMV family: lduMatrix::Amul / residual / sumA  (lduMatrixATmul.C:34-92, 203-280, 154-200)
 // ------------------------------------------------------------------------------------------------------------
 
@@ -152,6 +207,32 @@ k_spmv_sym(double* __restrict__ out, double* __restrict__ out2, const double* __
     if (MODE == SPMV_AMUL_AND_RESIDUAL) out2[p] = b[p] - acc;
 }
 
+// wA = A pA fused with wApA = wA.pA (PCG.C:159-161).  Grid-stride over rows with a bounded grid so that the
+// per-block partials fit the reduction scratch.
+template <bool SYM>
+__global__ void __launch_bounds__(256)
+k_spmv_dot(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ diag,
+           const int* __restrict__ Lptr, const int* __restrict__ Lcol, const double* __restrict__ Lval,
+           const unsigned char* __restrict__ Lslot, const int* __restrict__ Uptr, const int* __restrict__ Ucol,
+           const double* __restrict__ Uval, int n, double* __restrict__ dotOut, double* __restrict__ partials,
+           unsigned int* __restrict__ ticket) {
+    double v[1] = {0.0};
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int l0 = Lptr[p], l1 = Lptr[p + 1];
+        const int u0 = Uptr[p], u1 = Uptr[p + 1];
+        const double xp = x[p];
+        double acc = diag[p] * xp;
+        for (int j = l0; j < l1; j++) {
+            const int q = Lcol[j];
+            acc += (SYM ? Uval[Uptr[q] + Lslot[j]] : Lval[j]) * x[q];
+        }
+        for (int j = u0; j < u1; j++) acc += Uval[j] * x[Ucol[j]];
+        out[p] = acc;
+        v[0] += acc * xp;
+    }
+    if (grid_reduce<1>(v, partials, ticket)) dotOut[0] = v[0];
+}
+
 // Coupled-interface epilogue: result[faceCells[i]] -= coeffs[i]*recv[i] in (patch, face) order
 // (processorFvPatchScalarField.C:133-136).  One thread per boundary row.  sign = +1 for Amul, -1 when the
 // caller negated the coefficients (residual, GaussSeidel).
@@ -219,6 +300,11 @@ struct SweepArgs {
     double* out2;           // optional second output (factor: rD)
     double* clear;          // optional: array whose entry p is reset to the sentinel once row p is done
     int* err;
+    // optional fused dot product of the result with another vector (PCG: wArA = wA.rA, PCG.C:138)
+    const double* dotWith;
+    double* dotOut;
+    double* partials;
+    unsigned int* ticket;
 };
 
 // Dependency gather of one row: acc -= (scale*val[j]) * y[col[j]] for j ascending (DESC=false) or descending
@@ -354,6 +440,7 @@ __global__ void __launch_bounds__(256) k_sweep_fwd(SweepArgs a) {
 // backward substitution:  z[l] = y[l] - sum_{f descending} (rD[l]*upper[f]) * z[upper(f)]
 __global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
     const double sent = sentinel();
+    double dsum[1] = {0.0};
     SWEEP_TASK_LOOP(a) {
         const int2 next = SWEEP_NEXT_TASK(a);
         if (lane < task.y) {
@@ -364,9 +451,13 @@ __global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
             acc = gather_deps<true, true>(acc, rd, j0, j1, a.col, a.val, a.out, a.err);
             st_l2(a.out + p, acc);
             if (a.clear) a.clear[p] = sent;
+            if (a.dotWith) dsum[0] += acc * a.dotWith[p];
         }
         __syncwarp();
         task = next;
+    }
+    if (a.dotWith) {
+        if (grid_reduce<1>(dsum, a.partials, a.ticket)) a.dotOut[0] = dsum[0];
     }
 }
 
@@ -430,57 +521,6 @@ __global__ void __launch_bounds__(256) k_gs_sweep_rev(SweepArgs a) {
 // Reductions: per-thread grid-stride partial -> warp shuffle -> shared memory -> one partial per block; the
 // last block to finish (atomic ticket) folds the partials in a fixed order.  Deterministic for a fixed grid.
 // ------------------------------------------------------------------------------------------------------------
-
-static constexpr int kReduceBlocks = 592;    // 4 per SM on 148 SMs
-static constexpr int kReduceThreads = 256;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// Block-level sum of up to 2 values; returns true in the single thread that holds the grid totals.
-template <int NV>
-__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials,
-                                            unsigned int* __restrict__ ticket) {
-    __shared__ double sm[NV][kReduceThreads / 32];
-    __shared__ bool isLast;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        v[k] = warp_sum(v[k]);
-        if (lane == 0) sm[k][w] = v[k];
-    }
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double s = lane < (blockDim.x >> 5) ? sm[k][lane] : 0.0;
-            s = warp_sum(s);
-            if (lane == 0) partials[k * gridDim.x + blockIdx.x] = s;
-        }
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-        isLast = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!isLast) return false;
-    __threadfence();
-    // fixed-order fold of the block partials by warp 0
-    if (w == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double s = 0.0;
-            for (int i = lane; i < gridDim.x; i += 32) s += ld_l2(partials + k * gridDim.x + i);
-            v[k] = warp_sum(s);
-        }
-        return lane == 0;
-    }
-    return false;
-}
 
 enum { RED_DOT = 0, RED_SUMMAG = 1, RED_SUM = 2, RED_SUMSQR = 3 };
 
@@ -551,7 +591,13 @@ __global__ void k_pcg_update_p(double* __restrict__ pA, const double* __restrict
 __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update_xr(double* __restrict__ psi, double* __restrict__ rA, const double* __restrict__ pA,
                 const double* __restrict__ wA, const double* __restrict__ wArA, const double* __restrict__ wApA,
-                double* __restrict__ out, int n, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+                double normFactor, double* __restrict__ singularFlag, double* __restrict__ out, int n,
+                double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    // checkSingularity(mag(wApA)/normFactor) (PCG.C:165): leave psi/rA untouched and raise the flag
+    if (fabs(wApA[0]) / normFactor < 2.2250738585072014e-308) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) singularFlag[0] = 1.0;
+        return;
+    }
     const double alpha = wArA[0] / wApA[0];
     double v[1] = {0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

@@ -40,7 +40,7 @@ void ensureInit() {
     B2_CUDA(cudaGetDeviceProperties(&prop, c.device));
     c.numSMs = prop.multiProcessorCount;
     B2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    c.partials.alloc(4 * kReduceBlocks);
+    c.partials.alloc(8 * kReduceBlocks);
     c.ticket.alloc(1);
     c.errFlag.alloc(1);
     B2_CUDA(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned int), c.stream));
@@ -86,6 +86,8 @@ static void launchSweep(K kernel, SweepArgs& a) {
     occ = std::min(occ, c.sweepBlocksPerSM > 0 ? c.sweepBlocksPerSM : 4);
     const int blocks = std::max(1, std::min(occ * c.numSMs, (a.nTasks + 7) / 8));
     a.err = c.errFlag.p;
+    a.partials = c.partials.p;
+    a.ticket = c.ticket.p;
     void* args[] = {&a};
     B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(256), args, 0, c.stream));
     c.launches++;
@@ -461,7 +463,7 @@ void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
 
 // wA = M^-1 rA.  DIC/DILU: forward sweep into the level's sentinel scratch, backward sweep into wA; each sweep
 // re-arms the other's output buffer, so no fill kernels run in steady state.
-void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA) {
+void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA, double* dotOut) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     const int n = D.nCells;
@@ -505,6 +507,10 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
     b.in = M.tmpA.p;
     b.out = wA;
     b.clear = M.tmpA.p;
+    if (dotOut) {   // fused wA.rA
+        b.dotWith = rA;
+        b.dotOut = dotOut;
+    }
     launchSweep(k_sweep_bwd, b);
 }
 
@@ -530,7 +536,10 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
                 ifaceApply(m, level, M.tmpB.p, -1.0);
                 bPrime = M.tmpB.p;
             }
-            fillSentinel(spare, n);
+            // plain Gauss-Seidel re-arms the old iterate while it sweeps (every reader of old[p] sits in an
+            // earlier wavefront than row p), so only the first sweep of a call needs a fill kernel
+            const bool rearm = (smoother == B200LS_GAUSS_SEIDEL);
+            if (!(rearm && sweep > 0)) fillSentinel(spare, n);
             SweepArgs a{};
             a.tasks = D.fwdTasks.p;
             a.nTasks = D.nFwdTasks;
@@ -544,6 +553,7 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
             a.in = bPrime;
             a.old = psi;
             a.out = spare;
+            a.clear = (rearm && sweep + 1 < nSweeps) ? psi : nullptr;
             launchSweep(k_gs_sweep, a);
             if (smoother == B200LS_GAUSS_SEIDEL) {
                 std::swap(psi, spare);
@@ -601,7 +611,7 @@ static void reduce(double* out, const double* x, const double* y, int n) {
 enum {
     S_SUMPSI = 0, S_NORM = 1, S_RES = 2, S_WARA0 = 3, S_WARA1 = 4, S_WAPA = 5,
     S_RHO0 = 6, S_RHO1 = 7, S_RA0AYA = 8, S_ALPHA = 9, S_OMEGA = 10, S_TASA = 11, S_TATA = 12,
-    S_NUM = 13, S_DEN = 14, S_COUNT = 32
+    S_NUM = 13, S_DEN = 14, S_SINGULAR = 15, S_COUNT = 32
 };
 
 static double* scalar(b200ls_matrix_s* m, int i) {
@@ -687,7 +697,9 @@ static void applyPrecond(b200ls_matrix_s* m, const b200ls_controls& c, int lv, d
 static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, double* psi, const double* source,
                      b200ls_perf* perf, cudaEvent_t evLoopStart) {
     Context& cx = ctx();
-    const int n = DL(m, lv).nCells;
+    DevLevel& D = DL(m, lv);
+    MatLevel& M = m->levels[lv];
+    const int n = D.nCells;
     double* pA = lvec(m, lv, "pA");
     double* wA = lvec(m, lv, "wA");
     double* rA = lvec(m, lv, "rA");
@@ -705,28 +717,47 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
     if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
     if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
         preparePrecond(m, c, lv);
+        B2_CUDA(cudaMemsetAsync(scalar(m, S_SINGULAR), 0, sizeof(double), S()));
+        // the dot products ride on the kernels that produce their operands when nothing sits in between
+        const bool fuseSweepDot = (c.precond == B200LS_DIC || c.precond == B200LS_DILU);
+        const bool fuseSpmvDot = (D.nIfaces == 0);
+        const int spmvGrid = std::max(1, std::min(gridRows(n), 4 * kReduceBlocks));
         do {
             const int cur = S_WARA0 + (perf->nIterations & 1);
             const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
-            applyPrecond(m, c, lv, wA, rA);
-            reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
+            if (fuseSweepDot) {
+                opPrecondition(m, lv, c.precond, wA, rA, scalar(m, cur));
+            } else {
+                applyPrecond(m, c, lv, wA, rA);
+                reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
+            }
             allReduce(scalar(m, cur), 1);
             LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
                    perf->nIterations == 0 ? 1 : 0, n);
-            opAmul(m, lv, wA, pA);
-            reduce<RED_DOT>(scalar(m, S_WAPA), wA, pA, n);
+            if (fuseSpmvDot) {
+                if (m->symmetric && D.hasLslot) {
+                    LAUNCH(k_spmv_dot<true>, spmvGrid, 256, wA, pA, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
+                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p);
+                } else {
+                    LAUNCH(k_spmv_dot<false>, spmvGrid, 256, wA, pA, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
+                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p);
+                }
+            } else {
+                opAmul(m, lv, wA, pA);
+                reduce<RED_DOT>(scalar(m, S_WAPA), wA, pA, n);
+            }
             allReduce(scalar(m, S_WAPA), 1);
-            // singularity test needs wApA on the host before psi is touched (PCG.C:165)
-            readScalars(scalar(m, S_WAPA), 1);
-            if (std::fabs(cx.pinned[0]) / nf < kVSmall) {
+            // the singularity test (PCG.C:165) is evaluated on the device by every thread of the update kernel
+            LAUNCH(k_pcg_update_xr, kReduceBlocks, kReduceThreads, psi, rA, pA, wA, scalar(m, cur),
+                   scalar(m, S_WAPA), nf, scalar(m, S_SINGULAR), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
+            allReduce(scalar(m, S_RES), 1);
+            static_assert(S_SINGULAR - S_NUM == 2 && S_RES < S_NUM, "scalar layout");
+            readScalars(scalar(m, 0), S_SINGULAR + 1);   // one read-back per iteration
+            if (cx.pinned[S_SINGULAR] != 0.0) {
                 perf->singular = 1;
                 break;
             }
-            LAUNCH(k_pcg_update_xr, kReduceBlocks, kReduceThreads, psi, rA, pA, wA, scalar(m, cur),
-                   scalar(m, S_WAPA), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
-            allReduce(scalar(m, S_RES), 1);
-            readScalars(scalar(m, S_RES), 1);
-            perf->finalResidual = cx.pinned[0] / nf;
+            perf->finalResidual = cx.pinned[S_RES] / nf;
             record(perf, c, perf->finalResidual);
         } while ((++perf->nIterations < c.maxIter &&
                   !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||

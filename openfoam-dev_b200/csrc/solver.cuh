@@ -54,7 +54,9 @@ void opAmul(b200ls_matrix_s* m, int level, double* out, const double* x);
 void opResidual(b200ls_matrix_s* m, int level, double* out, const double* x, const double* b);
 void opSumA(b200ls_matrix_s* m, int level, double* out);
 void ensureFactor(b200ls_matrix_s* m, int level, int precond);
-void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA);
+// dotOut != nullptr (DIC/DILU only): also compute wA.rA into dotOut[0] inside the backward sweep
+void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, const double* rA,
+                    double* dotOut = nullptr);
 void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*& spare, const double* source,
               int nSweeps);
 void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, const double* sourceCell,

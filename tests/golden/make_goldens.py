@@ -105,6 +105,9 @@ def main():
     fixture("block_16x16x16_rand", cases.cavity_laplacian(16, 16, 16, coeffs="random"), SYM_SOLVES, sym_sm)
     fixture("block_24x24x24", cases.cavity_laplacian(24, 24, 24, rhs_kind="uniform"), SYM_SOLVES[1:2] + SYM_SOLVES[5:6],
             sym_sm[:1], agglom=False)
+    # irregular connectivity: rows with many neighbours, ragged wavefronts, irregular agglomeration
+    fixture("random_graph_sym_600", cases.random_graph(600, symmetric=True), SYM_SOLVES, sym_sm)
+    fixture("random_graph_asym_500", cases.random_graph(500, symmetric=False, seed=7), ASYM_SOLVES, asym_sm)
     fixture("convdiff_24x18x1", cases.convection_diffusion(24, 18, 1, dt_coeff=50.0), ASYM_SOLVES, asym_sm)
     fixture("convdiff_9x8x7", cases.convection_diffusion(9, 8, 7, dt_coeff=50.0, rhs_kind="uniform"), ASYM_SOLVES, asym_sm)
 
