@@ -3,8 +3,8 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
-#include "../openfoam-dev_b200/csrc/kernels.cuh"
-#include "../openfoam-dev_b200/csrc/mesh.hpp"
+#include "../../openfoam-dev_b200/csrc/kernels.cuh"
+#include "../../openfoam-dev_b200/csrc/mesh.hpp"
 using namespace b200ls;
 struct Task2 { int start, count, d1off, d1cnt; };
 struct Args { const Task2* tasks; int nTasks; const int* d1; const int* ptr; const int* col; const double* val; const double* rD; const double* in; double* out; int* err; };

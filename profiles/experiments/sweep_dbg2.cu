@@ -2,8 +2,8 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
-#include "../openfoam-dev_b200/csrc/kernels.cuh"
-#include "../openfoam-dev_b200/csrc/mesh.hpp"
+#include "../../openfoam-dev_b200/csrc/kernels.cuh"
+#include "../../openfoam-dev_b200/csrc/mesh.hpp"
 using namespace b200ls;
 __device__ __forceinline__ bool isS(double v){return __double_as_longlong(v)==(long long)kSentinelBits;}
 template <bool DESC>

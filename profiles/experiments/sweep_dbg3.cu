@@ -2,8 +2,8 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
-#include "../openfoam-dev_b200/csrc/kernels.cuh"
-#include "../openfoam-dev_b200/csrc/mesh.hpp"
+#include "../../openfoam-dev_b200/csrc/kernels.cuh"
+#include "../../openfoam-dev_b200/csrc/mesh.hpp"
 using namespace b200ls;
 __device__ __forceinline__ double ld_cv(const double* p){double v; asm volatile("ld.volatile.global.f64 %0, [%1];":"=d"(v):"l"(p):"memory"); return v;}
 __device__ __forceinline__ double ld_acq(const double* p){double v; asm volatile("ld.acquire.gpu.global.f64 %0, [%1];":"=d"(v):"l"(p):"memory"); return v;}

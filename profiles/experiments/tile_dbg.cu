@@ -3,7 +3,7 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
-#include "../openfoam-dev_b200/csrc/kernels.cuh"
+#include "../../openfoam-dev_b200/csrc/kernels.cuh"
 using namespace b200ls;
 struct Args { const int2* tasks; int nTasks; const int* ptr; const int* col; const double* val; const double* rD; const double* in; double* out; const unsigned char* lev; int* err; };
 template<int JIT>
