@@ -122,12 +122,21 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
     __syncthreads();
     if (!isLast) return false;
     __threadfence();
-    // fixed-order fold of the block partials by warp 0
+    // fixed-order fold of the block partials by the whole last block: strided per-thread sums, then the same
+    // warp/shared-memory tree as above
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += ld_l2(partials + k * gridDim.x + i);
+        s = warp_sum(s);
+        if (lane == 0) sm[k][w] = s;
+    }
+    __syncthreads();
     if (w == 0) {
 #pragma unroll
         for (int k = 0; k < NV; k++) {
-            double s = 0.0;
-            for (int i = lane; i < gridDim.x; i += 32) s += ld_l2(partials + k * gridDim.x + i);
+            double s = lane < (blockDim.x >> 5) ? sm[k][lane] : 0.0;
             v[k] = warp_sum(s);
         }
         return lane == 0;

@@ -21,6 +21,8 @@ namespace b200ls {
 // context
 // ------------------------------------------------------------------------------------------------------------
 
+static constexpr int kMaxPartials = 2 * 65536;   // up to 65536 blocks x 2 values
+
 Context& ctx() {
     static Context c;
     return c;
@@ -40,7 +42,7 @@ void ensureInit() {
     B2_CUDA(cudaGetDeviceProperties(&prop, c.device));
     c.numSMs = prop.multiProcessorCount;
     B2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    c.partials.alloc(8 * kReduceBlocks);
+    c.partials.alloc(kMaxPartials);
     c.ticket.alloc(1);
     c.errFlag.alloc(1);
     B2_CUDA(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned int), c.stream));
@@ -721,7 +723,7 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
         // the dot products ride on the kernels that produce their operands when nothing sits in between
         const bool fuseSweepDot = (c.precond == B200LS_DIC || c.precond == B200LS_DILU);
         const bool fuseSpmvDot = (D.nIfaces == 0);
-        const int spmvGrid = std::max(1, std::min(gridRows(n), 4 * kReduceBlocks));
+        const int spmvGrid = std::max(1, std::min(gridRows(n), kMaxPartials / 2));   // one row per thread when it fits
         do {
             const int cur = S_WARA0 + (perf->nIterations & 1);
             const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
