@@ -45,11 +45,81 @@ void loadNccl(NcclApi& n) {
     n.CommInitRank = sym<std::remove_pointer_t<decltype(n.CommInitRank)>>(n.handle, "ncclCommInitRank");
     n.CommDestroy = sym<std::remove_pointer_t<decltype(n.CommDestroy)>>(n.handle, "ncclCommDestroy");
     n.AllReduce = sym<std::remove_pointer_t<decltype(n.AllReduce)>>(n.handle, "ncclAllReduce");
+    n.AllGather = sym<std::remove_pointer_t<decltype(n.AllGather)>>(n.handle, "ncclAllGather");
     n.Send = sym<std::remove_pointer_t<decltype(n.Send)>>(n.handle, "ncclSend");
     n.Recv = sym<std::remove_pointer_t<decltype(n.Recv)>>(n.handle, "ncclRecv");
     n.GroupStart = sym<std::remove_pointer_t<decltype(n.GroupStart)>>(n.handle, "ncclGroupStart");
     n.GroupEnd = sym<std::remove_pointer_t<decltype(n.GroupEnd)>>(n.handle, "ncclGroupEnd");
     n.GetErrorString = sym<std::remove_pointer_t<decltype(n.GetErrorString)>>(n.handle, "ncclGetErrorString");
+}
+
+// Export this rank's P2P arena with CUDA IPC and map every peer's (same node, NVLink/NVSwitch).  Collective: either
+// every rank ends up with P2P enabled or none does (then all traffic stays on NCCL).
+void setupP2P(Context& c) {
+    P2PState& P = c.p2p;
+    if (P.enabled || c.nRanks < 2 || c.nRanks > kMaxRanks || getenv("B200LS_NO_P2P")) return;
+    size_t bytes = size_t(256) << 20;
+    if (const char* s = getenv("B200LS_P2P_ARENA_MB")) bytes = size_t(atol(s)) << 20;
+    bool ok = true;
+    if (cudaMalloc(&P.arena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        P.arena = nullptr;
+        ok = false;
+    }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok) {
+        B2_CUDA(cudaMemsetAsync(P.arena, 0, bytes, c.stream));
+        if (cudaIpcGetMemHandle(&mine, P.arena) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        }
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DevBuf<char> dMine, dAll;
+    dMine.alloc(64);
+    dAll.alloc(size_t(64) * c.nRanks);
+    B2_CUDA(cudaMemcpyAsync(dMine.p, &mine, 64, cudaMemcpyHostToDevice, c.stream));
+    if (c.nccl.AllGather(dMine.p, dAll.p, 64, ncclChar, c.comm, c.stream) != 0) throw CudaError("ncclAllGather failed");
+    std::vector<cudaIpcMemHandle_t> all(c.nRanks);
+    B2_CUDA(cudaMemcpyAsync(all.data(), dAll.p, size_t(64) * c.nRanks, cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    P.view.rank = c.rank;
+    P.view.nRanks = c.nRanks;
+    for (int r = 0; r < c.nRanks && ok; r++) {
+        if (r == c.rank) {
+            P.view.peer[r] = P.arena;
+            continue;
+        }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        P.opened.push_back(ptr);
+        P.view.peer[r] = static_cast<char*>(ptr);
+    }
+    // agree: P2P only if it worked everywhere (this all-reduce is also the barrier after the arena memsets)
+    DevBuf<double> flag;
+    flag.alloc(1);
+    const double bad = ok ? 0.0 : 1.0;
+    B2_CUDA(cudaMemcpyAsync(flag.p, &bad, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (c.nccl.AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, c.comm, c.stream) != 0)
+        throw CudaError("ncclAllReduce failed");
+    double total = 0;
+    B2_CUDA(cudaMemcpyAsync(&total, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    if (total != 0.0) {
+        for (void* q : P.opened) cudaIpcCloseMemHandle(q);
+        P.opened.clear();
+        if (P.arena) cudaFree(P.arena);
+        P.arena = nullptr;
+        return;
+    }
+    P.arenaBytes = bytes;
+    P.bump = kP2PReduceBytes;
+    P.enabled = true;
 }
 
 // stage a host vector of level-0 size into `dev` (cell order)
@@ -176,6 +246,7 @@ int b200ls_init(int device, const void* ncclUniqueId_, int rank, int nRanks) {
         }
         c.rank = rank;
         c.nRanks = nRanks;
+        if (nRanks > 1) setupP2P(c);
     });
 }
 
@@ -183,6 +254,9 @@ void b200ls_finalize(void) {
     Context& c = ctx();
     if (!c.initialised) return;
     cudaStreamSynchronize(c.stream);
+    for (void* q : c.p2p.opened) cudaIpcCloseMemHandle(q);
+    c.p2p.opened.clear();
+    c.p2p.enabled = false;
     if (c.comm) {
         c.nccl.CommDestroy(c.comm);
         c.comm = nullptr;

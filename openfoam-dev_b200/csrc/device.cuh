@@ -74,6 +74,7 @@ struct NcclApi {
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -81,8 +82,27 @@ struct NcclApi {
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
 };
 
+// Peer-to-peer communication over NVLink (one process per GPU): every rank exports one arena with CUDA IPC and maps
+// the arenas of all peers.  Small all-reduces and halo exchanges then are plain remote stores + release/acquire
+// flags issued from our own kernels instead of NCCL calls.
+static constexpr int kMaxRanks = 16;
+static constexpr size_t kP2PReduceBytes = 4096;          // [2 parities][kMaxRanks][4] doubles + [2][kMaxRanks] epochs
+struct P2PView {                                          // passed by value to kernels
+    int rank, nRanks;
+    char* peer[kMaxRanks];                                // arena base of every rank as mapped in this process
+};
+struct P2PState {
+    bool enabled = false;
+    char* arena = nullptr;
+    size_t arenaBytes = 0, bump = 0;
+    P2PView view{};
+    unsigned long long reduceEpoch = 0;
+    std::vector<void*> opened;                            // cudaIpcOpenMemHandle results
+};
+
 struct Context {
     bool initialised = false;
+    P2PState p2p;
     int device = 0;
     int numSMs = 148;
     int rank = 0, nRanks = 1;

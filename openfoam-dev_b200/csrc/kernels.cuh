@@ -14,6 +14,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "device.cuh"
+
 namespace b200ls {
 
 // Signalling-NaN bit pattern that fp64 arithmetic can never produce (arithmetic yields the canonical quiet
@@ -36,6 +38,24 @@ __device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longl
 
 // Poll budget of one wait: ~2^22 L2 round trips (seconds).  A logic error sets *err instead of hanging the GPU.
 static constexpr unsigned kMaxSpins = 1u << 22;
+
+// system-scope release/acquire on 64-bit flags (peer GPUs over NVLink) and system-scope relaxed data stores
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // elementwise / permutation
@@ -246,13 +266,29 @@ k_spmv_dot(double* __restrict__ out, const double* __restrict__ x, const double*
 // (processorFvPatchScalarField.C:133-136).  One thread per boundary row.  sign = +1 for Amul, -1 when the
 // caller negated the coefficients (residual, GaussSeidel).
 struct IfaceView {
-    const double* coeffs;   // per patch face
-    const double* recv;     // per patch face, neighbour values
+    const double* coeffs;           // per patch face
+    const double* recv;             // per patch face, neighbour values (P2P: two parity buffers back to back)
+    const unsigned long long* flag; // P2P: epoch written by the neighbour once its values have landed; else null
+    int size;
 };
 __global__ void k_iface_apply(double* __restrict__ result, const int* __restrict__ rowPos,
                               const int* __restrict__ rowPtr, const int* __restrict__ entIface,
-                              const int* __restrict__ entFace, const IfaceView* __restrict__ views, double sign,
-                              int nRows) {
+                              const int* __restrict__ entFace, const IfaceView* __restrict__ views, int nIfaces,
+                              unsigned long long epoch, double sign, int nRows, int* err) {
+    // P2P halos: wait until every neighbour has published this exchange (release/acquire over NVLink)
+    if (threadIdx.x < nIfaces) {
+        const unsigned long long* f = views[threadIdx.x].flag;
+        if (f) {
+            unsigned spins = 0;
+            while (ld_acquire_sys(f) < epoch) {
+                if (++spins > (1u << 26)) {
+                    *err = 2;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nRows) return;
     const int p = rowPos[r];
@@ -260,9 +296,63 @@ __global__ void k_iface_apply(double* __restrict__ result, const int* __restrict
     for (int e = rowPtr[r]; e < rowPtr[r + 1]; e++) {
         const IfaceView v = views[entIface[e]];
         const int f = entFace[e];
-        acc -= (sign * v.coeffs[f]) * v.recv[f];
+        const double* rv = v.flag ? v.recv + (epoch & 1) * v.size : v.recv;
+        acc -= (sign * v.coeffs[f]) * __ldcg(rv + f);
     }
     result[p] = acc;
+}
+
+// P2P halo send: the gathered boundary values are stored straight into the neighbour's receive buffer; the last
+// block to finish publishes the epoch flag (release, system scope).
+__global__ void k_iface_pack_p2p(double* __restrict__ remoteRecv, const double* __restrict__ psi,
+                                 const int* __restrict__ faceCellsPos, int n, unsigned int* __restrict__ ticket,
+                                 unsigned long long* remoteFlag, unsigned long long epoch) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_sys(remoteRecv + i, psi[faceCellsPos[i]]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            st_release_sys(remoteFlag, epoch);
+        }
+    }
+}
+
+// All-reduce (sum) of <= 4 doubles across ranks through the mapped peer arenas: every rank stores its values into
+// slot [parity][rank] of every arena and releases an epoch; every rank then acquires the nRanks epochs of its own
+// arena and adds the values in rank order (identical, deterministic result on all ranks).
+__global__ void k_allreduce_p2p(double* __restrict__ data, int count, P2PView v, unsigned long long epoch, int* err) {
+    const int lane = threadIdx.x;
+    const int par = int(epoch & 1);
+    const size_t valOff = (size_t(par) * kMaxRanks) * 4 * sizeof(double);
+    const size_t epoOff = 2 * kMaxRanks * 4 * sizeof(double) + size_t(par) * kMaxRanks * sizeof(unsigned long long);
+    if (lane < v.nRanks) {
+        double* dst = reinterpret_cast<double*>(v.peer[lane] + valOff) + v.rank * 4;
+        for (int k = 0; k < count; k++) st_sys(dst + k, data[k]);
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(v.peer[lane] + epoOff) + v.rank, epoch);
+    }
+    __syncwarp();
+    double vals[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < v.nRanks) {
+        const unsigned long long* e = reinterpret_cast<const unsigned long long*>(v.peer[v.rank] + epoOff) + lane;
+        unsigned spins = 0;
+        while (ld_acquire_sys(e) < epoch) {
+            if (++spins > (1u << 26)) {
+                *err = 2;
+                break;
+            }
+        }
+        const double* src = reinterpret_cast<const double*>(v.peer[v.rank] + valOff) + lane * 4;
+        for (int k = 0; k < count; k++) vals[k] = ld_sys(src + k);
+    }
+    for (int k = 0; k < count; k++) {
+        double s = 0.0;
+        for (int r = 0; r < v.nRanks; r++) s += __shfl_sync(0xffffffffu, vals[k], r);
+        if (lane == 0) data[k] = s;
+    }
 }
 
 // send[i] = psi[faceCellsPos[i]]  (patchInternalField, processorFvPatchScalarField.C:45)

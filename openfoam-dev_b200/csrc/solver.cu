@@ -102,7 +102,8 @@ void checkSweepError() {
     B2_CUDA(cudaStreamSynchronize(c.stream));
     if (h) {
         B2_CUDA(cudaMemsetAsync(c.errFlag.p, 0, sizeof(int), c.stream));
-        throw CudaError("wavefront sweep timed out waiting for a dependency (internal error)");
+        throw CudaError(h == 2 ? "timed out waiting for a peer GPU (P2P halo / all-reduce)"
+                               : "wavefront sweep timed out waiting for a dependency (internal error)");
     }
 }
 
@@ -115,6 +116,12 @@ static void readScalars(const double* dev, int n) {
 static void allReduce(double* dev, int count) {
     Context& c = ctx();
     if (c.nRanks == 1) return;
+    if (c.p2p.enabled && count <= 4) {
+        // our own kernel over the mapped peer arenas: remote stores + release/acquire epochs, no NCCL launch
+        k_allreduce_p2p<<<1, 32, 0, c.stream>>>(dev, count, c.p2p.view, ++c.p2p.reduceEpoch, c.errFlag.p);
+        c.launches++;
+        return;
+    }
     int r = c.nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, c.comm, c.stream);
     if (r != 0) throw CudaError(std::string("ncclAllReduce: ") + c.nccl.GetErrorString((ncclResult_t)r));
 }
@@ -259,16 +266,92 @@ static void syncMatrixWithMesh(b200ls_matrix_s* m) {
     }
 }
 
+// bump allocation inside this rank's IPC arena; returns nullptr when the arena is exhausted
+static char* arenaAlloc(size_t bytes) {
+    P2PState& P = ctx().p2p;
+    const size_t aligned = (bytes + 255) & ~size_t(255);
+    if (!P.enabled || P.bump + aligned > P.arenaBytes) return nullptr;
+    char* p = P.arena + P.bump;
+    P.bump += aligned;
+    return p;
+}
+
+// P2P halos: place the receive buffers (two parities) and epoch flags of this level in the arena and swap their
+// arena offsets with the neighbours (once per matrix level).  Falls back to the NCCL path if anything is missing.
+static void setupP2PHalos(b200ls_matrix_s* m, int level) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    Context& c = ctx();
+    if (M.p2pReady || !c.p2p.enabled || D.nIfaces == 0) return;
+    static const bool off = getenv("B200LS_NO_P2P_HALO") != nullptr;
+    if (off) return;
+    for (int i = 0; i < D.nIfaces; i++)
+        for (int j = 0; j < i; j++)
+            if (D.ifaceNbr[i] == D.ifaceNbr[j]) return;   // several patches to one neighbour: keep NCCL
+    std::vector<long long> mine(2 * D.nIfaces), theirs(2 * D.nIfaces, -1);
+    M.p2pLocalRecv.assign(D.nIfaces, nullptr);
+    M.p2pLocalFlag.assign(D.nIfaces, nullptr);
+    bool ok = true;
+    for (int i = 0; i < D.nIfaces; i++) {
+        char* r = arenaAlloc(size_t(2) * std::max(D.ifaceSize[i], 1) * sizeof(double));
+        char* f = arenaAlloc(sizeof(unsigned long long));
+        if (!r || !f) ok = false;
+        M.p2pLocalRecv[i] = reinterpret_cast<double*>(r);
+        M.p2pLocalFlag[i] = reinterpret_cast<unsigned long long*>(f);
+        mine[2 * i] = r ? r - c.p2p.arena : -1;
+        mine[2 * i + 1] = f ? f - c.p2p.arena : -1;
+    }
+    // exchange the offsets pairwise (also tells the neighbour if we ran out of arena)
+    DevBuf<long long> dMine, dTheirs;
+    dMine.upload(mine, c.stream);
+    dTheirs.alloc(theirs.size());
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    c.nccl.GroupStart();
+    for (int i = 0; i < D.nIfaces; i++) {
+        c.nccl.Send(dMine.p + 2 * i, 2, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
+        c.nccl.Recv(dTheirs.p + 2 * i, 2, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
+    }
+    if (c.nccl.GroupEnd() != 0) throw CudaError("nccl exchange of P2P halo offsets failed");
+    B2_CUDA(cudaMemcpyAsync(theirs.data(), dTheirs.p, sizeof(long long) * theirs.size(), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    for (long long v : theirs) ok = ok && v >= 0;
+    // every rank must take the same decision for a given interface pair; a global AND keeps it simple
+    DevBuf<double> flag;
+    flag.alloc(1);
+    const double mineOk = ok ? 0.0 : 1.0;
+    B2_CUDA(cudaMemcpyAsync(flag.p, &mineOk, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (c.nccl.AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, c.comm, c.stream) != 0)
+        throw CudaError("ncclAllReduce failed");
+    double bad = 0;
+    B2_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    if (bad != 0.0) return;
+    M.p2pRemoteRecv.resize(D.nIfaces);
+    M.p2pRemoteFlag.resize(D.nIfaces);
+    for (int i = 0; i < D.nIfaces; i++) {
+        char* base = c.p2p.view.peer[D.ifaceNbr[i]];
+        M.p2pRemoteRecv[i] = reinterpret_cast<double*>(base + theirs[2 * i]);
+        M.p2pRemoteFlag[i] = reinterpret_cast<unsigned long long*>(base + theirs[2 * i + 1]);
+    }
+    M.p2pTickets.alloc(D.nIfaces);
+    B2_CUDA(cudaMemsetAsync(M.p2pTickets.p, 0, sizeof(unsigned int) * D.nIfaces, c.stream));
+    M.haloEpoch = 0;
+    M.p2pReady = true;
+}
+
 static void setupIfaceViews(b200ls_matrix_s* m, int level) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     if (D.nIfaces == 0) return;
+    if (ctx().nRanks > 1) setupP2PHalos(m, level);
     std::vector<IfaceView> v(D.nIfaces);
     for (int i = 0; i < D.nIfaces; i++) {
         M.sendBuf[i].alloc(D.ifaceSize[i]);
         M.recvBuf[i].alloc(D.ifaceSize[i]);
         v[i].coeffs = M.bou[i].p;
-        v[i].recv = M.recvBuf[i].p;
+        v[i].recv = M.p2pReady ? M.p2pLocalRecv[i] : M.recvBuf[i].p;
+        v[i].flag = M.p2pReady ? M.p2pLocalFlag[i] : nullptr;
+        v[i].size = D.ifaceSize[i];
     }
     M.ifaceViews.alloc(v.size() * sizeof(IfaceView));
     B2_CUDA(cudaMemcpyAsync(M.ifaceViews.p, v.data(), v.size() * sizeof(IfaceView), cudaMemcpyHostToDevice, S()));
@@ -332,6 +415,16 @@ static void haloExchange(b200ls_matrix_s* m, int level, const double* psi) {
     Context& c = ctx();
     if (D.nIfaces == 0) return;
     if (c.nRanks == 1) throw CudaError("matrix has processor interfaces but b200ls_init was called with nRanks=1");
+    if (M.p2pReady) {
+        // remote stores into the neighbours' receive buffers + release of the epoch flag, from our own kernel
+        const unsigned long long epoch = ++M.haloEpoch;
+        for (int i = 0; i < D.nIfaces; i++) {
+            const int n = D.ifaceSize[i];
+            LAUNCH(k_iface_pack_p2p, gridRows(std::max(n, 1)), 256, M.p2pRemoteRecv[i] + (epoch & 1) * n, psi,
+                   D.ifaceCellsPos[i].p, n, M.p2pTickets.p + i, M.p2pRemoteFlag[i], epoch);
+        }
+        return;
+    }
     for (int i = 0; i < D.nIfaces; i++) {
         if (D.ifaceSize[i])
             LAUNCH(k_iface_pack, gridRows(D.ifaceSize[i]), 256, M.sendBuf[i].p, psi, D.ifaceCellsPos[i].p,
@@ -350,8 +443,10 @@ static void ifaceApply(b200ls_matrix_s* m, int level, double* result, double sig
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     if (D.nBRows == 0) return;
+    if (D.nIfaces > 256) throw CudaError("more than 256 coupled patches on one rank");
     LAUNCH(k_iface_apply, gridRows(D.nBRows), 256, result, D.bRowPos.p, D.bRowPtr.p, D.bEntIface.p, D.bEntFace.p,
-           reinterpret_cast<const IfaceView*>(M.ifaceViews.p), sign, D.nBRows);
+           reinterpret_cast<const IfaceView*>(M.ifaceViews.p), D.nIfaces, M.haloEpoch, sign, D.nBRows,
+           ctx().errFlag.p);
 }
 
 // ------------------------------------------------------------------------------------------------------------

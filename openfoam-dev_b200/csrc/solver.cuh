@@ -17,6 +17,14 @@ struct MatLevel {
     // interfaces: coefficients, send/recv buffers
     std::vector<DevBuf<double>> bou, inn, sendBuf, recvBuf;
     DevBuf<unsigned char> ifaceViews;   // IfaceView[nIfaces] on device
+    // P2P halos: receive buffers/flags live in this rank's IPC arena, the neighbour's are mapped pointers
+    bool p2pReady = false;
+    std::vector<double*> p2pRemoteRecv;                 // neighbour's receive buffer (2 parities)
+    std::vector<unsigned long long*> p2pRemoteFlag;     // neighbour's epoch flag
+    std::vector<double*> p2pLocalRecv;
+    std::vector<unsigned long long*> p2pLocalFlag;
+    DevBuf<unsigned int> p2pTickets;                    // one last-block ticket per interface
+    unsigned long long haloEpoch = 0;
     // level work vectors (GAMG): correction, source, scratch
     DevBuf<double> corr, src, tmpA, tmpB, tmpC;
     bool tmpASentinel = false;      // tmpA is known to be all-sentinel
