@@ -177,3 +177,41 @@ def test_agglomerate_from_reference_maps():
         assert np.array_equal(mesh.get_i32(capi.FACE_FLIP_MAP, lev), ref[k + "faceFlipMap"].astype(np.int32))
         assert np.array_equal(mesh.get_i32(capi.LOWER_ADDR, lev + 1), ref[k + "coarseLower"])
         assert np.array_equal(mesh.get_i32(capi.UPPER_ADDR, lev + 1), ref[k + "coarseUpper"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_agglomeration_matches_c_oracle_on_random_graphs(seed):
+    """Two independent restatements (C++ in libb200ls, plain C in oracle/) of the pair agglomeration and of
+    agglomerateLduAddressing agree level by level on irregular graphs (both are pinned to the reference on fixtures)."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ldu_oracle as orc
+
+    rng = np.random.default_rng(seed)
+    s = cases.random_graph(int(rng.integers(60, 900)), avg_degree=int(rng.integers(2, 9)), symmetric=bool(seed % 2),
+                           seed=100 + seed, max_span=int(rng.integers(5, 200)))
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    n = mesh.agglomerate(s.face_weights, forward_start=1)
+    levels = orc.agglomeration(orc.System(s))
+    assert n == len(levels)
+    for k, (ra, fra, ff, cl, cu) in enumerate(levels):
+        assert np.array_equal(mesh.get_i32(capi.RESTRICT_ADDRESSING, k), ra)
+        assert np.array_equal(mesh.get_i32(capi.FACE_RESTRICT_ADDRESSING, k), fra)
+        assert np.array_equal(mesh.get_i32(capi.FACE_FLIP_MAP, k), ff)
+        assert np.array_equal(mesh.get_i32(capi.LOWER_ADDR, k + 1), cl)
+        assert np.array_equal(mesh.get_i32(capi.UPPER_ADDR, k + 1), cu)
+
+
+def test_forward_flag_alternates_like_the_reference_static():
+    """pairGAMGAgglomeration::forward_ is process-global in the reference: with forwardStart = -1 the library
+    mirrors that (a second mesh starts with the flag the first one left), with 0/1 it is explicit."""
+    s = cases.random_graph(300, symmetric=True, seed=11)     # irregular: visiting order matters
+    a = capi.Mesh(s.n_cells, s.lower, s.upper)
+    b = capi.Mesh(s.n_cells, s.lower, s.upper)
+    a.agglomerate(s.face_weights, forward_start=1)
+    b.agglomerate(s.face_weights, forward_start=0)
+    assert not np.array_equal(a.get_i32(capi.RESTRICT_ADDRESSING, 0), b.get_i32(capi.RESTRICT_ADDRESSING, 0))
+    c = capi.Mesh(s.n_cells, s.lower, s.upper)
+    c.agglomerate(s.face_weights, forward_start=1)
+    assert np.array_equal(a.get_i32(capi.RESTRICT_ADDRESSING, 0), c.get_i32(capi.RESTRICT_ADDRESSING, 0))
