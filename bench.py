@@ -125,6 +125,18 @@ def run_reference_sample(sys_, iters):
     return sys_.n_cells * its / secs, secs, its
 
 
+def run_oracle_port_sample(sys_, iters):
+    """Fallback when oracle/_ref is absent: time the plain-C restatement (oracle/ldu_oracle.c, one core)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ldu_oracle as orc
+
+    S = orc.System(sys_)
+    t0 = time.perf_counter()
+    _, perf = orc.solve(S, "PCG", orc.controls("DIC", tolerance=0.0, relTol=0.0, maxIter=iters), sys_.source)
+    secs = time.perf_counter() - t0
+    return sys_.n_cells * perf["nIterations"] / secs, secs, perf["nIterations"]
+
+
 def bench_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The image has no MPI, so the
     reference runs as one serial process (Pstream/dummy); under torchrun only rank 0 works."""
@@ -138,8 +150,13 @@ def bench_reference(args):
 
     sys_ = cases.cavity_laplacian(N_SIDE, N_SIDE, N_SIDE)
     vals, secs_all = [], []
+    kind = "reference"
     for i in range(args.warmup + args.steps):
-        v, secs, its = run_reference_sample(sys_, ITERS)
+        r = run_reference_sample(sys_, ITERS)
+        if r is None:
+            kind = "port"
+            r = run_oracle_port_sample(sys_, ITERS)
+        v, secs, its = r
         if i >= args.warmup:
             vals.append(v)
             secs_all.append(secs)
@@ -150,9 +167,10 @@ def bench_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cavity {N_SIDE}^3 p-equation, PCG+DIC, {ITERS} iterations per solve",
                    "n_cells": sys_.n_cells, "iterations_per_step": ITERS},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"{args.steps} x {ITERS} PCG+DIC iterations on the {N_SIDE}^3 matrix, unmodified "
-                                   "reference lduMatrix::solver (serial Pstream/dummy; the image has no MPI)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{args.steps} x {ITERS} PCG+DIC iterations on the {N_SIDE}^3 matrix, " +
+                                   ("unmodified reference lduMatrix::solver (serial Pstream/dummy; the image has no MPI)"
+                                    if kind == "reference" else "C restatement oracle/ldu_oracle.c (oracle/_ref absent)")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -281,8 +299,11 @@ def bench_ours(args):
         b_pre = 72.0 * n_local + 32.0 * n_faces
         b_amul = 24.0 * n_local + 16.0 * n_faces
         ach = b_pre / (t_pre_ms * 1e-3) / 1e9
+        # DRAM bytes of one fwd+bwd pair from the ncu --set full capture of this workload
+        # (profiles/r01_ncu_full_pcg128_top_kernels.txt: 151.1 MB + 178.2 MB); only valid for the 128^3 subdomain
+        traffic = 329.3e6 if n_local == N_SIDE ** 3 else None
         roofline = {"bound": "hbm", "kernel": "DIC precondition = k_sweep_fwd + k_sweep_bwd (wavefront sweeps)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "bytes_per_launch": b_pre, "ms_per_launch": t_pre_ms}
         spmv = {"kernel": "k_spmv (lduMatrix::Amul)", "achieved": b_amul / (t_amul_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": b_amul / (t_amul_ms * 1e-3) / 1e9 / peak, "bytes_per_launch": b_amul,
@@ -295,6 +316,11 @@ def bench_ours(args):
                     cpu = {"value": r[0], "unit": UNIT, "cores": 1, "kind": "reference",
                            "sample": f"{r[2]} PCG+DIC iterations on the same {N_SIDE}^3 matrix by the unmodified "
                                      f"reference solver (oracle/_ref, serial Pstream/dummy, {r[1]:.1f} s)"}
+                else:
+                    r = run_oracle_port_sample(sys_, 100)
+                    cpu = {"value": r[0], "unit": UNIT, "cores": 1, "kind": "port",
+                           "sample": f"{r[2]} PCG+DIC iterations on the same {N_SIDE}^3 matrix by the C restatement "
+                                     f"oracle/ldu_oracle.c (oracle/_ref not built on this box, {r[1]:.1f} s)"}
             except Exception as ex:  # the reference binary may be absent on a box that never built it
                 cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {ex}"}
         h2d = 8 * (n_local + n_faces) + 16 * n_local

@@ -141,10 +141,6 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         std::vector<int32_t> offs;
         bucketSort(lbByPos, nBwd, offs, L.bwdPos);
         makeTasks(offs, L.bwdTasks);
-        // structured meshes: the backward order is the forward order walked level by level from the end;
-        // record whether it is a pure reversal of level blocks with ascending positions inside (always true
-        // by construction) and whether bwdPos is affine so kernels may skip the indirection
-        L.bwdIsReverse = false;
     }
 
     // interfaces and the rows they touch

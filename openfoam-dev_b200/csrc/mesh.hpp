@@ -52,7 +52,6 @@ struct LevelHost {
     std::vector<int32_t> Lidx, Uidx;          // face -> entry index in the L / U arrays
     std::vector<SweepTask> fwdTasks, bwdTasks;
     std::vector<int32_t> bwdPos;    // backward processing order -> position
-    bool bwdIsReverse = false;      // bwdPos[q] == nCells-1-q (structured meshes)
 
     std::vector<HostInterface> interfaces;
     // rows touched by interfaces: boundary-row CSR in (patch, face) order

@@ -1182,7 +1182,6 @@ __global__ void k_coarsest_solve(CoarsestArgs a) {
             for (int c = 0; c < n; c++) r0[c] = r[c];
             double rho = 0, alpha = 0, omega = 0;
             int it = 0;
-            bool done = false;
             do {
                 const double rhoOld = rho;
                 rho = 0.0;
@@ -1206,7 +1205,6 @@ __global__ void k_coarsest_solve(CoarsestArgs a) {
                 fin = sm / nfac;
                 if (++it >= 0 && c_converged(fin, ini, a.tolerance, a.relTol)) {
                     for (int c = 0; c < n; c++) x[c] += alpha * y[c];
-                    done = true;
                     break;
                 }
                 c_precondition(a, up, lo, rD, z, s);
@@ -1224,7 +1222,6 @@ __global__ void k_coarsest_solve(CoarsestArgs a) {
                 for (int c = 0; c < n; c++) sm += fabs(r[c]);
                 fin = sm / nfac;
             } while (it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
-            (void)done;
         }
     }
     for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = x[c];
@@ -1247,7 +1244,6 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
         static b200ls_perf cperf;
         memset(&cperf, 0, offsetof(b200ls_perf, history));
         B2_CUDA(cudaMemsetAsync(M.corr.p, 0, sizeof(double) * D.nCells, S()));
-        M.rDValid = M.rDValid && true;
         if (m->symmetric) solvePCG(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
         else solvePBiCGStab(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
         return;
@@ -1315,9 +1311,6 @@ static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, d
             ensureLevelScratch(m, l + 1);
             double* corr = ML.corr.p;
             double* spare = ML.tmpC.p;
-            if (c.precond == B200LS_DIC || c.precond == B200LS_DILU) {
-                // the DIC/DILU smoother needs tmpB/tmpC itself: use the coarse Apsi scratch as spare
-            }
             opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
                      std::min(c.nPreSweeps + c.preSweepsLevelMultiplier * l, c.maxPreSweeps));
             if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
@@ -1443,7 +1436,6 @@ void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, con
               b200ls_perf* perf) {
     if (!m->valuesSet) throw CudaError("b200ls_solve: matrix coefficients not set");
     Context& cx = ctx();
-    const int n = DL(m, 0).nCells;
     const int64_t launches0 = cx.launches;
     memset(perf, 0, offsetof(b200ls_perf, history));
 
@@ -1500,7 +1492,6 @@ void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, con
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     cudaEventDestroy(ev2);
-    (void)n;
 }
 
 }  // namespace b200ls
