@@ -129,6 +129,11 @@ struct DevLevel {
     DevBuf<unsigned char> Lslot;    // slot of each L entry inside its owner's U row (symmetric SpMV); empty if > 255
     bool hasLslot = false;
     DevBuf<int2> fwdTasks, bwdTasks;
+    std::vector<int2> hostFwdTasks;                 // host copy + wavefront index of every task, for fused task lists
+    std::vector<int> hostFwdTaskLevel;
+    int nFwdLevels = 0;
+    int maxFwdSpan = 1;                             // max wavefront distance between the two cells of a face
+    std::map<int, DevBuf<int4>> multiSweepTasks;    // nSweeps -> tasks ordered by tau = level + 2*sweep
     DevBuf<int> bwdPos;
     int nFwdTasks = 0, nBwdTasks = 0;
     // interfaces

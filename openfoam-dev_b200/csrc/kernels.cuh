@@ -590,6 +590,131 @@ __global__ void __launch_bounds__(256) k_gs_sweep(SweepArgs a) {
     }
 }
 
+// Several Gauss-Seidel sweeps in ONE launch, pipelined: sweep s of wavefront L only needs sweep s of wavefront L-1
+// (lower neighbours) and sweep s-1 of wavefront L+1 (upper neighbours), so sweep s trails sweep s-1 by two
+// wavefronts instead of starting after it has finished.  Tasks are ordered by tau = L + 2s; the dependency chain of
+// nSweeps sweeps shrinks from nSweeps*nLevels to nLevels + 2*(nSweeps-1) hops.  X[0] is the input iterate, sweep s
+// reads X[s] (plain loads for s = 0, polled otherwise) and publishes X[s+1]; every X[s>0] starts all-sentinel.
+// Arithmetic per row is identical to k_gs_sweep.
+// entries beyond the first four of a row (rare on hex meshes): one at a time, kept out of line to save registers
+__device__ __noinline__ double gather_tail(double acc, int j0, int j1, const int* __restrict__ col,
+                                           const double* __restrict__ val, const double* y, int* err) {
+    for (int j = j0; j < j1; j++) {
+        const int c = col[j];
+        double w = ld_l2(y + c);
+        unsigned spins = 0;
+        while (is_sentinel(w)) {
+            if (++spins > kMaxSpins) {
+                *err = 1;
+                break;
+            }
+            w = ld_l2(y + c);
+        }
+        acc -= val[j] * w;
+    }
+    return acc;
+}
+
+static constexpr int kMaxFusedSweeps = 8;
+struct MultiSweepArgs {
+    const int4* tasks;      // (start, count, sweep, -)
+    int nTasks;
+    const int* Lptr;
+    const int* Lcol;
+    const double* Lval;
+    const int* Uptr;
+    const int* Ucol;
+    const double* Uval;
+    const double* diag;
+    const double* b;
+    double* X[kMaxFusedSweeps + 1];
+    int* err;
+};
+__global__ void __launch_bounds__(256, 2) k_gs_multi(MultiSweepArgs a) {
+    const int wpb = blockDim.x >> 5;
+    const int nW = gridDim.x * wpb;
+    const int lane = threadIdx.x & 31;
+    int t = blockIdx.x * wpb + (threadIdx.x >> 5);
+    int4 task = t < a.nTasks ? a.tasks[t] : make_int4(0, 0, 0, 0);
+    for (; t < a.nTasks; t += nW) {
+        const int4 next = (t + nW) < a.nTasks ? a.tasks[t + nW] : make_int4(0, 0, 0, 0);
+        if (lane < task.y) {
+            const int p = task.x + lane;
+            const int s = task.z;
+            const double* xo = a.X[s];
+            double* xn = a.X[s + 1];
+            const int j0 = a.Lptr[p], j1 = a.Lptr[p + 1];
+            const int k0 = a.Uptr[p], k1 = a.Uptr[p + 1];
+            const double dg = a.diag[p];
+            double acc = a.b[p];
+            if (s == 0) {
+                double up[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k0 + k < k1) up[k] = a.Uval[k0 + k] * xo[a.Ucol[k0 + k]];
+                acc = gather_deps<false, false>(acc, 1.0, j0, j1, a.Lcol, a.Lval, xn, a.err);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k0 + k < k1) acc -= up[k];
+                for (int k = k0 + 4; k < k1; k++) acc -= a.Uval[k] * xo[a.Ucol[k]];
+            } else {
+                // both dependency sets (this sweep's lower neighbours, the previous sweep's upper neighbours)
+                // become visible at about the same time: poll the first four of each together
+                const int nl = min(4, j1 - j0), nu = min(4, k1 - k0);
+                int cl[4], cu[4];
+                double vl[4], vu[4], wl[4], wu[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < nl) {
+                        cl[k] = a.Lcol[j0 + k];
+                        vl[k] = a.Lval[j0 + k];
+                    }
+                    if (k < nu) {
+                        cu[k] = a.Ucol[k0 + k];
+                        vu[k] = a.Uval[k0 + k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < nl) wl[k] = ld_l2(xn + cl[k]);
+                    if (k < nu) wu[k] = ld_l2(xo + cu[k]);
+                }
+                unsigned spins = 0;
+                while (true) {
+                    bool pending = false;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k < nl && is_sentinel(wl[k])) pending = true;
+                        if (k < nu && is_sentinel(wu[k])) pending = true;
+                    }
+                    if (!pending) break;
+                    if (++spins > kMaxSpins) {
+                        *a.err = 1;
+                        break;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k < nl && is_sentinel(wl[k])) wl[k] = ld_l2(xn + cl[k]);
+                        if (k < nu && is_sentinel(wu[k])) wu[k] = ld_l2(xo + cu[k]);
+                    }
+                }
+                // accumulate in the reference's order: all lower-neighbour terms, then all upper-neighbour terms
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < nl) acc -= vl[k] * wl[k];
+                if (j0 + nl < j1) acc = gather_tail(acc, j0 + nl, j1, a.Lcol, a.Lval, xn, a.err);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (k < nu) acc -= vu[k] * wu[k];
+                if (k0 + nu < k1) acc = gather_tail(acc, k0 + nu, k1, a.Ucol, a.Uval, xo, a.err);
+            }
+            st_l2(xn + p, acc / dg);
+        }
+        __syncwarp();
+        task = next;
+    }
+}
+
 // Reverse half of symGaussSeidel (symGaussSeidelSmoother.C:178-205) in gather form.  After the forward loop
 // bPrime[c] = b'[c] - sum_{nbr faces asc} lower[f]*psi_fwd[l]; the reverse loop then subtracts the owner side with
 // the already reverse-updated upper neighbours:

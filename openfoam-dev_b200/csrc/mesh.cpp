@@ -94,6 +94,8 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         nFwd = std::max(nFwd, lf[c] + 1);
         nBwd = std::max(nBwd, lb[c] + 1);
     }
+    L.maxFwdSpan = 1;
+    for (int32_t f = 0; f < nFaces; f++) L.maxFwdSpan = std::max(L.maxFwdSpan, lf[upper[f]] - lf[lower[f]]);
     bucketSort(lf, nFwd, L.fwdOffsets, L.fwdRows);
     bucketSort(lb, nBwd, L.bwdOffsets, L.bwdRows);
 

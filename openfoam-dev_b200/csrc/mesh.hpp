@@ -43,6 +43,7 @@ struct LevelHost {
     std::vector<int32_t> lower, upper;                      // reference face order
     std::vector<int32_t> losort, ownerStart, losortStart;   // reference-exact (lduAddressing.C:32-170)
     std::vector<int32_t> fwdOffsets, fwdRows, bwdOffsets, bwdRows;   // canonical wavefronts (cells)
+    int32_t maxFwdSpan = 1;         // max over faces of Lf[upper] - Lf[lower] (1 on structured blocks)
 
     // ---- native layout: rows in forward-wavefront-major order ("positions") ----
     std::vector<int32_t> perm;      // position -> cell

@@ -170,6 +170,19 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         B2_CUDA(cudaMemcpyAsync(D.bwdTasks.p, H.bwdTasks.data(), H.bwdTasks.size() * sizeof(int2),
                                 cudaMemcpyHostToDevice, s));
     D.bwdPos.upload(H.bwdPos, s);
+    D.hostFwdTasks.assign(reinterpret_cast<const int2*>(H.fwdTasks.data()),
+                          reinterpret_cast<const int2*>(H.fwdTasks.data()) + H.fwdTasks.size());
+    D.nFwdLevels = int(H.fwdOffsets.size()) - 1;
+    D.maxFwdSpan = H.maxFwdSpan;
+    D.hostFwdTaskLevel.resize(H.fwdTasks.size());
+    {
+        int lev = 0;
+        for (size_t t = 0; t < H.fwdTasks.size(); t++) {
+            while (lev + 1 < D.nFwdLevels && H.fwdTasks[t].start >= H.fwdOffsets[lev + 1]) lev++;
+            D.hostFwdTaskLevel[t] = lev;
+        }
+    }
+    D.multiSweepTasks.clear();
 
     D.nIfaces = int(H.interfaces.size());
     D.ifaceSize.clear();
@@ -623,6 +636,72 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
     const int n = D.nCells;
     if (n == 0) return;
     ensureLevelScratch(m, level);
+    static const bool noFusedGS = getenv("B200LS_NO_FUSED_GS") != nullptr;
+    // lag between consecutive sweeps: an upper neighbour may sit up to maxFwdSpan wavefronts ahead, and its previous
+    // sweep must come earlier in the task order (deadlock freedom), so sweep s starts lag = maxFwdSpan + 1
+    // wavefronts after sweep s-1 (2 on structured blocks)
+    const int lag = D.maxFwdSpan + 1;
+    if (smoother == B200LS_GAUSS_SEIDEL && D.nIfaces == 0 && nSweeps >= 2 && nSweeps <= kMaxFusedSweeps && !noFusedGS &&
+        2 * lag <= D.nFwdLevels) {
+        // all sweeps in one pipelined launch (k_gs_multi): chain of nLevels + lag*(nSweeps-1) hops instead of
+        // nSweeps*nLevels.  Needs no communication between sweeps, so only levels without processor interfaces.
+        auto it = D.multiSweepTasks.find(nSweeps);
+        if (it == D.multiSweepTasks.end()) {
+            // bucket the (task, sweep) pairs by tau = level + 2*sweep
+            const int nT = int(D.hostFwdTasks.size());
+            std::vector<int> levelStart(D.nFwdLevels + 1, nT);
+            for (int t = nT - 1; t >= 0; t--) levelStart[D.hostFwdTaskLevel[t]] = t;
+            for (int l = D.nFwdLevels - 1; l >= 0; l--)
+                if (levelStart[l] == nT) levelStart[l] = levelStart[l + 1];
+            std::vector<int4> fused;
+            fused.reserve(size_t(nT) * nSweeps);
+            const int maxTau = D.nFwdLevels - 1 + lag * (nSweeps - 1);
+            for (int tau = 0; tau <= maxTau; tau++) {
+                for (int sw = 0; sw < nSweeps; sw++) {
+                    const int l = tau - lag * sw;
+                    if (l < 0 || l >= D.nFwdLevels) continue;
+                    for (int t = levelStart[l]; t < levelStart[l + 1]; t++)
+                        fused.push_back(make_int4(D.hostFwdTasks[t].x, D.hostFwdTasks[t].y, sw, 0));
+                }
+            }
+            DevBuf<int4>& buf = D.multiSweepTasks[nSweeps];
+            buf.alloc(fused.size());
+            if (!fused.empty())
+                B2_CUDA(cudaMemcpyAsync(buf.p, fused.data(), fused.size() * sizeof(int4), cudaMemcpyHostToDevice, S()));
+            B2_CUDA(cudaStreamSynchronize(S()));
+            it = D.multiSweepTasks.find(nSweeps);
+        }
+        if (M.gsBufs.n < size_t(nSweeps - 1) * n) M.gsBufs.alloc(size_t(nSweeps - 1) * n);
+        fillSentinel(M.gsBufs.p, (nSweeps - 1) * n);
+        fillSentinel(spare, n);
+        MultiSweepArgs a{};
+        a.tasks = it->second.p;
+        a.nTasks = int(it->second.n);
+        a.Lptr = D.Lptr.p;
+        a.Lcol = D.Lcol.p;
+        a.Lval = M.Lval(D.nFaces);
+        a.Uptr = D.Uptr.p;
+        a.Ucol = D.Ucol.p;
+        a.Uval = M.Uval();
+        a.diag = M.diag.p;
+        a.b = source;
+        a.X[0] = psi;
+        for (int sw = 1; sw < nSweeps; sw++) a.X[sw] = M.gsBufs.p + size_t(sw - 1) * n;
+        a.X[nSweeps] = spare;
+        a.err = ctx().errFlag.p;
+        {
+            Context& c = ctx();
+            static int occ = 0;
+            if (!occ) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_multi, 256, 0));
+            const int perSM = std::min(occ, c.sweepBlocksPerSM > 0 ? c.sweepBlocksPerSM : 4);
+            const int blocks = std::max(1, std::min(perSM * c.numSMs, (a.nTasks + 7) / 8));
+            void* args[] = {&a};
+            B2_CUDA(cudaLaunchCooperativeKernel((const void*)k_gs_multi, dim3(blocks), dim3(256), args, 0, c.stream));
+            c.launches++;
+        }
+        std::swap(psi, spare);
+        return;
+    }
     if (smoother == B200LS_GAUSS_SEIDEL || smoother == B200LS_SYM_GAUSS_SEIDEL) {
         for (int sweep = 0; sweep < nSweeps; sweep++) {
             const double* bPrime = source;

@@ -27,6 +27,7 @@ struct MatLevel {
     unsigned long long haloEpoch = 0;
     // level work vectors (GAMG): correction, source, scratch
     DevBuf<double> corr, src, tmpA, tmpB, tmpC;
+    DevBuf<double> gsBufs;          // intermediate iterates of the fused multi-sweep Gauss-Seidel kernel
     bool tmpASentinel = false;      // tmpA is known to be all-sentinel
     double* Uval() { return vals.p; }
     double* Lval(int nFaces) { return vals.p + nFaces; }
