@@ -1156,10 +1156,25 @@ __device__ static bool c_converged(double fin, double ini, double tol, double re
     return fin < tol || (relTol > 1e-20 && fin < relTol * ini);
 }
 
-__global__ void k_coarsest_solve(CoarsestArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
+    // The arithmetic is one thread's sequential replay of the reference; when the level fits, its vectors,
+    // coefficients and addressing are staged in shared memory first (the loops are chains of dependent loads).
+    extern __shared__ double csm[];
+    CoarsestArgs a = a_;
     const int n = a.nCells, nF = a.nFaces;
-    double* w = a.work;
+    if (useSmem) {
+        int* sl = reinterpret_cast<int*>(csm + 2 * nF + 12 * n);
+        int* su = sl + nF;
+        for (int f = threadIdx.x; f < nF; f += blockDim.x) {
+            sl[f] = a.lower[f];
+            su[f] = a.upper[f];
+        }
+        __syncthreads();
+        a.lower = sl;
+        a.upper = su;
+    }
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double* w = useSmem ? csm : a.work;
     double* up = w;            w += nF;
     double* lo = w;            w += nF;
     double* dg = w;            w += n;
@@ -1346,7 +1361,17 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
     a.tolerance = c.tolerance;
     a.relTol = c.relTol;
     a.maxIter = 1000;   // lduMatrix::solver::defaultMaxIter_
-    LAUNCH(k_coarsest_solve, 1, 32, a);
+    {
+        const size_t bytes = (size_t(2) * D.nFaces + size_t(12) * D.nCells) * sizeof(double) + size_t(2) * D.nFaces * sizeof(int);
+        const int useSmem = bytes <= 160 * 1024 ? 1 : 0;
+        static bool attr = false;
+        if (!attr) {
+            B2_CUDA(cudaFuncSetAttribute(k_coarsest_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr = true;
+        }
+        k_coarsest_solve<<<1, 32, useSmem ? bytes : 0, S()>>>(a, useSmem);
+        ctx().launches++;
+    }
 }
 
 // GAMGSolver::scale (GAMGSolverScale.C:31-76)
