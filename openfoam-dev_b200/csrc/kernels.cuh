@@ -236,6 +236,78 @@ k_spmv_sym(double* __restrict__ out, double* __restrict__ out2, const double* __
     if (MODE == SPMV_AMUL_AND_RESIDUAL) out2[p] = b[p] - acc;
 }
 
+// Two rows per thread (rows p and p + blockDim.x of a 2*blockDim.x tile): the gathers of the symmetric kernel form a
+// four-deep dependent chain (Lptr -> Lcol/Lslot -> Uptr[q] -> Uval), so two independent chains per thread double the
+// loads in flight.  Same arithmetic order per row as k_spmv_sym<SPMV_AMUL>.
+__global__ void __launch_bounds__(256)
+k_spmv_sym_x2(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ diag,
+              const int* __restrict__ Lptr, const int* __restrict__ Lcol, const unsigned char* __restrict__ Lslot,
+              const int* __restrict__ Uptr, const int* __restrict__ Ucol, const double* __restrict__ Uval, int n) {
+    const int pa = blockIdx.x * (2 * blockDim.x) + threadIdx.x;
+    const int pb = pa + blockDim.x;
+    const bool va = pa < n, vb = pb < n;
+    int la0 = 0, la1 = 0, ua0 = 0, ua1 = 0, lb0 = 0, lb1 = 0, ub0 = 0, ub1 = 0;
+    double acca = 0.0, accb = 0.0;
+    if (va) {
+        la0 = Lptr[pa];
+        la1 = Lptr[pa + 1];
+        ua0 = Uptr[pa];
+        ua1 = Uptr[pa + 1];
+    }
+    if (vb) {
+        lb0 = Lptr[pb];
+        lb1 = Lptr[pb + 1];
+        ub0 = Uptr[pb];
+        ub1 = Uptr[pb + 1];
+    }
+    if (va) acca = diag[pa] * x[pa];
+    if (vb) accb = diag[pb] * x[pb];
+    const int nl = max(la1 - la0, lb1 - lb0);
+    for (int k = 0; k < nl; k++) {
+        const bool ka = la0 + k < la1, kb = lb0 + k < lb1;
+        int qa = 0, qb = 0, sa = 0, sb = 0;
+        if (ka) {
+            qa = Lcol[la0 + k];
+            sa = Lslot[la0 + k];
+        }
+        if (kb) {
+            qb = Lcol[lb0 + k];
+            sb = Lslot[lb0 + k];
+        }
+        int ba = 0, bb = 0;
+        if (ka) ba = Uptr[qa];
+        if (kb) bb = Uptr[qb];
+        double ca = 0.0, cb = 0.0, xa = 0.0, xb = 0.0;
+        if (ka) {
+            ca = Uval[ba + sa];
+            xa = x[qa];
+        }
+        if (kb) {
+            cb = Uval[bb + sb];
+            xb = x[qb];
+        }
+        if (ka) acca += ca * xa;
+        if (kb) accb += cb * xb;
+    }
+    const int nu = max(ua1 - ua0, ub1 - ub0);
+    for (int k = 0; k < nu; k++) {
+        const bool ka = ua0 + k < ua1, kb = ub0 + k < ub1;
+        double ca = 0.0, cb = 0.0, xa = 0.0, xb = 0.0;
+        if (ka) {
+            ca = Uval[ua0 + k];
+            xa = x[Ucol[ua0 + k]];
+        }
+        if (kb) {
+            cb = Uval[ub0 + k];
+            xb = x[Ucol[ub0 + k]];
+        }
+        if (ka) acca += ca * xa;
+        if (kb) accb += cb * xb;
+    }
+    if (va) out[pa] = acca;
+    if (vb) out[pb] = accb;
+}
+
 // wA = A pA fused with wApA = wA.pA (PCG.C:159-161).  Grid-stride over rows with a bounded grid so that the
 // per-block partials fit the reduction scratch.
 template <bool SYM>
