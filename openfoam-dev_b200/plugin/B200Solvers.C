@@ -38,6 +38,7 @@
 #include <map>
 #include <vector>
 #include <cstdlib>
+#include <cstdint>
 
 namespace Foam
 {
@@ -55,6 +56,7 @@ struct cacheEntry
     b200ls_matrix_t matrix;
     label nCells;
     label nFaces;
+    uint64_t fingerprint;
     bool agglomerated;
 
     cacheEntry()
@@ -63,12 +65,30 @@ struct cacheEntry
         matrix(nullptr),
         nCells(-1),
         nFaces(-1),
+        fingerprint(0),
         agglomerated(false)
     {}
 };
 
 static std::map<const lduAddressing*, cacheEntry> cache_;
 static bool initialised_ = false;
+
+
+//- Cheap fingerprint of the addressing (sizes + a strided sample of lower/upper): a mesh that changed topology
+//  under an unchanged lduAddressing object must not reuse the cached device layout
+static uint64_t fingerprint(const lduAddressing& addr)
+{
+    const labelUList& l = addr.lowerAddr();
+    const labelUList& u = addr.upperAddr();
+    uint64_t h = 1469598103934665603ull ^ uint64_t(addr.size());
+    const label stride = max(label(1), l.size()/4096);
+    for (label f = 0; f < l.size(); f += stride)
+    {
+        h = (h ^ uint64_t(uint32_t(l[f]))) * 1099511628211ull;
+        h = (h ^ uint64_t(uint32_t(u[f]))) * 1099511628211ull;
+    }
+    return h ^ uint64_t(l.size());
+}
 
 
 static void check(const int rc, const char* what)
@@ -172,7 +192,9 @@ protected:
         const label nCells = addr.size();
         const label nFaces = addr.lowerAddr().size();
 
-        if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces))
+        const uint64_t fp = B200::fingerprint(addr);
+
+        if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces || e.fingerprint != fp))
         {
             // mesh changed under the same address: rebuild
             b200ls_matrix_free(e.matrix);
@@ -228,6 +250,7 @@ protected:
             e.matrix = b200ls_matrix_create(e.mesh);
             e.nCells = nCells;
             e.nFaces = nFaces;
+            e.fingerprint = fp;
         }
 
         return e;
