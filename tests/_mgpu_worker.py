@@ -61,6 +61,24 @@ def main():
         if rank == 0:
             print(f"{kind}: amul rel err {err:.2e} residual rel err {err_r:.2e}", flush=True)
 
+        if kind == "sym":
+            # residual history of the decomposed PCG+DIC against the in-process emulation of the reference's
+            # decomposed algorithm (tests/_emulated_ranks.py): same iteration count, residuals within 1e-9
+            import _emulated_ranks as em
+
+            e_psi, e_perf = em.pcg(parts, "DIC", tolerance=1e-10)
+            ctl = capi.controls("PCG", preconditioner="DIC", tolerance=1e-10, relTol=0.0, recordHistory=1)
+            psi, perf = mat.solve(ctl, part.source)
+            h = capi.history(perf)
+            nh = min(len(h), len(e_perf["history"]))
+            dh = float(np.max(np.abs(h[:nh] - e_perf["history"][:nh]))) if nh else 0.0
+            dpsi = float(np.max(np.abs(psi - e_psi[rank])) / np.max(np.abs(e_psi[rank])))
+            good = abs(perf.nIterations - e_perf["nIterations"]) <= 1 and dh <= 1e-9 * e_perf["initialResidual"] and \
+                (perf.nIterations != e_perf["nIterations"] or dpsi <= 1e-9)
+            ok &= bool(good)
+            if rank == 0:
+                print(f"sym: decomposed PCG+DIC vs emulated ranks: iterations {perf.nIterations}/{e_perf['nIterations']} "
+                      f"max history diff {dh:.2e} solution rel diff {dpsi:.2e} {'OK' if good else 'FAIL'}", flush=True)
         exact = np.linalg.solve(A, glob.source)
         combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
         combos += [("GAMG", "GaussSeidel"), ("GAMG", "DIC" if kind == "sym" else "DILU")]

@@ -79,3 +79,30 @@ def test_solvers_bit_exact(fx):
         if hkey in ref:
             n = min(len(perf["history"]), len(ref[hkey]), int(rperf[2]))
             assert np.array_equal(perf["history"][:n], ref[hkey][:n]), ctx
+
+
+def test_emulated_ranks_reduce_to_the_reference_at_one_rank():
+    """tests/_emulated_ranks.py (decomposed PCG built from the C oracle) equals the reference golden when there is a
+    single rank, and converges to the global solution when the system is cut in two."""
+    import _emulated_ranks as em
+    from _util import cases, max_rel_diff
+    from _pkg import load_pkg
+
+    load_pkg()
+    from b200ls import decompose
+
+    inp, ref = load_fixture("block_16x16x16_rand")
+    s = system_from_entries(inp)
+    psi, perf = em.pcg([s], "DIC", tolerance=1e-10)
+    r = ref["solve.1.perf"]
+    assert perf["nIterations"] == int(r[2])
+    assert abs(perf["finalResidual"] - r[1]) <= 1e-12 * r[0]
+    assert max_rel_diff(psi[0], ref["solve.1.psi"]) <= 1e-12
+    g = cases.cavity_laplacian(12, 10, 8, coeffs="random")
+    parts, maps = decompose.decompose_system(g, decompose.box_cell_ranks(12, 10, 8, (2, 1, 1)), 2)
+    psi2, perf2 = em.pcg(parts, "DIC", tolerance=1e-12)
+    full = np.zeros(g.n_cells)
+    for m, x in zip(maps, psi2):
+        full[m] = x
+    xg, pg = orc.solve(orc.System(g), "PCG", orc.controls("DIC", tolerance=1e-12), g.source)
+    assert max_rel_diff(full, xg) <= 1e-10
