@@ -132,3 +132,19 @@ def test_pcg_rejects_asymmetric_matrix():
     mesh, mat = capi.from_system(s)
     with pytest.raises(capi.B200Error, match="symmetric"):
         mat.solve(capi.controls("PCG", "DIC"), s.source)
+
+
+def test_solve_dev_matches_host_pointer_solve():
+    """b200ls_solve_dev (psi/source already resident in HBM, cell order) == b200ls_solve (host pointers)."""
+    torch = pytest.importorskip("torch")
+    s = cases.cavity_laplacian(12, 9, 7, coeffs="random", rhs_kind="uniform")
+    mesh, mat = capi.from_system(s)
+    ctl = capi.controls("PCG", "DIC", tolerance=1e-10, relTol=0.0)
+    psi_h, perf_h = mat.solve(ctl, s.source)
+    d_src = torch.from_numpy(s.source).cuda()
+    d_psi = torch.zeros(s.n_cells, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    perf_d = mat.solve_dev(ctl, d_psi.data_ptr(), d_src.data_ptr())
+    assert perf_d.nIterations == perf_h.nIterations
+    assert np.array_equal(d_psi.cpu().numpy(), psi_h)
+    assert perf_d.kernelLaunches > 0 and perf_d.solveMs > 0
