@@ -15,11 +15,14 @@ import numpy as np
 
 @dataclass
 class Interface:
-    """One processor patch of a decomposed system (reference: processorFvPatch)."""
+    """One coupled patch: a processor patch of a decomposed system (reference: processorFvPatch) when
+    nbr_patch < 0, or one half of a cyclic pair on the same rank (reference: cyclicFvPatch; face i is coupled
+    to face i of patch `nbr_patch`) when nbr_patch >= 0."""
     neighb_rank: int
     face_cells: np.ndarray          # int32 [nPatchFaces], local cell of each patch face
     bou_coeffs: np.ndarray          # float64, interfaceBouCoeffs
     int_coeffs: np.ndarray          # float64, interfaceIntCoeffs
+    nbr_patch: int = -1
 
 
 @dataclass
@@ -146,6 +149,46 @@ def convection_diffusion(nx, ny, nz=1, nu=0.01, dt_coeff=0.5, seed=20261017, rhs
     )
 
 
+def _axis_planes(shape, axis):
+    """Cells of the low and high boundary planes normal to `axis`, both in ascending cell order (so face i of
+    one plane faces face i of the other)."""
+    nx, ny, nz = shape
+    c = np.arange(nx * ny * nz, dtype=np.int64)
+    idx = [c % nx, (c // nx) % ny, c // (nx * ny)][axis]
+    lo = c[idx == 0].astype(np.int32)
+    hi = c[idx == shape[axis] - 1].astype(np.int32)
+    return lo, hi
+
+
+def add_cyclic(sys_, axis, seed=1):
+    """Make the block periodic along `axis`: a cyclic patch pair (low plane, high plane) whose faces carry the
+    same kind of coefficients as the internal faces normal to `axis` (the wrap-around face is owned by the
+    high-plane cell).  Coupled-patch convention of the reference (fvMatrix.C:112-173 addBoundaryDiag,
+    lduMatrixATmul.C:82 updateMatrixInterfaces): row c gets  -bouCoeffs * psi[neighbour cell],  the diagonal
+    gets internalCoeffs; with negSumDiag semantics internalCoeffs = -(off-diagonal coefficient)."""
+    lo_cells, hi_cells = _axis_planes(sys_.shape, axis)
+    n = lo_cells.size
+    rng = np.random.Generator(np.random.PCG64(seed + 17 * axis))
+    base = np.abs(sys_.upper_coeffs[sys_.face_dir == axis]).mean() if np.any(sys_.face_dir == axis) else 1.0
+    sign = -1.0 if sys_.upper_coeffs.mean() < 0 else 1.0
+    # coefficient multiplying psi[high] in the low rows ("lower" of the wrap face) and psi[low] in the high rows
+    c_hi_rows = sign * base * (0.75 + 0.5 * rng.random(n))
+    c_lo_rows = c_hi_rows if sys_.symmetric else sign * base * (0.75 + 0.5 * rng.random(n))
+    diag = sys_.diag.copy()
+    # negSumDiag: Diag[l] -= Lower, Diag[u] -= Upper (l = high-plane owner, u = low-plane neighbour)
+    np.subtract.at(diag, hi_cells, c_lo_rows)
+    np.subtract.at(diag, lo_cells, c_hi_rows)
+    first = len(sys_.interfaces)
+    sys_.diag = diag
+    sys_.interfaces = list(sys_.interfaces) + [
+        Interface(neighb_rank=-1, face_cells=lo_cells, bou_coeffs=-c_lo_rows, int_coeffs=-c_hi_rows,
+                  nbr_patch=first + 1),
+        Interface(neighb_rank=-1, face_cells=hi_cells, bou_coeffs=-c_hi_rows, int_coeffs=-c_lo_rows,
+                  nbr_patch=first),
+    ]
+    return sys_
+
+
 def random_graph(n_cells, avg_degree=5, symmetric=True, seed=20261017, max_span=None):
     """Unstructured stand-in: a random upper-triangular-ordered LDU graph (every cell owns a few faces to random
     higher-numbered cells within `max_span`), random coefficients, strictly diagonally dominant.  Exercises rows
@@ -189,4 +232,13 @@ def to_entries(sys_: LduSystem):
         e["source"] = sys_.source.astype(np.float64)
     if sys_.face_weights is not None:
         e["faceWeights"] = sys_.face_weights.astype(np.float64)
+    if sys_.interfaces:
+        if any(i.nbr_patch < 0 for i in sys_.interfaces):
+            raise ValueError("only cyclic interfaces can be written to a single-process B2LS case")
+        e["nIfaces"] = len(sys_.interfaces)
+        for k, i in enumerate(sys_.interfaces):
+            e[f"iface.{k}.faceCells"] = i.face_cells.astype(np.int32)
+            e[f"iface.{k}.nbrPatch"] = int(i.nbr_patch)
+            e[f"iface.{k}.bouCoeffs"] = i.bou_coeffs.astype(np.float64)
+            e[f"iface.{k}.intCoeffs"] = i.int_coeffs.astype(np.float64)
     return e

@@ -13,10 +13,21 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* A coupled patch whose neighbour cells live in the same address space: one half of a cyclic pair
+ * (lduAddressing/lduInterface/cyclicLduInterface.H; face e is coupled to face e of the neighbour patch, so
+ * nbrCells = faceCells of that patch).  Processor patches are emulated on top of this file by tests/_emulated_ranks.py. */
+typedef struct {
+    int32_t n;
+    const int32_t *faceCells, *nbrCells;
+    const double *bou, *inn;       /* interfaceBouCoeffs, interfaceIntCoeffs */
+} iface_t;
+
 typedef struct {
     int32_t nCells, nFaces;
     const int32_t *l, *u;          /* lowerAddr, upperAddr */
     const double *diag, *upper, *lower; /* lower == upper when symmetric */
+    int32_t nIfaces;
+    const iface_t* ifaces;
 } ldu_t;
 
 typedef struct {
@@ -42,12 +53,27 @@ static const double SMALL_ = 1e-20;                    /* solverPerformance::sma
 
 /* ---- lduMatrix::Amul / residual / sumA  (lduMatrix/lduMatrixATmul.C:34-92, 203-280, 154-200) ---- */
 
+/* lduMatrix::updateMatrixInterfaces (lduMatrix/lduMatrixUpdateMatrixInterfaces.C:94-266), patches in index order, with
+ * the cyclic update  result[faceCells[e]] -= coeffs[e]*psi[nbrFaceCells[e]]  (finiteVolume cyclicFvPatchField.C:150-174,
+ * solvers/GAMG/interfaceFields/cyclicGAMGInterfaceField/cyclicGAMGInterfaceField.C:124-146).  negate: the caller passes
+ * -interfaceBouCoeffs (residual, lduMatrixATmul.C:236-244; GaussSeidelSmoother.C:95-107). */
+static void update_interfaces(const ldu_t* A, int negate, const double* psi, double* result) {
+    for (int i = 0; i < A->nIfaces; i++) {
+        const iface_t* I = &A->ifaces[i];
+        for (int e = 0; e < I->n; e++) {
+            const double c = negate ? -I->bou[e] : I->bou[e];
+            result[I->faceCells[e]] -= c * psi[I->nbrCells[e]];
+        }
+    }
+}
+
 void oracle_amul(const ldu_t* A, const double* psi, double* Apsi) {
     for (int c = 0; c < A->nCells; c++) Apsi[c] = A->diag[c] * psi[c];
     for (int f = 0; f < A->nFaces; f++) {
         Apsi[A->u[f]] += A->lower[f] * psi[A->l[f]];
         Apsi[A->l[f]] += A->upper[f] * psi[A->u[f]];
     }
+    update_interfaces(A, 0, psi, Apsi);
 }
 
 void oracle_residual(const ldu_t* A, const double* psi, const double* source, double* rA) {
@@ -56,6 +82,7 @@ void oracle_residual(const ldu_t* A, const double* psi, const double* source, do
         rA[A->u[f]] -= A->lower[f] * psi[A->l[f]];
         rA[A->l[f]] -= A->upper[f] * psi[A->u[f]];
     }
+    update_interfaces(A, 1, psi, rA);
 }
 
 void oracle_sum_a(const ldu_t* A, double* sumA) {
@@ -64,6 +91,8 @@ void oracle_sum_a(const ldu_t* A, double* sumA) {
         sumA[A->u[f]] += A->lower[f];
         sumA[A->l[f]] += A->upper[f];
     }
+    for (int i = 0; i < A->nIfaces; i++)                   /* lduMatrixATmul.C:185-199 */
+        for (int e = 0; e < A->ifaces[i].n; e++) sumA[A->ifaces[i].faceCells[e]] -= A->ifaces[i].bou[e];
 }
 
 /* ---- lduAddressing::calcLosort (lduAddressing/lduAddressing.C:32-90) ---- */
@@ -144,6 +173,7 @@ void oracle_smooth(const ldu_t* A, int kind, double* psi, const double* source, 
         double* bPrime = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
         for (int sweep = 0; sweep < nSweeps; sweep++) {
             memcpy(bPrime, source, sizeof(double) * (size_t)n);
+            update_interfaces(A, 1, psi, bPrime);
             for (int c = 0; c < n; c++) {
                 double psii = bPrime[c];
                 for (int f = os[c]; f < os[c + 1]; f++) psii -= A->upper[f] * psi[A->u[f]];
@@ -168,6 +198,7 @@ void oracle_smooth(const ldu_t* A, int kind, double* psi, const double* source, 
         double* bPrime = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
         for (int sweep = 0; sweep < nSweeps; sweep++) {
             memcpy(bPrime, source, sizeof(double) * (size_t)n);
+            update_interfaces(A, 1, psi, bPrime);
             for (int c = 0; c < n; c++) {
                 double psii = bPrime[c];
                 for (int f = os[c]; f < os[c + 1]; f++) psii -= A->upper[f] * psi[A->u[f]];
@@ -390,7 +421,17 @@ typedef struct {
     int32_t* faceRestrictAddr;
     uint8_t* faceFlip;
     double *corr, *src;
+    int32_t nIfaces;
+    struct lev_iface* ifs;         /* cyclic patches of this level */
+    iface_t* views;                /* the same as ldu_t views */
 } level_t;
+
+typedef struct lev_iface {
+    int32_t n, nbrPatch;
+    int32_t *faceCells, *nbrCells;
+    int32_t* faceRestrict;         /* patch face -> coarse patch face (NULL on the coarsest level) */
+    double *bou, *inn;
+} lev_iface_t;
 
 typedef struct {
     int nLevels;                   /* incl. the finest */
@@ -504,13 +545,71 @@ static void agglomerate_addressing(level_t* fine, level_t* coarse, int nCoarse) 
     free(cnt); free(cfaces); free(initNei); free(renum);
 }
 
+/* cyclicGAMGInterface constructor (solvers/GAMG/interfaces/cyclicGAMGInterface/cyclicGAMGInterface.C:85-157; the same
+ * pair logic as processorGAMGInterface.C:75-147): coarse patch faces are the distinct (master coarse cell, slave coarse
+ * cell) pairs in first-seen order; the owner patch (lower patch index) is the master. */
+static void agglomerate_interfaces(level_t* fine, level_t* coarse) {
+    const int32_t* rm = fine->restrictAddr;
+    coarse->nIfaces = fine->nIfaces;
+    coarse->ifs = calloc((size_t)(fine->nIfaces > 0 ? fine->nIfaces : 1), sizeof(lev_iface_t));
+    coarse->views = calloc((size_t)(fine->nIfaces > 0 ? fine->nIfaces : 1), sizeof(iface_t));
+    for (int i = 0; i < fine->nIfaces; i++) {
+        lev_iface_t* F = &fine->ifs[i];
+        lev_iface_t* Cc = &coarse->ifs[i];
+        const int owner = i < F->nbrPatch;
+        size_t cap = 16;
+        while (cap < (size_t)F->n * 4) cap *= 2;
+        int64_t* keys = malloc(sizeof(int64_t) * cap);
+        int32_t* vals = malloc(sizeof(int32_t) * cap);
+        for (size_t k = 0; k < cap; k++) keys[k] = -1;
+        F->faceRestrict = malloc(sizeof(int32_t) * (size_t)(F->n > 0 ? F->n : 1));
+        Cc->faceCells = malloc(sizeof(int32_t) * (size_t)(F->n > 0 ? F->n : 1));
+        Cc->nbrPatch = F->nbrPatch;
+        int nC = 0;
+        for (int e = 0; e < F->n; e++) {
+            const int32_t loc = rm[F->faceCells[e]], nbr = rm[F->nbrCells[e]];   /* interfaceInternalField / internalFieldTransfer */
+            const int64_t key = owner ? (((int64_t)loc << 32) | (uint32_t)nbr) : (((int64_t)nbr << 32) | (uint32_t)loc);
+            size_t h = (size_t)((uint64_t)key * 0x9E3779B97F4A7C15ull) & (cap - 1);
+            while (keys[h] != -1 && keys[h] != key) h = (h + 1) & (cap - 1);
+            if (keys[h] == -1) {
+                keys[h] = key;
+                vals[h] = nC;
+                Cc->faceCells[nC++] = loc;
+            }
+            F->faceRestrict[e] = vals[h];
+        }
+        Cc->n = nC;
+        free(keys);
+        free(vals);
+    }
+    for (int i = 0; i < coarse->nIfaces; i++) {            /* nbrPatch().faceCells() */
+        lev_iface_t* Cc = &coarse->ifs[i];
+        const lev_iface_t* N = &coarse->ifs[Cc->nbrPatch];
+        if (N->n != Cc->n) abort();                         /* both halves must number their coarse faces alike */
+        Cc->nbrCells = malloc(sizeof(int32_t) * (size_t)(Cc->n > 0 ? Cc->n : 1));
+        memcpy(Cc->nbrCells, N->faceCells, sizeof(int32_t) * (size_t)Cc->n);
+    }
+}
+
 static void restrict_field(double* cf, const double* ff, const int32_t* map, int nFine, int nCoarse) {
     for (int i = 0; i < nCoarse; i++) cf[i] = 0;          /* GAMGAgglomerationTemplates.C:84-89 */
     for (int i = 0; i < nFine; i++) cf[map[i]] += ff[i];
 }
 
+hierarchy_t* oracle_gamg_build_coupled(int32_t nCells, int32_t nFaces, const int32_t* l, const int32_t* u,
+                                       const double* faceWeights, int minCells, int forwardStart, int32_t nIfaces,
+                                       const int32_t* ifaceSizes, const int32_t* const* ifaceFaceCells,
+                                       const int32_t* ifaceNbrPatch);
+
 hierarchy_t* oracle_gamg_build(int32_t nCells, int32_t nFaces, const int32_t* l, const int32_t* u,
                                const double* faceWeights, int minCells, int forwardStart) {
+    return oracle_gamg_build_coupled(nCells, nFaces, l, u, faceWeights, minCells, forwardStart, 0, NULL, NULL, NULL);
+}
+
+hierarchy_t* oracle_gamg_build_coupled(int32_t nCells, int32_t nFaces, const int32_t* l, const int32_t* u,
+                                       const double* faceWeights, int minCells, int forwardStart, int32_t nIfaces,
+                                       const int32_t* ifaceSizes, const int32_t* const* ifaceFaceCells,
+                                       const int32_t* ifaceNbrPatch) {
     hierarchy_t* H = calloc(1, sizeof(hierarchy_t));
     level_t* L0 = &H->lev[0];
     L0->nCells = nCells;
@@ -519,6 +618,19 @@ hierarchy_t* oracle_gamg_build(int32_t nCells, int32_t nFaces, const int32_t* l,
     L0->u = malloc(sizeof(int32_t) * (size_t)(nFaces > 0 ? nFaces : 1));
     memcpy(L0->l, l, sizeof(int32_t) * (size_t)nFaces);
     memcpy(L0->u, u, sizeof(int32_t) * (size_t)nFaces);
+    L0->nIfaces = nIfaces;
+    L0->ifs = calloc((size_t)(nIfaces > 0 ? nIfaces : 1), sizeof(lev_iface_t));
+    L0->views = calloc((size_t)(nIfaces > 0 ? nIfaces : 1), sizeof(iface_t));
+    for (int i = 0; i < nIfaces; i++) {
+        lev_iface_t* I = &L0->ifs[i];
+        const int32_t n = ifaceSizes[i];
+        I->n = n;
+        I->nbrPatch = ifaceNbrPatch[i];
+        I->faceCells = malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        I->nbrCells = malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        memcpy(I->faceCells, ifaceFaceCells[i], sizeof(int32_t) * (size_t)n);
+        memcpy(I->nbrCells, ifaceFaceCells[ifaceNbrPatch[i]], sizeof(int32_t) * (size_t)n);
+    }
     H->nLevels = 1;
     int forward = forwardStart;
     double* w = malloc(sizeof(double) * (size_t)(nFaces > 0 ? nFaces : 1));
@@ -534,6 +646,7 @@ hierarchy_t* oracle_gamg_build(int32_t nCells, int32_t nFaces, const int32_t* l,
         fine->restrictAddr = map;
         level_t* coarse = &H->lev[H->nLevels];
         agglomerate_addressing(fine, coarse, nCoarse);
+        agglomerate_interfaces(fine, coarse);
         double* cw = calloc((size_t)(coarse->nFaces > 0 ? coarse->nFaces : 1), sizeof(double));
         for (int f = 0; f < fine->nFaces; f++)              /* restrictFaceField */
             if (fine->faceRestrictAddr[f] >= 0) cw[fine->faceRestrictAddr[f]] += w[f];
@@ -561,9 +674,37 @@ void oracle_gamg_level_arrays(const hierarchy_t* H, int lev, int32_t* restrictAd
     memcpy(coarseUpper, c->u, sizeof(int32_t) * (size_t)c->nFaces);
 }
 
+/* coarse patch `iface` of level lev+1: its size, faceCells and the fine patch's faceRestrictAddressing */
+int oracle_gamg_iface_size(const hierarchy_t* H, int lev, int iface) { return H->lev[lev].ifs[iface].n; }
+void oracle_gamg_iface_arrays(const hierarchy_t* H, int lev, int iface, int32_t* coarseFaceCells,
+                              int32_t* faceRestrictAddr) {
+    const lev_iface_t* F = &H->lev[lev].ifs[iface];
+    const lev_iface_t* Cc = &H->lev[lev + 1].ifs[iface];
+    memcpy(coarseFaceCells, Cc->faceCells, sizeof(int32_t) * (size_t)Cc->n);
+    memcpy(faceRestrictAddr, F->faceRestrict, sizeof(int32_t) * (size_t)F->n);
+}
+
 static ldu_t as_ldu(const level_t* L) {
-    ldu_t A = {L->nCells, L->nFaces, L->l, L->u, L->diag, L->upper, L->lower};
+    for (int i = 0; i < L->nIfaces; i++) {
+        const lev_iface_t* I = &L->ifs[i];
+        iface_t v = {I->n, I->faceCells, I->nbrCells, I->bou, I->inn};
+        L->views[i] = v;
+    }
+    ldu_t A = {L->nCells, L->nFaces, L->l, L->u, L->diag, L->upper, L->lower, L->nIfaces, L->views};
     return A;
+}
+
+/* interfaceBouCoeffs / interfaceIntCoeffs of the finest level (copied); call before set_matrix / solve */
+void oracle_gamg_set_interface_coeffs(hierarchy_t* H, const double* const* bou, const double* const* inn) {
+    level_t* L0 = &H->lev[0];
+    for (int i = 0; i < L0->nIfaces; i++) {
+        lev_iface_t* I = &L0->ifs[i];
+        free(I->bou); free(I->inn);
+        I->bou = malloc(sizeof(double) * (size_t)(I->n > 0 ? I->n : 1));
+        I->inn = malloc(sizeof(double) * (size_t)(I->n > 0 ? I->n : 1));
+        memcpy(I->bou, bou[i], sizeof(double) * (size_t)I->n);
+        memcpy(I->inn, inn[i], sizeof(double) * (size_t)I->n);
+    }
 }
 
 /* agglomerateMatrix for all levels (GAMGSolver.C:196-208, GAMGSolverAgglomerateMatrix.C:33-193) */
@@ -585,6 +726,16 @@ static void gamg_set_matrix(hierarchy_t* H, const double* diag, const double* up
     if (!H->symmetric) memcpy(L0->lower, lower, sizeof(double) * (size_t)L0->nFaces);
     for (int k = 0; k + 1 < H->nLevels; k++) {
         level_t *F = &H->lev[k], *C = &H->lev[k + 1];
+        for (int i = 0; i < F->nIfaces; i++) {             /* agglomerateInterfaceCoefficients, GAMGSolverAgglomerateMatrix.C:196-275 */
+            lev_iface_t *fi = &F->ifs[i], *ci = &C->ifs[i];
+            free(ci->bou); free(ci->inn);
+            ci->bou = calloc((size_t)(ci->n > 0 ? ci->n : 1), sizeof(double));
+            ci->inn = calloc((size_t)(ci->n > 0 ? ci->n : 1), sizeof(double));
+            for (int e = 0; e < fi->n; e++) {
+                ci->bou[fi->faceRestrict[e]] += fi->bou[e];
+                ci->inn[fi->faceRestrict[e]] += fi->inn[e];
+            }
+        }
         restrict_field(C->diag, F->diag, F->restrictAddr, F->nCells, C->nCells);
         for (int f = 0; f < F->nFaces; f++) {
             const int cf = F->faceRestrictAddr[f];
@@ -741,6 +892,11 @@ void oracle_gamg_free(hierarchy_t* H) {
         if (L->lower && L->lower != L->upper) free(L->lower);
         free(L->l); free(L->u); free(L->diag); free(L->upper); free(L->restrictAddr); free(L->faceRestrictAddr);
         free(L->faceFlip); free(L->corr); free(L->src);
+        for (int i = 0; i < L->nIfaces; i++) {
+            lev_iface_t* I = &L->ifs[i];
+            free(I->faceCells); free(I->nbrCells); free(I->faceRestrict); free(I->bou); free(I->inn);
+        }
+        free(L->ifs); free(L->views);
     }
     free(H);
 }

@@ -11,9 +11,15 @@ PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2, "DILU": 3, "GaussSeidel": 4, "sy
             "DICGaussSeidel": 6, "DILUGaussSeidel": 7, "GAMG": 8}
 
 
+class Iface(C.Structure):
+    _fields_ = [("n", C.c_int32), ("faceCells", C.c_void_p), ("nbrCells", C.c_void_p), ("bou", C.c_void_p),
+                ("inn", C.c_void_p)]
+
+
 class Ldu(C.Structure):
     _fields_ = [("nCells", C.c_int32), ("nFaces", C.c_int32), ("l", C.c_void_p), ("u", C.c_void_p),
-                ("diag", C.c_void_p), ("upper", C.c_void_p), ("lower", C.c_void_p)]
+                ("diag", C.c_void_p), ("upper", C.c_void_p), ("lower", C.c_void_p), ("nIfaces", C.c_int32),
+                ("ifaces", C.c_void_p)]
 
 
 class Perf(C.Structure):
@@ -43,6 +49,12 @@ def lib():
         _lib.oracle_norm_factor.restype = C.c_double
         _lib.oracle_gamg_build.restype = C.c_void_p
         _lib.oracle_gamg_build.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        _lib.oracle_gamg_build_coupled.restype = C.c_void_p
+        _lib.oracle_gamg_build_coupled.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                   C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_gamg_set_interface_coeffs.argtypes = [C.c_void_p] * 3
+        _lib.oracle_gamg_iface_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib.oracle_gamg_iface_arrays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.oracle_gamg_n_levels.argtypes = [C.c_void_p]
         _lib.oracle_gamg_level_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.oracle_gamg_level_arrays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
@@ -68,8 +80,35 @@ class System:
         self.lower = self.upper if s.lower_coeffs is None else np.ascontiguousarray(s.lower_coeffs, dtype=np.float64)
         self.symmetric = s.lower_coeffs is None
         self.n = int(s.n_cells)
-        self.c = Ldu(self.n, self.l.size, _p(self.l), _p(self.u), _p(self.diag), _p(self.upper), _p(self.lower))
+        # cyclic (same-process) coupled patches; processor patches are emulated by tests/_emulated_ranks.py
+        ifs = list(getattr(s, "interfaces", []) or [])
+        if any(i.nbr_patch < 0 for i in ifs):
+            raise ValueError("the C oracle only takes cyclic interfaces")
+        self.n_ifaces = len(ifs)
+        self.nbr_patch = np.array([i.nbr_patch for i in ifs], dtype=np.int32)
+        self.if_sizes = np.array([i.face_cells.size for i in ifs], dtype=np.int32)
+        self.if_cells = [np.ascontiguousarray(i.face_cells, dtype=np.int32) for i in ifs]
+        self.if_bou = [np.ascontiguousarray(i.bou_coeffs, dtype=np.float64) for i in ifs]
+        self.if_int = [np.ascontiguousarray(i.int_coeffs, dtype=np.float64) for i in ifs]
+        self.if_views = (Iface * max(1, len(ifs)))()
+        for k in range(len(ifs)):
+            self.if_views[k] = Iface(self.if_cells[k].size, _p(self.if_cells[k]), _p(self.if_cells[ifs[k].nbr_patch]),
+                                     _p(self.if_bou[k]), _p(self.if_int[k]))
+        self.c = Ldu(self.n, self.l.size, _p(self.l), _p(self.u), _p(self.diag), _p(self.upper), _p(self.lower),
+                     len(ifs), C.cast(self.if_views, C.c_void_p))
         self.face_weights = s.face_weights
+
+    def _ptr_array(self, arrays):
+        return (C.c_void_p * max(1, len(arrays)))(*[a.ctypes.data for a in arrays])
+
+    def gamg_build(self, min_cells=10, forward_start=1):
+        """hierarchy_t* with the cyclic patches agglomerated and the finest-level interface coefficients set."""
+        H = lib().oracle_gamg_build_coupled(self.n, self.l.size, _p(self.l), _p(self.u),
+                                            _p(np.ascontiguousarray(self.face_weights)), min_cells, forward_start,
+                                            self.n_ifaces, _p(self.if_sizes), self._ptr_array(self.if_cells),
+                                            _p(self.nbr_patch))
+        lib().oracle_gamg_set_interface_coeffs(H, self._ptr_array(self.if_bou), self._ptr_array(self.if_int))
+        return H
 
 
 def controls(precond="DIC", tolerance=1e-6, relTol=0.0, maxIter=1000, minIter=0, nSweeps=1, nPreSweeps=0,
@@ -139,7 +178,7 @@ def solve(S, solver, ctl, source, psi0=None):
     x = np.zeros(S.n) if psi0 is None else np.ascontiguousarray(psi0, dtype=np.float64).copy()
     p = Perf()
     if solver == "GAMG":
-        H = lib().oracle_gamg_build(S.n, S.l.size, _p(S.l), _p(S.u), _p(np.ascontiguousarray(S.face_weights)), 10, 1)
+        H = S.gamg_build()
         try:
             lib().oracle_gamg_solve(H, _p(S.diag), _p(S.upper), None if S.symmetric else _p(S.lower), C.byref(ctl),
                                     _p(x), _p(b), C.byref(p))
@@ -150,8 +189,7 @@ def solve(S, solver, ctl, source, psi0=None):
               "smoothSolver": lib().oracle_smooth_solver}[solver]
         H = None
         if ctl.precond == PRECONDS["GAMG"]:     # preconditioner GAMG: build the hierarchy + coarse matrices first
-            H = lib().oracle_gamg_build(S.n, S.l.size, _p(S.l), _p(S.u), _p(np.ascontiguousarray(S.face_weights)),
-                                        10, 1)
+            H = S.gamg_build()
             lib().oracle_gamg_set_matrix(H, _p(S.diag), _p(S.upper), None if S.symmetric else _p(S.lower))
             ctl.hierarchy = H
         try:
@@ -165,8 +203,7 @@ def solve(S, solver, ctl, source, psi0=None):
 
 def agglomeration(S, min_cells=10, forward_start=1):
     """Per level: (restrictAddressing, faceRestrictAddressing, faceFlipMap, coarseLower, coarseUpper)."""
-    H = lib().oracle_gamg_build(S.n, S.l.size, _p(S.l), _p(S.u), _p(np.ascontiguousarray(S.face_weights)),
-                                min_cells, forward_start)
+    H = S.gamg_build(min_cells, forward_start)
     out = []
     try:
         n_levels = lib().oracle_gamg_n_levels(H)
@@ -181,6 +218,24 @@ def agglomeration(S, min_cells=10, forward_start=1):
             cu = np.empty(nfc.value, dtype=np.int32)
             lib().oracle_gamg_level_arrays(H, k, _p(ra), _p(fra), _p(ff), _p(cl), _p(cu))
             out.append((ra, fra, ff, cl, cu))
+    finally:
+        lib().oracle_gamg_free(H)
+    return out
+
+
+def interface_agglomeration(S, min_cells=10, forward_start=1):
+    """Per level, per cyclic patch: (coarse faceCells, faceRestrictAddressing of the fine patch)."""
+    H = S.gamg_build(min_cells, forward_start)
+    out = []
+    try:
+        for k in range(lib().oracle_gamg_n_levels(H) - 1):
+            lev = []
+            for i in range(S.n_ifaces):
+                fc = np.empty(lib().oracle_gamg_iface_size(H, k + 1, i), dtype=np.int32)
+                fra = np.empty(lib().oracle_gamg_iface_size(H, k, i), dtype=np.int32)
+                lib().oracle_gamg_iface_arrays(H, k, i, _p(fc), _p(fra))
+                lev.append((fc, fra))
+            out.append(lev)
     finally:
         lib().oracle_gamg_free(H)
     return out

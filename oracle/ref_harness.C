@@ -18,6 +18,13 @@
       src/finiteVolume/.../faceAreaPairGAMGAgglomeration.C:55-108 does, but taking the
       face weights from the case file instead of an fvMesh.
 
+    * optional cyclic (same-process) coupled patches: the fine-level lduInterface /
+      lduInterfaceField pair is supplied here (harnessCyclicInterface[Field], the
+      lduPrimitiveMesh analogue of finiteVolume's cyclicFvPatch / cyclicFvPatchField.C:150-174);
+      every coarse level then uses the reference's own cyclicGAMGInterface[Field], and all
+      callers (Amul/residual/sumA/smoothers/solvers/GAMG) are the reference's.  This is the
+      serial pin for the interface code that processor patches share.
+
   One mesh per process: pairGAMGAgglomeration::forward_ is a process-global static.
 
   File formats are documented in openfoam-dev_b200/ldu_io.py.
@@ -28,6 +35,10 @@
 #include "lduMatrix.H"
 #include "pairGAMGAgglomeration.H"
 #include "GAMGAgglomeration.H"
+#include "GAMGInterface.H"
+#include "cyclicLduInterface.H"
+#include "cyclicLduInterfaceField.H"
+#include "lduInterfaceField.H"
 #include "DICPreconditioner.H"
 #include "DILUPreconditioner.H"
 #include "addToRunTimeSelectionTable.H"
@@ -83,6 +94,139 @@ public:
     }
 };
 
+
+
+//- Fine-level cyclic coupled patch on an lduPrimitiveMesh (the role cyclicFvPatch plays on an fvMesh):
+//  face i of this patch is coupled to face i of patch nbrIndex_ of the same mesh.
+class harnessCyclicInterface
+:
+    public lduInterface,
+    public cyclicLduInterface
+{
+    const label index_;
+    const label nbrIndex_;
+    const labelList faceCells_;
+    const UPtrList<harnessCyclicInterface>& all_;
+    const transformer transform_;
+
+public:
+
+    TypeName("cyclic");
+
+    harnessCyclicInterface
+    (
+        const label index,
+        const label nbrIndex,
+        const labelList& faceCells,
+        const UPtrList<harnessCyclicInterface>& all
+    )
+    :
+        index_(index),
+        nbrIndex_(nbrIndex),
+        faceCells_(faceCells),
+        all_(all),
+        transform_()
+    {}
+
+    virtual const labelUList& faceCells() const
+    {
+        return faceCells_;
+    }
+
+    virtual tmp<labelField> interfaceInternalField(const labelUList& iF) const
+    {
+        tmp<labelField> t(new labelField(faceCells_.size()));
+        labelField& f = t.ref();
+        forAll(f, i)
+        {
+            f[i] = iF[faceCells_[i]];
+        }
+        return t;
+    }
+
+    virtual tmp<labelField> internalFieldTransfer
+    (
+        const Pstream::commsTypes,
+        const labelUList& iF
+    ) const
+    {
+        return all_[nbrIndex_].interfaceInternalField(iF);
+    }
+
+    virtual label nbrPatchIndex() const
+    {
+        return nbrIndex_;
+    }
+
+    virtual bool owner() const
+    {
+        return index_ < nbrIndex_;
+    }
+
+    virtual const cyclicLduInterface& nbrPatch() const
+    {
+        return all_[nbrIndex_];
+    }
+
+    virtual const transformer& transform() const
+    {
+        return transform_;
+    }
+};
+
+defineTypeName(harnessCyclicInterface);
+
+
+//- Fine-level cyclic interface field, scalar (rank 0, no transformation)
+class harnessCyclicInterfaceField
+:
+    public lduInterfaceField,
+    public cyclicLduInterfaceField
+{
+    const harnessCyclicInterface& patch_;
+
+public:
+
+    TypeName("cyclic");
+
+    harnessCyclicInterfaceField(const harnessCyclicInterface& p)
+    :
+        lduInterfaceField(p),
+        patch_(p)
+    {}
+
+    virtual const transformer& transform() const
+    {
+        return patch_.transform();
+    }
+
+    virtual int rank() const
+    {
+        return 0;
+    }
+
+    virtual void updateInterfaceMatrix
+    (
+        scalarField& result,
+        const scalarField& psiInternal,
+        const scalarField& coeffs,
+        const direction,
+        const Pstream::commsTypes
+    ) const
+    {
+        const labelUList& nbrFaceCells =
+            dynamic_cast<const harnessCyclicInterface&>(patch_.nbrPatch())
+           .faceCells();
+        const labelUList& faceCells = patch_.faceCells();
+        scalarField pnf(psiInternal, nbrFaceCells);
+        forAll(faceCells, i)
+        {
+            result[faceCells[i]] -= coeffs[i]*pnf[i];
+        }
+    }
+};
+
+defineTypeName(harnessCyclicInterfaceField);
 
 //- faceAreaPair restated on pairGAMGAgglomeration with file-supplied weights
 class harnessFaceAreaPairAgglomeration
@@ -349,8 +493,38 @@ int main(int argc, char* argv[])
     }
 
     harnessLduMesh mesh(runTime, nCells, l, u);
-    lduInterfacePtrsList noInterfaces(0);
-    mesh.addInterfaces(noInterfaces, lduSchedule());
+    // cyclic coupled patches: "nIfaces", "iface.<i>.{faceCells,nbrPatch,bouCoeffs,intCoeffs}"
+    const label nIfaces = has(in, "nIfaces") ? i32(in, "nIfaces")[0] : 0;
+    // owned by the mesh once added (lduPrimitiveMesh::addInterfaces, lduPrimitiveMesh.C:219-237)
+    UPtrList<harnessCyclicInterface> cyclicPatches(nIfaces);
+    PtrList<harnessCyclicInterfaceField> cyclicFields(nIfaces);
+    lduInterfacePtrsList meshInterfaces(nIfaces);
+    lduInterfaceFieldPtrsList ifaceFields(nIfaces);
+    Field<Field<scalar>> bouCoeffs(nIfaces), intCoeffs(nIfaces);
+    for (label i = 0; i < nIfaces; i++)
+    {
+        const std::string k = "iface." + std::to_string(i);
+        const label n = in.at(k + ".faceCells").count;
+        labelList fc(n);
+        for (label j = 0; j < n; j++)
+        {
+            fc[j] = i32(in, k + ".faceCells")[j];
+        }
+        cyclicPatches.set
+        (
+            i,
+            new harnessCyclicInterface
+            (
+                i, i32(in, k + ".nbrPatch")[0], fc, cyclicPatches
+            )
+        );
+        meshInterfaces.set(i, &cyclicPatches[i]);
+        cyclicFields.set(i, new harnessCyclicInterfaceField(cyclicPatches[i]));
+        ifaceFields.set(i, &cyclicFields[i]);
+        bouCoeffs[i] = toField(in, k + ".bouCoeffs");
+        intCoeffs[i] = toField(in, k + ".intCoeffs");
+    }
+    mesh.addInterfaces(meshInterfaces, lduSchedule());
 
     // --- integer addressing -------------------------------------------------
     putI32(out, "losort", mesh.lduAddr().losortAddr());
@@ -368,25 +542,23 @@ int main(int argc, char* argv[])
         }
     }
 
-    const Field<Field<scalar>> noCoeffs(0);
-    const lduInterfaceFieldPtrsList noIfaces(0);
 
     // --- operators ------------------------------------------------------------
     if (has(in, "x"))
     {
         const scalarField x(toField(in, "x"));
         scalarField Ax(nCells);
-        A.Amul(Ax, x, noCoeffs, noIfaces, 0);
+        A.Amul(Ax, x, bouCoeffs, ifaceFields, 0);
         putF64(out, "Amul", Ax);
 
         scalarField sA(nCells);
-        A.sumA(sA, noCoeffs, noIfaces);
+        A.sumA(sA, bouCoeffs, ifaceFields);
         putF64(out, "sumA", sA);
 
         if (has(in, "source"))
         {
             scalarField rA(nCells);
-            A.residual(rA, x, toField(in, "source"), noCoeffs, noIfaces, 0);
+            A.residual(rA, x, toField(in, "source"), bouCoeffs, ifaceFields, 0);
             putF64(out, "residual", rA);
         }
 
@@ -414,7 +586,7 @@ int main(int argc, char* argv[])
             dictionary d(is);
             autoPtr<lduMatrix::solver> sol = lduMatrix::solver::New
             (
-                "p", A, noCoeffs, noCoeffs, noIfaces, d
+                "p", A, bouCoeffs, intCoeffs, ifaceFields, d
             );
             autoPtr<lduMatrix::preconditioner> pre =
                 lduMatrix::preconditioner::New(sol(), d);
@@ -435,7 +607,7 @@ int main(int argc, char* argv[])
         dictionary d(is);
         autoPtr<lduMatrix::smoother> sm = lduMatrix::smoother::New
         (
-            "p", A, noCoeffs, noCoeffs, noIfaces, d
+            "p", A, bouCoeffs, intCoeffs, ifaceFields, d
         );
         scalarField psi(toField(in, "x"));
         const scalarField b(toField(in, "source"));
@@ -464,7 +636,7 @@ int main(int argc, char* argv[])
         clockTime timer;
         solverPerformance perf = lduMatrix::solver::New
         (
-            "p", A, noCoeffs, noCoeffs, noIfaces, d
+            "p", A, bouCoeffs, intCoeffs, ifaceFields, d
         )->solve(psi, b);
         const double secs = timer.elapsedTime();
 
@@ -499,7 +671,7 @@ int main(int argc, char* argv[])
                 scalarField psik(psi0);
                 solverPerformance pk = lduMatrix::solver::New
                 (
-                    "p", A, noCoeffs, noCoeffs, noIfaces, dk
+                    "p", A, bouCoeffs, intCoeffs, ifaceFields, dk
                 )->solve(psik, b);
                 hist.push_back(pk.finalResidual());
             }
@@ -535,6 +707,21 @@ int main(int argc, char* argv[])
             const lduAddressing& ca = agg.meshLevel(lev + 1).lduAddr();
             putI32(out, k + ".coarseLower", ca.lowerAddr());
             putI32(out, k + ".coarseUpper", ca.upperAddr());
+
+            const lduInterfacePtrsList ci(agg.meshLevel(lev + 1).interfaces());
+            forAll(ci, pi)
+            {
+                if (!ci.set(pi)) continue;
+                const GAMGInterface& gi = refCast<const GAMGInterface>(ci[pi]);
+                const std::string ki = k + ".iface." + std::to_string(pi);
+                putI32(out, ki + ".faceCells", gi.faceCells());
+                putI32
+                (
+                    out,
+                    ki + ".faceRestrictAddressing",
+                    gi.faceRestrictAddressing()
+                );
+            }
         }
     }
 

@@ -6,6 +6,8 @@ contributions are applied after the face loop in patch order, and rank sums are 
 import sys
 from pathlib import Path
 
+import dataclasses
+
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
@@ -31,7 +33,8 @@ def amul(parts, S, fields):
 
 
 def pcg(parts, kind="DIC", tolerance=1e-6, rel_tol=0.0, max_iter=1000):
-    S = [orc.System(p) for p in parts]
+    # rank-local operators only: the processor-patch terms are added by _amul below
+    S = [orc.System(dataclasses.replace(p, interfaces=[])) for p in parts]
     n_tot = sum(p.n_cells for p in parts)
     psi = [np.zeros(p.n_cells) for p in parts]
     src = [p.source for p in parts]

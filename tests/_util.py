@@ -24,6 +24,12 @@ def system_from_entries(inp):
         n_cells=int(inp["nCells"][0]), lower=inp["lower"], upper=inp["upper"], diag=inp["diag"],
         upper_coeffs=inp["upperCoeffs"], lower_coeffs=inp.get("lowerCoeffs"), source=inp.get("source"),
         face_weights=inp.get("faceWeights"),
+        interfaces=[
+            cases.Interface(neighb_rank=-1, face_cells=inp[f"iface.{k}.faceCells"],
+                            bou_coeffs=inp[f"iface.{k}.bouCoeffs"], int_coeffs=inp[f"iface.{k}.intCoeffs"],
+                            nbr_patch=int(inp[f"iface.{k}.nbrPatch"][0]))
+            for k in range(int(inp["nIfaces"][0]) if "nIfaces" in inp else 0)
+        ],
     )
 
 

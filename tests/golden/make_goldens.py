@@ -110,6 +110,16 @@ def main():
     fixture("random_graph_asym_500", cases.random_graph(500, symmetric=False, seed=7), ASYM_SOLVES, asym_sm)
     fixture("convdiff_24x18x1", cases.convection_diffusion(24, 18, 1, dt_coeff=50.0), ASYM_SOLVES, asym_sm)
     fixture("convdiff_9x8x7", cases.convection_diffusion(9, 8, 7, dt_coeff=50.0, rhs_kind="uniform"), ASYM_SOLVES, asym_sm)
+    # cyclic (periodic) patch pairs: the serial pin of the coupled-interface code that processor patches share
+    # (interface terms of Amul/residual/sumA/smoothers, cyclicGAMGInterface agglomeration, coarse interface
+    # coefficients, coarsest-level solve with interfaces)
+    fixture("cyclic_x_12x10x8_rand", cases.add_cyclic(cases.cavity_laplacian(12, 10, 8, coeffs="random"), 0),
+            SYM_SOLVES, sym_sm)
+    fixture("cyclic_xz_9x8x7_rand",
+            cases.add_cyclic(cases.add_cyclic(cases.cavity_laplacian(9, 8, 7, coeffs="random", rhs_kind="uniform"), 0), 2),
+            SYM_SOLVES, sym_sm)
+    fixture("cyclic_y_convdiff_10x9x6", cases.add_cyclic(cases.convection_diffusion(10, 9, 6, dt_coeff=50.0), 1),
+            ASYM_SOLVES, asym_sm)
 
 
 if __name__ == "__main__":

@@ -53,6 +53,11 @@ def test_agglomeration(fx):
         assert np.array_equal(fra, ref[p + "faceRestrictAddressing"])
         assert np.array_equal(ff, ref[p + "faceFlipMap"].astype(np.int32))
         assert np.array_equal(cl, ref[p + "coarseLower"]) and np.array_equal(cu, ref[p + "coarseUpper"])
+    # coarse cyclic patches (cyclicGAMGInterface): faceCells + faceRestrictAddressing of every level
+    for k, lev in enumerate(orc.interface_agglomeration(S)):
+        for i, (fc, fra) in enumerate(lev):
+            assert np.array_equal(fc, ref[f"agg.{k}.iface.{i}.faceCells"]), (name, k, i)
+            assert np.array_equal(fra, ref[f"agg.{k}.iface.{i}.faceRestrictAddressing"]), (name, k, i)
 
 
 def test_solvers_bit_exact(fx):
