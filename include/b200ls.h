@@ -64,8 +64,13 @@ int b200ls_set_host_comm(int32_t rank, int32_t nRanks, b200ls_exchange_fn exchan
 /* ---- mesh (cached per lduAddressing by the caller) ---------------------------------------------- */
 
 /* Host analysis only (no device work): losort/ownerStart/losortStart, forward/backward wavefronts,
- * wavefront-major permutation and the native row layout.  Interfaces: one entry per COUPLED patch
- * (processor patches), in patch order. */
+ * wavefront-major permutation and the native row layout.  Interfaces: one entry per COUPLED patch, in patch order.
+ * ifaceNeighbRank[i] >= 0: processor patch to that rank (processorLduInterface::neighbProcNo()).
+ * ifaceNeighbRank[i] <  0: one half of a cyclic pair on this rank (lduAddressing/lduInterface/cyclicLduInterface.H):
+ *   the value is B200LS_CYCLIC(p) = -(1 + p), p = cyclicLduInterface::nbrPatchIndex() counted among the coupled
+ *   patches passed here; face e of patch i is coupled to face e of patch p, and the half with the lower index is the
+ *   owner.  Scalar (rank-0, untransformed) coupling only. */
+#define B200LS_CYCLIC(partnerPatch) (-(1 + (partnerPatch)))
 b200ls_mesh_t b200ls_mesh_create(int32_t nCells, int32_t nFaces,
                                  const int32_t* lower, const int32_t* upper,
                                  int32_t nInterfaces, const int32_t* ifaceSizes,

@@ -184,7 +184,9 @@ class Mesh:
         self.interfaces = list(interfaces)
         n_if = len(self.interfaces)
         sizes = _i32([len(i.face_cells) for i in self.interfaces])
-        nbr = _i32([i.neighb_rank for i in self.interfaces])
+        # cyclic halves are passed as B200LS_CYCLIC(partner) = -(1 + partner)
+        nbr = _i32([-(1 + i.nbr_patch) if getattr(i, "nbr_patch", -1) >= 0 else i.neighb_rank
+                    for i in self.interfaces])
         self._fc = [_i32(i.face_cells) for i in self.interfaces]
         fc_ptrs = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in self._fc])
         self.h = lib().b200ls_mesh_create(self.n_cells, self.lower.size, _ptr(self.lower), _ptr(self.upper),

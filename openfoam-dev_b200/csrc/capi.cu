@@ -279,8 +279,18 @@ b200ls_mesh_t b200ls_mesh_create(int32_t nCells, int32_t nFaces, const int32_t* 
     int rc = guarded([&] {
         std::vector<HostInterface> ifs(nInterfaces);
         for (int i = 0; i < nInterfaces; i++) {
-            ifs[i].neighbRank = ifaceNeighbRank[i];
             ifs[i].faceCells.assign(ifaceFaceCells[i], ifaceFaceCells[i] + ifaceSizes[i]);
+            if (ifaceNeighbRank[i] >= 0) {
+                ifs[i].neighbRank = ifaceNeighbRank[i];
+            } else {
+                // cyclic half: -(1 + partner patch)
+                const int partner = -1 - ifaceNeighbRank[i];
+                if (partner >= nInterfaces || partner == i || ifaceNeighbRank[partner] != -1 - i)
+                    throw CudaError("cyclic patch " + std::to_string(i) + ": partner patch does not point back");
+                if (ifaceSizes[partner] != ifaceSizes[i])
+                    throw CudaError("cyclic patch " + std::to_string(i) + ": partner patch has a different size");
+                ifs[i].partner = partner;
+            }
         }
         std::unique_ptr<b200ls_mesh_s> m(new b200ls_mesh_s);
         m->host.levels.resize(1);

@@ -139,6 +139,8 @@ struct DevLevel {
     // interfaces
     int nIfaces = 0;
     std::vector<int> ifaceSize, ifaceNbr;
+    std::vector<int> ifacePartner;      // >= 0: cyclic half coupled to that patch of this rank; -1: processor patch
+    bool anyProcIface = false;
     std::vector<DevBuf<int>> ifaceCellsPos;
     DevBuf<int> bRowPos, bRowPtr, bEntIface, bEntFace;
     int nBRows = 0;

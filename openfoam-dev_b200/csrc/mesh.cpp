@@ -411,39 +411,66 @@ static void agglomerateInterfaces(LevelHost& fine, std::vector<HostInterface>& c
     fine.patchFaceRestrictAddr.assign(nI, {});
     coarseIfaces.assign(nI, {});
     if (nI == 0) return;
-    if (!comm || !comm->exchange) throw std::runtime_error("agglomerating processor interfaces needs a communicator");
-    std::vector<int32_t> nbr(nI);
-    std::vector<std::vector<int32_t>> send(nI), recv(nI);
+    // interfaceInternalField(restrictMap) of every patch; the neighbour's values come from the partner patch for a
+    // cyclic pair (cyclicGAMGInterface::internalFieldTransfer, cyclicGAMGInterface.C:180-197) and over the
+    // communicator for processor patches (processorGAMGInterface.C:195-214)
+    std::vector<std::vector<int32_t>> local(nI), remote(nI);
     for (size_t i = 0; i < nI; i++) {
         const auto& fc = fine.interfaces[i].faceCells;
-        nbr[i] = fine.interfaces[i].neighbRank;
-        send[i].resize(fc.size());
-        for (size_t k = 0; k < fc.size(); k++) send[i][k] = fine.restrictAddr[fc[k]];   // interfaceInternalField
-        recv[i].assign(fc.size(), -1);
+        local[i].resize(fc.size());
+        for (size_t k = 0; k < fc.size(); k++) local[i][k] = fine.restrictAddr[fc[k]];
     }
-    comm->exchange(nbr, send, recv);
+    std::vector<int32_t> procIdx, nbr;
     for (size_t i = 0; i < nI; i++) {
-        const bool master = myRank < nbr[i];
+        const int32_t partner = fine.interfaces[i].partner;
+        if (partner >= 0) {
+            remote[i] = local[size_t(partner)];
+        } else {
+            procIdx.push_back(int32_t(i));
+            nbr.push_back(fine.interfaces[i].neighbRank);
+        }
+    }
+    if (!procIdx.empty()) {
+        if (!comm || !comm->exchange) throw std::runtime_error("agglomerating processor interfaces needs a communicator");
+        std::vector<std::vector<int32_t>> send(procIdx.size()), recv(procIdx.size());
+        for (size_t j = 0; j < procIdx.size(); j++) {
+            send[j] = local[size_t(procIdx[j])];
+            recv[j].assign(send[j].size(), -1);
+        }
+        comm->exchange(nbr, send, recv);
+        for (size_t j = 0; j < procIdx.size(); j++) remote[size_t(procIdx[j])] = std::move(recv[j]);
+    }
+    // coarse patch faces = distinct (master coarse cell, slave coarse cell) pairs in first-seen order
+    // (processorGAMGInterface.C:75-147, cyclicGAMGInterface.C:85-157)
+    for (size_t i = 0; i < nI; i++) {
+        const HostInterface& fi = fine.interfaces[i];
+        const bool master = fi.partner >= 0 ? int32_t(i) < fi.partner : myRank < fi.neighbRank;
         std::unordered_map<uint64_t, int32_t> seen;
-        seen.reserve(send[i].size() * 2);
+        seen.reserve(local[i].size() * 2);
         HostInterface& ci = coarseIfaces[i];
-        ci.neighbRank = nbr[i];
+        ci.neighbRank = fi.neighbRank;
+        ci.partner = fi.partner;
         auto& pr = fine.patchFaceRestrictAddr[i];
-        pr.resize(send[i].size());
-        for (size_t k = 0; k < send[i].size(); k++) {
-            const uint32_t a = uint32_t(master ? send[i][k] : recv[i][k]);
-            const uint32_t b = uint32_t(master ? recv[i][k] : send[i][k]);
+        pr.resize(local[i].size());
+        for (size_t k = 0; k < local[i].size(); k++) {
+            const uint32_t a = uint32_t(master ? local[i][k] : remote[i][k]);
+            const uint32_t b = uint32_t(master ? remote[i][k] : local[i][k]);
             const uint64_t key = (uint64_t(a) << 32) | b;
             auto it = seen.find(key);
             if (it == seen.end()) {
                 const int32_t cf = int32_t(ci.faceCells.size());
                 seen.emplace(key, cf);
-                ci.faceCells.push_back(send[i][k]);
+                ci.faceCells.push_back(local[i][k]);
                 pr[k] = cf;
             } else {
                 pr[k] = it->second;
             }
         }
+    }
+    for (size_t i = 0; i < nI; i++) {
+        const int32_t partner = coarseIfaces[i].partner;
+        if (partner >= 0 && coarseIfaces[size_t(partner)].faceCells.size() != coarseIfaces[i].faceCells.size())
+            throw std::runtime_error("cyclic halves agglomerated to different sizes");
     }
 }
 

@@ -12,8 +12,12 @@
 
 namespace b200ls {
 
+// One coupled patch.  partner < 0: processor patch to rank neighbRank (processorLduInterface).  partner >= 0: one half
+// of a cyclic pair on this rank (cyclicLduInterface): face i is coupled to face i of patch `partner`; the half with
+// the lower patch index is the owner (cyclicLduInterface::owner()).
 struct HostInterface {
     int32_t neighbRank = -1;
+    int32_t partner = -1;
     std::vector<int32_t> faceCells;      // reference cell index of each patch face
 };
 

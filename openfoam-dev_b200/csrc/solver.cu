@@ -187,12 +187,16 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
     D.nIfaces = int(H.interfaces.size());
     D.ifaceSize.clear();
     D.ifaceNbr.clear();
+    D.ifacePartner.clear();
+    D.anyProcIface = false;
     D.ifaceCellsPos.clear();
     D.ifaceCellsPos.resize(D.nIfaces);
     for (int i = 0; i < D.nIfaces; i++) {
         const auto& fc = H.interfaces[i].faceCells;
         D.ifaceSize.push_back(int(fc.size()));
         D.ifaceNbr.push_back(H.interfaces[i].neighbRank);
+        D.ifacePartner.push_back(H.interfaces[i].partner);
+        D.anyProcIface = D.anyProcIface || H.interfaces[i].partner < 0;
         std::vector<int32_t> pos(fc.size());
         for (size_t k = 0; k < fc.size(); k++) pos[k] = H.ipos[fc[k]];
         D.ifaceCellsPos[i].upload(pos, s);
@@ -295,17 +299,22 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     Context& c = ctx();
-    if (M.p2pReady || !c.p2p.enabled || D.nIfaces == 0) return;
+    if (M.p2pReady || !c.p2p.enabled || !D.anyProcIface) return;
     static const bool off = getenv("B200LS_NO_P2P_HALO") != nullptr;
     if (off) return;
+    auto isProc = [&](int i) { return D.ifacePartner[i] < 0; };   // cyclic halves never leave this GPU
     for (int i = 0; i < D.nIfaces; i++)
         for (int j = 0; j < i; j++)
-            if (D.ifaceNbr[i] == D.ifaceNbr[j]) return;   // several patches to one neighbour: keep NCCL
+            if (isProc(i) && isProc(j) && D.ifaceNbr[i] == D.ifaceNbr[j]) return;   // several patches to one neighbour: keep NCCL
     std::vector<long long> mine(2 * D.nIfaces), theirs(2 * D.nIfaces, -1);
     M.p2pLocalRecv.assign(D.nIfaces, nullptr);
     M.p2pLocalFlag.assign(D.nIfaces, nullptr);
     bool ok = true;
     for (int i = 0; i < D.nIfaces; i++) {
+        if (!isProc(i)) {
+            mine[2 * i] = mine[2 * i + 1] = theirs[2 * i] = theirs[2 * i + 1] = 0;
+            continue;
+        }
         char* r = arenaAlloc(size_t(2) * std::max(D.ifaceSize[i], 1) * sizeof(double));
         char* f = arenaAlloc(sizeof(unsigned long long));
         if (!r || !f) ok = false;
@@ -321,12 +330,18 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     B2_CUDA(cudaStreamSynchronize(c.stream));
     c.nccl.GroupStart();
     for (int i = 0; i < D.nIfaces; i++) {
+        if (!isProc(i)) continue;
         c.nccl.Send(dMine.p + 2 * i, 2, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
         c.nccl.Recv(dTheirs.p + 2 * i, 2, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
     }
     if (c.nccl.GroupEnd() != 0) throw CudaError("nccl exchange of P2P halo offsets failed");
-    B2_CUDA(cudaMemcpyAsync(theirs.data(), dTheirs.p, sizeof(long long) * theirs.size(), cudaMemcpyDeviceToHost, c.stream));
-    B2_CUDA(cudaStreamSynchronize(c.stream));
+    {
+        std::vector<long long> got(theirs.size());
+        B2_CUDA(cudaMemcpyAsync(got.data(), dTheirs.p, sizeof(long long) * got.size(), cudaMemcpyDeviceToHost, c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        for (int i = 0; i < D.nIfaces; i++)
+            if (isProc(i)) { theirs[2 * i] = got[2 * i]; theirs[2 * i + 1] = got[2 * i + 1]; }
+    }
     for (long long v : theirs) ok = ok && v >= 0;
     // every rank must take the same decision for a given interface pair; a global AND keeps it simple
     DevBuf<double> flag;
@@ -342,6 +357,7 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     M.p2pRemoteRecv.resize(D.nIfaces);
     M.p2pRemoteFlag.resize(D.nIfaces);
     for (int i = 0; i < D.nIfaces; i++) {
+        if (!isProc(i)) { M.p2pRemoteRecv[i] = nullptr; M.p2pRemoteFlag[i] = nullptr; continue; }
         char* base = c.p2p.view.peer[D.ifaceNbr[i]];
         M.p2pRemoteRecv[i] = reinterpret_cast<double*>(base + theirs[2 * i]);
         M.p2pRemoteFlag[i] = reinterpret_cast<unsigned long long*>(base + theirs[2 * i + 1]);
@@ -361,9 +377,18 @@ static void setupIfaceViews(b200ls_matrix_s* m, int level) {
     for (int i = 0; i < D.nIfaces; i++) {
         M.sendBuf[i].alloc(D.ifaceSize[i]);
         M.recvBuf[i].alloc(D.ifaceSize[i]);
+    }
+    for (int i = 0; i < D.nIfaces; i++) {
         v[i].coeffs = M.bou[i].p;
-        v[i].recv = M.p2pReady ? M.p2pLocalRecv[i] : M.recvBuf[i].p;
-        v[i].flag = M.p2pReady ? M.p2pLocalFlag[i] : nullptr;
+        if (D.ifacePartner[i] >= 0) {
+            // cyclic half: the neighbour values are the partner patch's packed boundary cells, same GPU, same stream
+            // (cyclicGAMGInterfaceField.C:124-146: pnf = nbrPatch().interfaceInternalField(psi))
+            v[i].recv = M.sendBuf[D.ifacePartner[i]].p;
+            v[i].flag = nullptr;
+        } else {
+            v[i].recv = M.p2pReady ? M.p2pLocalRecv[i] : M.recvBuf[i].p;
+            v[i].flag = M.p2pReady ? M.p2pLocalFlag[i] : nullptr;
+        }
         v[i].size = D.ifaceSize[i];
     }
     M.ifaceViews.alloc(v.size() * sizeof(IfaceView));
@@ -427,12 +452,17 @@ static void haloExchange(b200ls_matrix_s* m, int level, const double* psi) {
     MatLevel& M = m->levels[level];
     Context& c = ctx();
     if (D.nIfaces == 0) return;
-    if (c.nRanks == 1) throw CudaError("matrix has processor interfaces but b200ls_init was called with nRanks=1");
+    if (D.anyProcIface && c.nRanks == 1)
+        throw CudaError("matrix has processor interfaces but b200ls_init was called with nRanks=1");
     if (M.p2pReady) {
         // remote stores into the neighbours' receive buffers + release of the epoch flag, from our own kernel
         const unsigned long long epoch = ++M.haloEpoch;
         for (int i = 0; i < D.nIfaces; i++) {
             const int n = D.ifaceSize[i];
+            if (D.ifacePartner[i] >= 0) {
+                if (n) LAUNCH(k_iface_pack, gridRows(n), 256, M.sendBuf[i].p, psi, D.ifaceCellsPos[i].p, n);
+                continue;
+            }
             LAUNCH(k_iface_pack_p2p, gridRows(std::max(n, 1)), 256, M.p2pRemoteRecv[i] + (epoch & 1) * n, psi,
                    D.ifaceCellsPos[i].p, n, M.p2pTickets.p + i, M.p2pRemoteFlag[i], epoch);
         }
@@ -443,8 +473,10 @@ static void haloExchange(b200ls_matrix_s* m, int level, const double* psi) {
             LAUNCH(k_iface_pack, gridRows(D.ifaceSize[i]), 256, M.sendBuf[i].p, psi, D.ifaceCellsPos[i].p,
                    D.ifaceSize[i]);
     }
+    if (!D.anyProcIface) return;
     c.nccl.GroupStart();
     for (int i = 0; i < D.nIfaces; i++) {
+        if (D.ifacePartner[i] >= 0) continue;
         c.nccl.Send(M.sendBuf[i].p, D.ifaceSize[i], ncclDouble, D.ifaceNbr[i], c.comm, c.stream);
         c.nccl.Recv(M.recvBuf[i].p, D.ifaceSize[i], ncclDouble, D.ifaceNbr[i], c.comm, c.stream);
     }
@@ -796,12 +828,15 @@ enum {
     S_NUM = 13, S_DEN = 14, S_SINGULAR = 15, S_COUNT = 32
 };
 
+// Two banks: the coarsest-level Krylov solve nested inside a V-cycle (bank 1) must not clobber the scalars the
+// enclosing solver keeps on the device across its iterations (e.g. PCG's previous wArA when GAMG is its preconditioner).
+static int g_scalarBank = 0;
 static double* scalar(b200ls_matrix_s* m, int i) {
-    if (m->scalars.n != S_COUNT) {
-        m->scalars.alloc(S_COUNT);
-        B2_CUDA(cudaMemsetAsync(m->scalars.p, 0, S_COUNT * sizeof(double), S()));
+    if (m->scalars.n != 2 * S_COUNT) {
+        m->scalars.alloc(2 * S_COUNT);
+        B2_CUDA(cudaMemsetAsync(m->scalars.p, 0, 2 * S_COUNT * sizeof(double), S()));
     }
-    return m->scalars.p + i;
+    return m->scalars.p + g_scalarBank * S_COUNT + i;
 }
 
 // normFactor (lduMatrixSolver.C:174-197). tmp is clobbered.
@@ -994,7 +1029,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
                 perf->singular = 1;
                 break;
             }
-            LAUNCH(k_bicg_update_p, gridStride(n), 256, pA, rA, AyA, m->scalars.p, cur, old, S_ALPHA, S_OMEGA,
+            LAUNCH(k_bicg_update_p, gridStride(n), 256, pA, rA, AyA, scalar(m, 0), cur, old, S_ALPHA, S_OMEGA,
                    perf->nIterations == 0 ? 1 : 0, n);
             applyPrecond(m, c, lv, yA, pA);
             opAmul(m, lv, AyA, yA);
@@ -1331,8 +1366,13 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
     const int k = int(m->levels.size()) - 1;
     DevLevel& D = DL(m, k);
     MatLevel& M = m->levels[k];
-    if (ctx().nRanks > 1) {
-        // distributed coarsest level: the regular PCG+DIC / PBiCGStab+DILU on that level with the parent's
+    if (ctx().nRanks == 1 && D.nIfaces > 0 && D.nFaces == 0) {
+        // lduMatrix::diagonal() -> diagonalSolver, which ignores the interfaces (GAMGSolver.C:271-284, diagonalSolver.C:66)
+        LAUNCH(k_div, gridStride(D.nCells), 256, M.corr.p, M.src.p, M.diag.p, D.nCells);
+        return;
+    }
+    if (ctx().nRanks > 1 || D.nIfaces > 0) {
+        // coarsest level with coupled patches (distributed, or cyclic on one rank): the regular PCG+DIC / PBiCGStab+DILU on that level with the parent's
         // tolerance and relTol, zero initial guess (GAMGSolver.C:286-319, GAMGSolverSolve.C:538-545)
         b200ls_controls cc;
         memset(&cc, 0, sizeof(cc));
@@ -1344,8 +1384,15 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
         static b200ls_perf cperf;
         memset(&cperf, 0, offsetof(b200ls_perf, history));
         B2_CUDA(cudaMemsetAsync(M.corr.p, 0, sizeof(double) * D.nCells, S()));
-        if (m->symmetric) solvePCG(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
-        else solvePBiCGStab(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
+        g_scalarBank = 1;
+        try {
+            if (m->symmetric) solvePCG(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
+            else solvePBiCGStab(m, cc, k, M.corr.p, M.src.p, &cperf, nullptr);
+        } catch (...) {
+            g_scalarBank = 0;
+            throw;
+        }
+        g_scalarBank = 0;
         return;
     }
     m->coarsestWork.alloc(size_t(12) * D.nCells + size_t(2) * D.nFaces + 16);

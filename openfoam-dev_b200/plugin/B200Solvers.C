@@ -28,6 +28,8 @@
 
 #include "lduMatrix.H"
 #include "processorLduInterface.H"
+#include "cyclicLduInterface.H"
+#include "cyclicLduInterfaceField.H"
 #include "GAMGAgglomeration.H"
 #include "addToRunTimeSelectionTable.H"
 #include "Pstream.H"
@@ -207,26 +209,67 @@ protected:
             std::vector<int32_t> sizes, nbr;
             std::vector<const int32_t*> faceCells;
 
+            // coupled patches in patch order; cyclic halves refer to their
+            // partner by its index among the coupled patches
+            std::vector<int32_t> coupledIndex(interfaces_.size(), -1);
+            forAll(interfaces_, patchi)
+            {
+                if (interfaces_.set(patchi))
+                {
+                    coupledIndex[patchi] = sizes.size();
+                    sizes.push_back(0);
+                }
+            }
+            sizes.clear();
+
             forAll(interfaces_, patchi)
             {
                 if (interfaces_.set(patchi))
                 {
                     const lduInterface& li = interfaces_[patchi].interface();
-                    if (!isA<processorLduInterface>(li))
-                    {
-                        FatalErrorInFunction
-                            << "coupled patch " << patchi << " of type "
-                            << li.type() << " is not a processor interface:"
-                            << " only processor patches are supported"
-                            << exit(FatalError);
-                    }
                     const labelUList& fc = li.faceCells();
                     sizes.push_back(fc.size());
                     faceCells.push_back(fc.begin());
-                    nbr.push_back
-                    (
-                        refCast<const processorLduInterface>(li).neighbProcNo()
-                    );
+
+                    if (isA<processorLduInterface>(li))
+                    {
+                        nbr.push_back
+                        (
+                            refCast<const processorLduInterface>(li)
+                           .neighbProcNo()
+                        );
+                    }
+                    else if (isA<cyclicLduInterface>(li))
+                    {
+                        if
+                        (
+                            isA<cyclicLduInterfaceField>(interfaces_[patchi])
+                         && refCast<const cyclicLduInterfaceField>
+                            (
+                                interfaces_[patchi]
+                            ).transforms()
+                        )
+                        {
+                            FatalErrorInFunction
+                                << "cyclic patch " << patchi
+                                << " transforms the field (rotational cyclic"
+                                << " on a vector/tensor component): not"
+                                << " supported by libB200LinearSolvers"
+                                << exit(FatalError);
+                        }
+                        const label nbrPatch =
+                            refCast<const cyclicLduInterface>(li)
+                           .nbrPatchIndex();
+                        nbr.push_back(B200LS_CYCLIC(coupledIndex[nbrPatch]));
+                    }
+                    else
+                    {
+                        FatalErrorInFunction
+                            << "coupled patch " << patchi << " of type "
+                            << li.type() << " is neither a processor nor a"
+                            << " cyclic interface"
+                            << exit(FatalError);
+                    }
                 }
             }
 

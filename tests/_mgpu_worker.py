@@ -82,6 +82,8 @@ def main():
         exact = np.linalg.solve(A, glob.source)
         combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
         combos += [("GAMG", "GaussSeidel"), ("GAMG", "DIC" if kind == "sym" else "DILU")]
+        # V-cycles as the preconditioner: the coarsest-level Krylov solve is nested inside the outer Krylov loop
+        combos.append(("PCG" if kind == "sym" else "PBiCGStab", "GAMG"))
         if kind == "asym":   # Gauss-Seidel alone converges far too slowly on the Laplacian to pin a solution
             combos.append(("smoothSolver", "GaussSeidel"))
         for solver, pre in combos:

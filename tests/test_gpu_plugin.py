@@ -19,7 +19,8 @@ HARNESS = ROOT / "oracle/_ref/ref_harness"
 PLUGIN = ROOT / "openfoam-dev_b200/libB200LinearSolvers.so"
 
 
-@pytest.mark.parametrize("name", ["cavity_20x20x1", "block_16x16x16_rand", "convdiff_9x8x7"])
+@pytest.mark.parametrize("name", ["cavity_20x20x1", "block_16x16x16_rand", "convdiff_9x8x7",
+                                  "cyclic_xz_9x8x7_rand", "cyclic_y_convdiff_10x9x6"])
 def test_reference_selects_b200_solvers_by_name(name, tmp_path):
     if not HARNESS.exists() or not PLUGIN.exists():
         pytest.skip("oracle/_ref or the plugin was not built (needs /root/reference at build time)")

@@ -46,12 +46,16 @@ def test_addressing_bit_exact(name):
 def test_agglomeration_bit_exact(name):
     inp, ref = load_fixture(name)
     s = system_from_entries(inp)
-    mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    mesh = capi.Mesh(s.n_cells, s.lower, s.upper, s.interfaces)
     n_coarse = mesh.agglomerate(s.face_weights, forward_start=1)
     assert n_coarse == int(ref["agg.nLevels"][0])
     assert mesh.n_levels == n_coarse + 1
     for lev in range(n_coarse):
         k = f"agg.{lev}."
+        # coarse cyclic patches (cyclicGAMGInterface.C:85-157), from the unmodified reference
+        for i in range(len(s.interfaces)):
+            assert np.array_equal(mesh.get_iface_i32(0, lev + 1, i), ref[f"{k}iface.{i}.faceCells"]), (lev, i)
+            assert np.array_equal(mesh.get_iface_i32(1, lev, i), ref[f"{k}iface.{i}.faceRestrictAddressing"]), (lev, i)
         assert np.array_equal(mesh.get_i32(capi.RESTRICT_ADDRESSING, lev), ref[k + "restrictAddressing"])
         assert np.array_equal(mesh.get_i32(capi.FACE_RESTRICT_ADDRESSING, lev), ref[k + "faceRestrictAddressing"])
         assert np.array_equal(mesh.get_i32(capi.FACE_FLIP_MAP, lev), ref[k + "faceFlipMap"].astype(np.int32))
@@ -215,3 +219,19 @@ def test_forward_flag_alternates_like_the_reference_static():
     c = capi.Mesh(s.n_cells, s.lower, s.upper)
     c.agglomerate(s.face_weights, forward_start=1)
     assert np.array_equal(a.get_i32(capi.RESTRICT_ADDRESSING, 0), c.get_i32(capi.RESTRICT_ADDRESSING, 0))
+
+
+def test_cyclic_patch_validation():
+    lower, upper, _ = cases.block_addressing(4, 3, 2)
+    a = cases.Interface(neighb_rank=-1, face_cells=np.array([0, 4, 8], np.int32), bou_coeffs=np.ones(3),
+                        int_coeffs=np.ones(3), nbr_patch=1)
+    b = cases.Interface(neighb_rank=-1, face_cells=np.array([3, 7], np.int32), bou_coeffs=np.ones(2),
+                        int_coeffs=np.ones(2), nbr_patch=0)
+    with pytest.raises(capi.B200Error, match="different size"):
+        capi.Mesh(24, lower, upper, [a, b])
+    b.face_cells = np.array([3, 7, 11], np.int32)
+    b.nbr_patch = 1
+    with pytest.raises(capi.B200Error, match="point back"):
+        capi.Mesh(24, lower, upper, [a, b])
+    b.nbr_patch = 0
+    capi.Mesh(24, lower, upper, [a, b])
