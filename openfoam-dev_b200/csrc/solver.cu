@@ -860,6 +860,13 @@ static bool converged(double finalRes, double initRes, double tol, double relTol
     return finalRes < tol || (relTol > 1e-20 && finalRes < relTol * initRes);
 }
 
+// SolverPerformance::checkConvergence (SolverPerformance.C:60-92) stores its result: the flag a solve reports is the
+// one of the last call the loop conditions actually made (at maxIter the `&&` skips the call).
+static bool checkConvergence(b200ls_perf* perf, const b200ls_controls& c) {
+    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
+    return perf->converged != 0;
+}
+
 // named work vector of a level (level 0 vectors are the solver's finest-level vectors)
 static double* lvec(b200ls_matrix_s* m, int lv, const char* name) {
     if (lv == 0) return m->vec(name);
@@ -932,7 +939,7 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
     perf->nIterations = 0;
 
     if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
-    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+    if (c.minIter > 0 || !checkConvergence(perf, c)) {
         preparePrecond(m, c, lv);
         B2_CUDA(cudaMemsetAsync(scalar(m, S_SINGULAR), 0, sizeof(double), S()));
         // the dot products ride on the kernels that produce their operands when nothing sits in between
@@ -977,10 +984,9 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
             perf->finalResidual = cx.pinned[S_RES] / nf;
             record(perf, c, perf->finalResidual);
         } while ((++perf->nIterations < c.maxIter &&
-                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                  !checkConvergence(perf, c)) ||
                  perf->nIterations < c.minIter);
     }
-    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1006,7 +1012,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
     perf->nIterations = 0;
 
     if (evLoopStart) B2_CUDA(cudaEventRecord(evLoopStart, S()));
-    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+    if (c.minIter > 0 || !checkConvergence(perf, c)) {
         double* AyA = lvec(m, lv, "AyA");
         double* sA = lvec(m, lv, "sA");
         double* zA = lvec(m, lv, "zA");
@@ -1041,7 +1047,7 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
             readScalars(scalar(m, S_RES), 1);
             perf->finalResidual = cx.pinned[0] / nf;
             if (++perf->nIterations >= c.minIter &&
-                converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+                checkConvergence(perf, c)) {
                 LAUNCH(k_axpy_s, gridStride(n), 256, psi, yA, scalar(m, S_ALPHA), n);
                 record(perf, c, perf->finalResidual);
                 perf->converged = 1;
@@ -1062,10 +1068,9 @@ static void solvePBiCGStab(b200ls_matrix_s* m, const b200ls_controls& c, int lv,
             perf->finalResidual = cx.pinned[0] / nf;
             record(perf, c, perf->finalResidual);
         } while ((perf->nIterations < c.maxIter &&
-                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                  !checkConvergence(perf, c)) ||
                  perf->nIterations < c.minIter);
     }
-    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1095,7 +1100,7 @@ static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& p
     perf->initialResidual = cx.pinned[0] / nf;
     perf->finalResidual = perf->initialResidual;
     B2_CUDA(cudaEventRecord(evLoopStart, S()));
-    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+    if (c.minIter > 0 || !checkConvergence(perf, c)) {
         do {
             opSmooth(m, 0, c.precond, psi, spare, source, c.nSweeps);
             opResidual(m, 0, rA, psi, source);
@@ -1105,10 +1110,9 @@ static void solveSmooth(b200ls_matrix_s* m, const b200ls_controls& c, double*& p
             perf->finalResidual = cx.pinned[0] / nf;
             record(perf, c, perf->finalResidual);
         } while (((perf->nIterations += c.nSweeps) < c.maxIter &&
-                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                  !checkConvergence(perf, c)) ||
                  perf->nIterations < c.minIter);
     }
-    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1568,7 +1572,7 @@ static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi
     perf->nIterations = 0;
 
     B2_CUDA(cudaEventRecord(evLoopStart, S()));
-    if (c.minIter > 0 || !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) {
+    if (c.minIter > 0 || !checkConvergence(perf, c)) {
         do {
             vcycle(m, c, psi, psiSpare, source, Apsi, finestCorrection, finestResidual, scaleCorrection);
             opAmul(m, 0, Apsi, psi);
@@ -1579,10 +1583,9 @@ static void solveGAMG(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi
             perf->finalResidual = cx.pinned[0] / nf;
             record(perf, c, perf->finalResidual);
         } while ((++perf->nIterations < c.maxIter &&
-                  !converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol)) ||
+                  !checkConvergence(perf, c)) ||
                  perf->nIterations < c.minIter);
     }
-    perf->converged = converged(perf->finalResidual, perf->initialResidual, c.tolerance, c.relTol) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------

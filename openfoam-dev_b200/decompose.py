@@ -111,3 +111,39 @@ def cavity_subdomain(nx, ny, nz, split, rank):
     return LduSystem(n_cells=n, lower=lower, upper=upper, diag=diag, upper_coeffs=up, source=src,
                      face_weights=face_area_pair_weights(nx, ny, nz, fdir), face_dir=fdir, interfaces=ifaces,
                      shape=(lx, ly, lz))
+
+
+def as_cyclic_blocks(parts):
+    """The decomposed system as ONE block-diagonal LDU system: rank r's cells follow rank r-1's, every rank keeps its
+    own internal faces, and each processor-patch pair becomes a cyclic patch pair between the two blocks.
+
+    Run through the serial reference this executes the reference's *decomposed* algorithm: interface terms applied
+    after the face loop in patch order, block-local (= rank-local) DIC/DILU and Gauss-Seidel with lagged interface
+    values, per-block pair agglomeration with the lower rank as the master of each coarse patch
+    (cyclicGAMGInterface.C:85-157 has the same pair logic as processorGAMGInterface.C:75-147; the owner half is the
+    one with the lower patch index = the lower rank here), block-local DIC on the coarsest level.  Only the global
+    sums differ: one sequential pass over all cells instead of per-rank partial sums added in rank order.
+    GAMG needs nCellsInCoarsestLevel = 10*len(parts) to reproduce the decomposed stop criterion
+    (GAMGAgglomeration.C:205-230).  Returns (LduSystem, cell offsets)."""
+    offs = np.concatenate([[0], np.cumsum([p.n_cells for p in parts])]).astype(np.int64)
+    sym = parts[0].symmetric
+    first = np.concatenate([[0], np.cumsum([len(p.interfaces) for p in parts])])
+    ifaces = []
+    for r, p in enumerate(parts):
+        for itf in p.interfaces:
+            s = itf.neighb_rank
+            back = [k for k, o in enumerate(parts[s].interfaces) if o.neighb_rank == r]
+            if len(back) != 1:
+                raise ValueError("as_cyclic_blocks needs exactly one processor patch per rank pair")
+            ifaces.append(Interface(neighb_rank=-1, face_cells=(itf.face_cells + offs[r]).astype(np.int32),
+                                    bou_coeffs=itf.bou_coeffs.copy(), int_coeffs=itf.int_coeffs.copy(),
+                                    nbr_patch=int(first[s] + back[0])))
+    cat = np.concatenate
+    return LduSystem(
+        n_cells=int(offs[-1]),
+        lower=cat([p.lower + offs[r] for r, p in enumerate(parts)]).astype(np.int32),
+        upper=cat([p.upper + offs[r] for r, p in enumerate(parts)]).astype(np.int32),
+        diag=cat([p.diag for p in parts]), upper_coeffs=cat([p.upper_coeffs for p in parts]),
+        lower_coeffs=None if sym else cat([p.lower_coeffs for p in parts]),
+        source=cat([p.source for p in parts]), face_weights=cat([p.face_weights for p in parts]),
+        interfaces=ifaces), offs

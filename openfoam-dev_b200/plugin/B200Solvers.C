@@ -439,15 +439,19 @@ protected:
             "b200ls_solve"
         );
 
-        solverPerformance solverPerf(solverName, fieldName_);
-        solverPerf.initialResidual() = perf->initialResidual;
-        solverPerf.finalResidual() = perf->finalResidual;
-        solverPerf.nIterations() = perf->nIterations;
-        solverPerf.checkConvergence(tolerance_, relTol_);
-        if (perf->singular)
-        {
-            solverPerf.checkSingularity(0);
-        }
+        // converged_ is the flag of the last checkConvergence call the
+        // reference's loop would have made (SolverPerformance.C:60-92),
+        // which libb200ls tracks; do not re-evaluate it here
+        solverPerformance solverPerf
+        (
+            solverName,
+            fieldName_,
+            perf->initialResidual,
+            perf->finalResidual,
+            perf->nIterations,
+            perf->converged != 0,
+            perf->singular != 0
+        );
         delete perf;
 
         return solverPerf;

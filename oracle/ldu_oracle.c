@@ -252,8 +252,12 @@ double oracle_norm_factor(const ldu_t* A, const double* psi, const double* sourc
     return nf + SMALL_;
 }
 
-static int converged(const perf_t* p, double tol, double relTol) {  /* SolverPerformance.C:60-92 */
-    return p->finalResidual < tol || (relTol > SMALL_ && p->finalResidual < relTol * p->initialResidual);
+/* SolverPerformance::checkConvergence (LduMatrix/LduMatrix/SolverPerformance.C:60-92): the converged flag a solve
+ * reports is the result of the LAST CALL the loop conditions actually made -- when maxIter is reached the `&&`
+ * short-circuits the call, so the flag keeps the value of the previous iteration's check. */
+static int check(perf_t* p, double tol, double relTol) {
+    p->converged = p->finalResidual < tol || (relTol > SMALL_ && p->finalResidual < relTol * p->initialResidual);
+    return p->converged;
 }
 
 static void record(perf_t* p) {
@@ -281,7 +285,7 @@ void oracle_pcg(const ldu_t* A, const ctl_t* c, double* psi, const double* sourc
     perf->normFactor = nf;
     perf->initialResidual = sum_mag(rA, n) / nf;
     perf->finalResidual = perf->initialResidual;
-    if (c->minIter > 0 || !converged(perf, c->tolerance, c->relTol)) {
+    if (c->minIter > 0 || !check(perf, c->tolerance, c->relTol)) {
         make_rD(A, c->precond, rD);
         do {
             wArAold = wArA;
@@ -306,10 +310,9 @@ void oracle_pcg(const ldu_t* A, const ctl_t* c, double* psi, const double* sourc
             }
             perf->finalResidual = sum_mag(rA, n) / nf;
             record(perf);
-        } while ((++perf->nIterations < c->maxIter && !converged(perf, c->tolerance, c->relTol)) ||
+        } while ((++perf->nIterations < c->maxIter && !check(perf, c->tolerance, c->relTol)) ||
                  perf->nIterations < c->minIter);
     }
-    perf->converged = converged(perf, c->tolerance, c->relTol);
     free(pA);
 }
 
@@ -327,7 +330,7 @@ void oracle_pbicgstab(const ldu_t* A, const ctl_t* c, double* psi, const double*
     perf->normFactor = nf;
     perf->initialResidual = sum_mag(rA, n) / nf;
     perf->finalResidual = perf->initialResidual;
-    if (c->minIter > 0 || !converged(perf, c->tolerance, c->relTol)) {
+    if (c->minIter > 0 || !check(perf, c->tolerance, c->relTol)) {
         memcpy(rA0, rA, sizeof(double) * (size_t)n);
         double rA0rA = 0, alpha = 0, omega = 0;
         make_rD(A, c->precond, rD);
@@ -354,7 +357,7 @@ void oracle_pbicgstab(const ldu_t* A, const ctl_t* c, double* psi, const double*
             alpha = rA0rA / rA0AyA;
             for (int i = 0; i < n; i++) sA[i] = rA[i] - alpha * AyA[i];
             perf->finalResidual = sum_mag(sA, n) / nf;
-            if (++perf->nIterations >= c->minIter && converged(perf, c->tolerance, c->relTol)) {
+            if (++perf->nIterations >= c->minIter && check(perf, c->tolerance, c->relTol)) {
                 for (int i = 0; i < n; i++) psi[i] += alpha * yA[i];
                 record(perf);
                 perf->converged = 1;
@@ -372,10 +375,9 @@ void oracle_pbicgstab(const ldu_t* A, const ctl_t* c, double* psi, const double*
             }
             perf->finalResidual = sum_mag(rA, n) / nf;
             record(perf);
-        } while ((perf->nIterations < c->maxIter && !converged(perf, c->tolerance, c->relTol)) ||
+        } while ((perf->nIterations < c->maxIter && !check(perf, c->tolerance, c->relTol)) ||
                  perf->nIterations < c->minIter);
     }
-    perf->converged = converged(perf, c->tolerance, c->relTol);
     free(pA);
 }
 
@@ -393,16 +395,15 @@ void oracle_smooth_solver(const ldu_t* A, const ctl_t* c, double* psi, const dou
     for (int i = 0; i < n; i++) s += fabs(source[i] - Apsi[i]);
     perf->initialResidual = s / nf;
     perf->finalResidual = perf->initialResidual;
-    if (c->minIter > 0 || !converged(perf, c->tolerance, c->relTol)) {
+    if (c->minIter > 0 || !check(perf, c->tolerance, c->relTol)) {
         do {
             oracle_smooth(A, c->precond, psi, source, c->nSweeps);
             oracle_residual(A, psi, source, tmp);
             perf->finalResidual = sum_mag(tmp, n) / nf;
             record(perf);
-        } while (((perf->nIterations += c->nSweeps) < c->maxIter && !converged(perf, c->tolerance, c->relTol)) ||
+        } while (((perf->nIterations += c->nSweeps) < c->maxIter && !check(perf, c->tolerance, c->relTol)) ||
                  perf->nIterations < c->minIter);
     }
-    perf->converged = converged(perf, c->tolerance, c->relTol);
     free(Apsi);
 }
 
@@ -872,17 +873,16 @@ void oracle_gamg_solve(hierarchy_t* H, const double* diag, const double* upper, 
     for (int i = 0; i < n; i++) finestResidual[i] = source[i] - Apsi[i];
     perf->initialResidual = sum_mag(finestResidual, n) / nf;
     perf->finalResidual = perf->initialResidual;
-    if (c->minIter > 0 || !converged(perf, c->tolerance, c->relTol)) {
+    if (c->minIter > 0 || !check(perf, c->tolerance, c->relTol)) {
         do {
             gamg_vcycle(H, c, psi, source, Apsi, finestCorrection, finestResidual, scratch);
             oracle_amul(&A0, psi, Apsi);
             for (int i = 0; i < n; i++) finestResidual[i] = source[i] - Apsi[i];
             perf->finalResidual = sum_mag(finestResidual, n) / nf;
             record(perf);
-        } while ((++perf->nIterations < c->maxIter && !converged(perf, c->tolerance, c->relTol)) ||
+        } while ((++perf->nIterations < c->maxIter && !check(perf, c->tolerance, c->relTol)) ||
                  perf->nIterations < c->minIter);
     }
-    perf->converged = converged(perf, c->tolerance, c->relTol);
     free(Apsi);
 }
 

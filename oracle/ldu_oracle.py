@@ -72,7 +72,8 @@ def _p(a):
 class System:
     """Keeps the numpy arrays alive next to the C view."""
 
-    def __init__(self, s):
+    def __init__(self, s, min_cells=10):
+        self.min_cells = min_cells       # nCellsInCoarsestLevel of the GAMG hierarchy built by solve()/agglomeration()
         self.l = np.ascontiguousarray(s.lower, dtype=np.int32)
         self.u = np.ascontiguousarray(s.upper, dtype=np.int32)
         self.diag = np.ascontiguousarray(s.diag, dtype=np.float64)
@@ -101,8 +102,9 @@ class System:
     def _ptr_array(self, arrays):
         return (C.c_void_p * max(1, len(arrays)))(*[a.ctypes.data for a in arrays])
 
-    def gamg_build(self, min_cells=10, forward_start=1):
+    def gamg_build(self, min_cells=None, forward_start=1):
         """hierarchy_t* with the cyclic patches agglomerated and the finest-level interface coefficients set."""
+        min_cells = self.min_cells if min_cells is None else min_cells
         H = lib().oracle_gamg_build_coupled(self.n, self.l.size, _p(self.l), _p(self.u),
                                             _p(np.ascontiguousarray(self.face_weights)), min_cells, forward_start,
                                             self.n_ifaces, _p(self.if_sizes), self._ptr_array(self.if_cells),
@@ -201,7 +203,7 @@ def solve(S, solver, ctl, source, psi0=None):
     return x, _perf(p)
 
 
-def agglomeration(S, min_cells=10, forward_start=1):
+def agglomeration(S, min_cells=None, forward_start=1):
     """Per level: (restrictAddressing, faceRestrictAddressing, faceFlipMap, coarseLower, coarseUpper)."""
     H = S.gamg_build(min_cells, forward_start)
     out = []
@@ -223,7 +225,7 @@ def agglomeration(S, min_cells=10, forward_start=1):
     return out
 
 
-def interface_agglomeration(S, min_cells=10, forward_start=1):
+def interface_agglomeration(S, min_cells=None, forward_start=1):
     """Per level, per cyclic patch: (coarse faceCells, faceRestrictAddressing of the fine patch)."""
     H = S.gamg_build(min_cells, forward_start)
     out = []

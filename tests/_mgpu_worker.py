@@ -12,6 +12,51 @@ from _pkg import load_pkg  # noqa: E402
 
 load_pkg()
 from b200ls import capi, cases, decompose  # noqa: E402
+from _util import GOLDEN, controls_from_dict, load_fixture, solve_keys  # noqa: E402
+
+
+def check_against_reference_fixture(kind, world, rank, parts, mat, part):
+    """tests/golden/decomp<world>_<kind>.b2ls: the unmodified reference executing its decomposed algorithm in serial
+    (processor patches as cyclic pairs between diagonal blocks, decompose.as_cyclic_blocks).  Bars as on one GPU:
+    iterations +-1, residuals within 1e-9 of the reference on the scale of the initial residual, solution within 1e-9
+    when the iteration counts agree.  The residual history of BiCGStab is compared over its first 12 iterations."""
+    name = f"decomp{world}_{kind}"
+    if not (GOLDEN / f"{name}.b2ls").exists():
+        return True
+    inp, ref = load_fixture(name)
+    blk, offs = decompose.as_cyclic_blocks(parts)
+    same = np.array_equal(blk.lower, inp["lower"]) and np.array_equal(blk.diag, inp["diag"]) and \
+        np.array_equal(blk.upper_coeffs, inp["upperCoeffs"]) and np.array_equal(blk.source, inp["source"])
+    ok = bool(same)
+    lo, hi = int(offs[rank]), int(offs[rank + 1])
+    worst = 0.0
+    for i, text in solve_keys(inp):
+        ctl = controls_from_dict(text, recordHistory=1)
+        psi, perf = mat.solve(ctl, part.source)
+        rperf = ref[f"solve.{i}.perf"]
+        good = abs(perf.nIterations - int(rperf[2])) <= 1 and abs(perf.initialResidual - rperf[0]) <= 1e-9 * abs(rperf[0])
+        if perf.nIterations == int(rperf[2]):
+            rpsi = ref[f"solve.{i}.psi"][lo:hi]
+            dpsi = float(np.max(np.abs(psi - rpsi)) / max(np.max(np.abs(rpsi)), 1e-300))
+            worst = max(worst, dpsi) if "PBiCGStab" not in text else worst
+            sol_tol = max(1e-9, ctl.tolerance) if "PBiCGStab" in text and perf.nIterations > 12 else 1e-9
+            good = good and abs(perf.finalResidual - rperf[1]) <= 1e-9 * abs(rperf[0]) and dpsi <= sol_tol and \
+                bool(perf.converged) == bool(rperf[3])
+        hkey = f"solve.{i}.historyResiduals"
+        if hkey in ref:
+            h, rh = capi.history(perf), ref[hkey]
+            n = min(len(h), len(rh), int(rperf[2]))
+            if "PBiCGStab" in text:
+                n = min(n, 12)
+            good = good and n > 0 and bool(np.all(np.abs(h[:n] - rh[:n]) <= 1e-9 * abs(rperf[0])))
+        if not good and rank == 0:
+            print(f"{name}: FAIL {text}: iterations {perf.nIterations}/{int(rperf[2])} "
+                  f"final {perf.finalResidual:.6e}/{rperf[1]:.6e}", flush=True)
+        ok &= bool(good)
+    if rank == 0:
+        print(f"{name}: {len(list(solve_keys(inp)))} solver configurations vs the reference run as cyclic blocks: "
+              f"{'OK' if ok else 'FAIL'} (max solution rel diff {worst:.2e})", flush=True)
+    return ok
 
 
 def dense(sys_):
@@ -79,6 +124,7 @@ def main():
             if rank == 0:
                 print(f"sym: decomposed PCG+DIC vs emulated ranks: iterations {perf.nIterations}/{e_perf['nIterations']} "
                       f"max history diff {dh:.2e} solution rel diff {dpsi:.2e} {'OK' if good else 'FAIL'}", flush=True)
+        ok &= check_against_reference_fixture(kind, world, rank, parts, mat, part)
         exact = np.linalg.solve(A, glob.source)
         combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
         combos += [("GAMG", "GaussSeidel"), ("GAMG", "DIC" if kind == "sym" else "DILU")]

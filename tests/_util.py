@@ -1,4 +1,5 @@
 """Shared helpers of the parity tests."""
+import re
 from pathlib import Path
 
 import numpy as np
@@ -31,6 +32,16 @@ def system_from_entries(inp):
             for k in range(int(inp["nIfaces"][0]) if "nIfaces" in inp else 0)
         ],
     )
+
+
+def min_cells_of(inp):
+    """nCellsInCoarsestLevel of a fixture's GAMG dictionaries (10 = the reference default, GAMGAgglomeration.C:254)."""
+    for k, v in inp.items():
+        if k.endswith(".dict"):
+            m = re.search(r"nCellsInCoarsestLevel\s+(\d+)", v if isinstance(v, str) else ldu_io.as_str(v))
+            if m:
+                return int(m.group(1))
+    return 10
 
 
 def parse_dict(text):

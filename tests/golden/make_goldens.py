@@ -22,7 +22,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 from _pkg import load_pkg  # noqa: E402
 
 b200ls = load_pkg()
-from b200ls import cases, ldu_io  # noqa: E402
+from b200ls import cases, decompose, ldu_io  # noqa: E402
 
 
 def run_ref(entries):
@@ -70,8 +70,26 @@ ASYM_SOLVES = [
 ]
 
 
-def fixture(name, sys_, solves, smoothers, agglom=True):
+def decomposed_case(kind, n_ranks):
+    """The decomposed systems of tests/_mgpu_worker.py folded into one block-diagonal system whose processor patches
+    are cyclic pairs (decompose.as_cyclic_blocks): the serial reference then runs its decomposed algorithm."""
+    split = decompose.simple_split(n_ranks)
+    nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
+    glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if kind == "sym" else \
+        cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
+    parts, _ = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), n_ranks)
+    return decompose.as_cyclic_blocks(parts)
+
+
+def with_coarsest(solves, n):
+    return [(d.replace("solver GAMG;", f"solver GAMG; nCellsInCoarsestLevel {n};")
+              .replace("preconditioner GAMG;", f"preconditioner GAMG; nCellsInCoarsestLevel {n};"), h)
+            for d, h in solves]
+
+
+def fixture(name, sys_, solves, smoothers, agglom=True, agglom_dict="solver GAMG;", extra=None):
     e = cases.to_entries(sys_)
+    e.update(extra or {})
     n = sys_.n_cells
     e["x"] = np.cos(0.11 * np.arange(n)) + 0.25
     for i, (d, hist) in enumerate(solves):
@@ -82,7 +100,10 @@ def fixture(name, sys_, solves, smoothers, agglom=True):
         e[f"smooth.{i}.dict"] = d
         e[f"smooth.{i}.nSweeps"] = ns
     if agglom:
-        e["agglomerate.dict"] = "solver GAMG;"
+        e["agglomerate.dict"] = agglom_dict
+    if (HERE / f"{name}.b2ls").exists() and "--all" not in sys.argv:
+        print(f"{name}: kept (pass --all to regenerate)")
+        return
     out = run_ref(e)
     merged = {f"in.{k}": v for k, v in e.items()}
     merged.update({f"ref.{k}": v for k, v in out.items()})
@@ -120,6 +141,14 @@ def main():
             SYM_SOLVES, sym_sm)
     fixture("cyclic_y_convdiff_10x9x6", cases.add_cyclic(cases.convection_diffusion(10, 9, 6, dt_coeff=50.0), 1),
             ASYM_SOLVES, asym_sm)
+    # decomposed runs, executed by the SERIAL reference as block-diagonal systems with cyclic pairs in place of the
+    # processor patches; nCellsInCoarsestLevel = 10*nRanks reproduces the decomposed stop criterion
+    for kind, n_ranks, solves, sm in (("sym", 2, SYM_SOLVES, sym_sm), ("asym", 2, ASYM_SOLVES, asym_sm),
+                                      ("sym", 4, SYM_SOLVES, sym_sm), ("asym", 4, ASYM_SOLVES, asym_sm)):
+        blk, offs = decomposed_case(kind, n_ranks)
+        fixture(f"decomp{n_ranks}_{kind}", blk, with_coarsest(solves, 10 * n_ranks), sm,
+                agglom_dict=f"solver GAMG; nCellsInCoarsestLevel {10 * n_ranks};",
+                extra={"rankOffsets": offs.astype(np.int32)})
 
 
 if __name__ == "__main__":

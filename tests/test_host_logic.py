@@ -6,7 +6,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from _util import FIXTURES, capi, cases, ldu_io, load_fixture, system_from_entries
+from _util import FIXTURES, min_cells_of, capi, cases, ldu_io, load_fixture, system_from_entries
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -47,7 +47,7 @@ def test_agglomeration_bit_exact(name):
     inp, ref = load_fixture(name)
     s = system_from_entries(inp)
     mesh = capi.Mesh(s.n_cells, s.lower, s.upper, s.interfaces)
-    n_coarse = mesh.agglomerate(s.face_weights, forward_start=1)
+    n_coarse = mesh.agglomerate(s.face_weights, min_cells_per_processor=min_cells_of(inp), forward_start=1)
     assert n_coarse == int(ref["agg.nLevels"][0])
     assert mesh.n_levels == n_coarse + 1
     for lev in range(n_coarse):

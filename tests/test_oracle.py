@@ -7,7 +7,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from _util import FIXTURES, ldu_io, load_fixture, parse_dict, smooth_keys, solve_keys, system_from_entries
+from _util import FIXTURES, ldu_io, load_fixture, min_cells_of, parse_dict, smooth_keys, solve_keys, system_from_entries
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
 import ldu_oracle as orc  # noqa: E402
@@ -17,7 +17,7 @@ import ldu_oracle as orc  # noqa: E402
 def fx(request):
     inp, ref = load_fixture(request.param)
     s = system_from_entries(inp)
-    return request.param, inp, ref, s, orc.System(s)
+    return request.param, inp, ref, s, orc.System(s, min_cells=min_cells_of(inp))
 
 
 def test_operators(fx):
@@ -65,7 +65,7 @@ def test_solvers_bit_exact(fx):
     for i, text in solve_keys(inp):
         d = parse_dict(text)
         kw = {k: (float(v) if k in ("tolerance", "relTol") else int(v)) for k, v in d.items()
-              if k not in ("solver", "preconditioner", "smoother")}
+              if k not in ("solver", "preconditioner", "smoother", "nCellsInCoarsestLevel")}
         pre = d.get("preconditioner") or d.get("smoother")
         if isinstance(pre, dict):
             sub, pre = pre, pre["preconditioner"]
@@ -111,3 +111,32 @@ def test_emulated_ranks_reduce_to_the_reference_at_one_rank():
         full[m] = x
     xg, pg = orc.solve(orc.System(g), "PCG", orc.controls("DIC", tolerance=1e-12), g.source)
     assert max_rel_diff(full, xg) <= 1e-10
+
+
+@pytest.mark.parametrize("name", ["decomp2_sym", "decomp4_sym"])
+def test_emulated_ranks_match_the_reference_run_as_cyclic_blocks(name):
+    """The decomposed fixtures are the REFERENCE running its decomposed algorithm in serial (processor patches as
+    cyclic pairs between diagonal blocks).  The rank-by-rank emulation used by the multi-GPU test must agree with it:
+    same iteration count, residual history to ~1e-15 (only the grouping of the global sums differs)."""
+    import _emulated_ranks as em
+    from _pkg import load_pkg
+
+    load_pkg()
+    from b200ls import cases, decompose
+
+    inp, ref = load_fixture(name)
+    n_ranks = len(inp["rankOffsets"]) - 1
+    split = decompose.simple_split(n_ranks)
+    nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
+    glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random")
+    parts, _ = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), n_ranks)
+    blk, offs = decompose.as_cyclic_blocks(parts)
+    assert np.array_equal(blk.lower, inp["lower"]) and np.array_equal(blk.diag, inp["diag"])   # same case as the fixture
+    i = [k for k, t in solve_keys(inp) if "PCG" in t and "DIC" in t and "1e-10" in t][0]
+    e_psi, e_perf = em.pcg(parts, "DIC", tolerance=1e-10)
+    rperf = ref[f"solve.{i}.perf"]
+    assert e_perf["nIterations"] == int(rperf[2])
+    rh = ref[f"solve.{i}.historyResiduals"]
+    n = min(len(rh), len(e_perf["history"]), int(rperf[2]))
+    assert np.max(np.abs(e_perf["history"][:n] - rh[:n])) <= 1e-12 * rperf[0]
+    assert np.max(np.abs(np.concatenate(e_psi) - ref[f"solve.{i}.psi"])) <= 1e-11 * np.max(np.abs(ref[f"solve.{i}.psi"]))
