@@ -1,8 +1,9 @@
 """In-process emulation of the reference's DECOMPOSED PCG (PCG.C:65-193 on every rank, processor-patch updates as in
 processorFvPatchScalarField.C:36-152, reductions as in FieldReductionFunctions.C:190-292 + reduce(sumOp)), built from
-the single-rank C oracle (oracle/ldu_oracle.c) for all rank-local arithmetic.  The image has no MPI, so this is the
-strongest available stand-in for the reference run under mpirun: the preconditioner is rank-local, the interface
-contributions are applied after the face loop in patch order, and rank sums are added in rank order."""
+the single-rank C oracle (oracle/ldu_oracle.c) for all rank-local arithmetic: the preconditioner is rank-local, the
+interface contributions are applied after the face loop in patch order, and rank sums are added in rank order (the
+grouping MPI's reduce would use).  It is itself pinned against the reference running the same decomposed algorithm in
+serial as cyclic blocks (tests/golden/decomp*_sym.b2ls, tests/test_oracle.py)."""
 import sys
 from pathlib import Path
 
