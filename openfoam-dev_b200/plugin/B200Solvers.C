@@ -170,6 +170,163 @@ static int preconditionerId(const word& name)
     return -1;
 }
 
+//- Mesh/matrix handles for an addressing (created on demand, cached)
+static cacheEntry& entryFor
+(
+    const lduMatrix& matrix,
+    const lduInterfaceFieldPtrsList& interfaces
+)
+{
+    init();
+
+    const lduAddressing& addr = matrix.lduAddr();
+    cacheEntry& e = cache_[&addr];
+
+    const label nCells = addr.size();
+    const label nFaces = addr.lowerAddr().size();
+
+    const uint64_t fp = fingerprint(addr);
+
+    if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces || e.fingerprint != fp))
+    {
+        // mesh changed under the same address: rebuild
+        b200ls_matrix_free(e.matrix);
+        b200ls_mesh_free(e.mesh);
+        e = cacheEntry();
+    }
+
+    if (!e.mesh)
+    {
+        std::vector<int32_t> sizes, nbr;
+        std::vector<const int32_t*> faceCells;
+
+        // coupled patches in patch order; cyclic halves refer to their
+        // partner by its index among the coupled patches
+        std::vector<int32_t> coupledIndex(interfaces.size(), -1);
+        forAll(interfaces, patchi)
+        {
+            if (interfaces.set(patchi))
+            {
+                coupledIndex[patchi] = sizes.size();
+                sizes.push_back(0);
+            }
+        }
+        sizes.clear();
+
+        forAll(interfaces, patchi)
+        {
+            if (interfaces.set(patchi))
+            {
+                const lduInterface& li = interfaces[patchi].interface();
+                const labelUList& fc = li.faceCells();
+                sizes.push_back(fc.size());
+                faceCells.push_back(fc.begin());
+
+                if (isA<processorLduInterface>(li))
+                {
+                    nbr.push_back
+                    (
+                        refCast<const processorLduInterface>(li)
+                       .neighbProcNo()
+                    );
+                }
+                else if (isA<cyclicLduInterface>(li))
+                {
+                    if
+                    (
+                        isA<cyclicLduInterfaceField>(interfaces[patchi])
+                     && refCast<const cyclicLduInterfaceField>
+                        (
+                            interfaces[patchi]
+                        ).transforms()
+                    )
+                    {
+                        FatalErrorInFunction
+                            << "cyclic patch " << patchi
+                            << " transforms the field (rotational cyclic"
+                            << " on a vector/tensor component): not"
+                            << " supported by libB200LinearSolvers"
+                            << exit(FatalError);
+                    }
+                    const label nbrPatch =
+                        refCast<const cyclicLduInterface>(li)
+                       .nbrPatchIndex();
+                    nbr.push_back(B200LS_CYCLIC(coupledIndex[nbrPatch]));
+                }
+                else
+                {
+                    FatalErrorInFunction
+                        << "coupled patch " << patchi << " of type "
+                        << li.type() << " is neither a processor nor a"
+                        << " cyclic interface"
+                        << exit(FatalError);
+                }
+            }
+        }
+
+        e.mesh = b200ls_mesh_create
+        (
+            nCells,
+            nFaces,
+            addr.lowerAddr().begin(),
+            addr.upperAddr().begin(),
+            sizes.size(),
+            sizes.data(),
+            faceCells.data(),
+            nbr.data()
+        );
+        if (!e.mesh)
+        {
+            FatalErrorInFunction
+                << "b200ls_mesh_create failed: " << b200ls_last_error()
+                << exit(FatalError);
+        }
+        e.matrix = b200ls_matrix_create(e.mesh);
+        e.nCells = nCells;
+        e.nFaces = nFaces;
+        e.fingerprint = fp;
+    }
+
+    return e;
+}
+
+
+//- Upload the coefficients a solver/smoother/preconditioner object was
+//  constructed with
+static void uploadCoeffs
+(
+    cacheEntry& e,
+    const lduMatrix& matrix,
+    const Field<Field<scalar>>& bouCoeffs,
+    const Field<Field<scalar>>& intCoeffs,
+    const lduInterfaceFieldPtrsList& interfaces
+)
+{
+    std::vector<const double*> bou, inn;
+    forAll(interfaces, patchi)
+    {
+        if (interfaces.set(patchi))
+        {
+            bou.push_back(bouCoeffs[patchi].begin());
+            inn.push_back(intCoeffs[patchi].begin());
+        }
+    }
+
+    check
+    (
+        b200ls_matrix_set
+        (
+            e.matrix,
+            matrix.diag().begin(),
+            matrix.upper().begin(),
+            matrix.asymmetric() ? matrix.lower().begin() : nullptr,
+            bou.data(),
+            inn.data()
+        ),
+        "b200ls_matrix_set"
+    );
+}
+
 } // End namespace B200
 
 
@@ -186,144 +343,15 @@ protected:
     //- Mesh/matrix handles for this solver's addressing (created on demand)
     B200::cacheEntry& entry() const
     {
-        B200::init();
-
-        const lduAddressing& addr = matrix_.lduAddr();
-        B200::cacheEntry& e = B200::cache_[&addr];
-
-        const label nCells = addr.size();
-        const label nFaces = addr.lowerAddr().size();
-
-        const uint64_t fp = B200::fingerprint(addr);
-
-        if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces || e.fingerprint != fp))
-        {
-            // mesh changed under the same address: rebuild
-            b200ls_matrix_free(e.matrix);
-            b200ls_mesh_free(e.mesh);
-            e = B200::cacheEntry();
-        }
-
-        if (!e.mesh)
-        {
-            std::vector<int32_t> sizes, nbr;
-            std::vector<const int32_t*> faceCells;
-
-            // coupled patches in patch order; cyclic halves refer to their
-            // partner by its index among the coupled patches
-            std::vector<int32_t> coupledIndex(interfaces_.size(), -1);
-            forAll(interfaces_, patchi)
-            {
-                if (interfaces_.set(patchi))
-                {
-                    coupledIndex[patchi] = sizes.size();
-                    sizes.push_back(0);
-                }
-            }
-            sizes.clear();
-
-            forAll(interfaces_, patchi)
-            {
-                if (interfaces_.set(patchi))
-                {
-                    const lduInterface& li = interfaces_[patchi].interface();
-                    const labelUList& fc = li.faceCells();
-                    sizes.push_back(fc.size());
-                    faceCells.push_back(fc.begin());
-
-                    if (isA<processorLduInterface>(li))
-                    {
-                        nbr.push_back
-                        (
-                            refCast<const processorLduInterface>(li)
-                           .neighbProcNo()
-                        );
-                    }
-                    else if (isA<cyclicLduInterface>(li))
-                    {
-                        if
-                        (
-                            isA<cyclicLduInterfaceField>(interfaces_[patchi])
-                         && refCast<const cyclicLduInterfaceField>
-                            (
-                                interfaces_[patchi]
-                            ).transforms()
-                        )
-                        {
-                            FatalErrorInFunction
-                                << "cyclic patch " << patchi
-                                << " transforms the field (rotational cyclic"
-                                << " on a vector/tensor component): not"
-                                << " supported by libB200LinearSolvers"
-                                << exit(FatalError);
-                        }
-                        const label nbrPatch =
-                            refCast<const cyclicLduInterface>(li)
-                           .nbrPatchIndex();
-                        nbr.push_back(B200LS_CYCLIC(coupledIndex[nbrPatch]));
-                    }
-                    else
-                    {
-                        FatalErrorInFunction
-                            << "coupled patch " << patchi << " of type "
-                            << li.type() << " is neither a processor nor a"
-                            << " cyclic interface"
-                            << exit(FatalError);
-                    }
-                }
-            }
-
-            e.mesh = b200ls_mesh_create
-            (
-                nCells,
-                nFaces,
-                addr.lowerAddr().begin(),
-                addr.upperAddr().begin(),
-                sizes.size(),
-                sizes.data(),
-                faceCells.data(),
-                nbr.data()
-            );
-            if (!e.mesh)
-            {
-                FatalErrorInFunction
-                    << "b200ls_mesh_create failed: " << b200ls_last_error()
-                    << exit(FatalError);
-            }
-            e.matrix = b200ls_matrix_create(e.mesh);
-            e.nCells = nCells;
-            e.nFaces = nFaces;
-            e.fingerprint = fp;
-        }
-
-        return e;
+        return B200::entryFor(matrix_, interfaces_);
     }
 
     //- Upload the coefficients this solver object was constructed with
     void upload(B200::cacheEntry& e) const
     {
-        std::vector<const double*> bou, inn;
-        forAll(interfaces_, patchi)
-        {
-            if (interfaces_.set(patchi))
-            {
-                bou.push_back(interfaceBouCoeffs_[patchi].begin());
-                inn.push_back(interfaceIntCoeffs_[patchi].begin());
-            }
-        }
-
-        B200::check
+        B200::uploadCoeffs
         (
-            b200ls_matrix_set
-            (
-                e.matrix,
-                matrix_.diag().begin(),
-                matrix_.upper().begin(),
-                matrix_.asymmetric() ? matrix_.lower().begin() : nullptr,
-                bou.data(),
-                inn.data()
-            ),
-            "b200ls_matrix_set"
+            e, matrix_, interfaceBouCoeffs_, interfaceIntCoeffs_, interfaces_
         );
     }
 
@@ -617,6 +645,154 @@ public:
 
 
 // ---------------------------------------------------------------------------
+// B200DIC / B200DILU preconditioners and B200* smoothers: the operator-level
+// drop-ins (lduMatrix::preconditioner, lduMatrix.H:410-509; lduMatrix::smoother,
+// :270-406) for callers that keep the REFERENCE's solver loop, e.g.
+//     p { solver PCG;  preconditioner B200DIC; }
+//     p { solver GAMG; smoother B200GaussSeidel; }
+// Every application crosses the host<->device boundary (wA/rA or psi/source), so
+// these are for validation and mixed use; the B200 solvers above keep the whole
+// loop on the device.
+// ---------------------------------------------------------------------------
+
+template<int Kind>
+class B200Preconditioner
+:
+    public lduMatrix::preconditioner
+{
+    B200::cacheEntry& e_;
+
+public:
+
+    B200Preconditioner(const lduMatrix::solver& sol, const dictionary&)
+    :
+        lduMatrix::preconditioner(sol),
+        e_(B200::entryFor(sol.matrix(), sol.interfaces()))
+    {
+        // coefficients are read once per construction, like
+        // DICPreconditioner's calcReciprocalD (DICPreconditioner.C:42-52)
+        B200::uploadCoeffs
+        (
+            e_,
+            sol.matrix(),
+            sol.interfaceBouCoeffs(),
+            sol.interfaceIntCoeffs(),
+            sol.interfaces()
+        );
+    }
+
+    virtual void precondition
+    (
+        scalarField& wA,
+        const scalarField& rA,
+        const direction cmpt = 0
+    ) const
+    {
+        B200::check
+        (
+            b200ls_precondition(e_.matrix, Kind, rA.begin(), wA.begin()),
+            "b200ls_precondition"
+        );
+    }
+};
+
+class B200DICPreconditioner
+:
+    public B200Preconditioner<B200LS_DIC>
+{
+public:
+    TypeName("B200DIC");
+    using B200Preconditioner<B200LS_DIC>::B200Preconditioner;
+};
+
+class B200DILUPreconditioner
+:
+    public B200Preconditioner<B200LS_DILU>
+{
+public:
+    TypeName("B200DILU");
+    using B200Preconditioner<B200LS_DILU>::B200Preconditioner;
+};
+
+
+template<int Kind>
+class B200Smoother
+:
+    public lduMatrix::smoother
+{
+    B200::cacheEntry& e_;
+
+public:
+
+    B200Smoother
+    (
+        const word& fieldName,
+        const lduMatrix& matrix,
+        const Field<Field<scalar>>& interfaceBouCoeffs,
+        const Field<Field<scalar>>& interfaceIntCoeffs,
+        const lduInterfaceFieldPtrsList& interfaces
+    )
+    :
+        lduMatrix::smoother
+        (
+            fieldName,
+            matrix,
+            interfaceBouCoeffs,
+            interfaceIntCoeffs,
+            interfaces
+        ),
+        e_(B200::entryFor(matrix, interfaces))
+    {
+        B200::uploadCoeffs
+        (
+            e_, matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces
+        );
+    }
+
+    virtual void smooth
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt,
+        const label nSweeps
+    ) const
+    {
+        B200::check
+        (
+            b200ls_smooth(e_.matrix, Kind, psi.begin(), source.begin(), nSweeps),
+            "b200ls_smooth"
+        );
+    }
+};
+
+#define B200_SMOOTHER(ClassName, Kind, Name)                                   \
+    class ClassName                                                            \
+    :                                                                          \
+        public B200Smoother<Kind>                                              \
+    {                                                                          \
+    public:                                                                    \
+        TypeName(Name);                                                        \
+        using B200Smoother<Kind>::B200Smoother;                                \
+    }
+
+B200_SMOOTHER(B200GaussSeidelSmoother, B200LS_GAUSS_SEIDEL, "B200GaussSeidel");
+B200_SMOOTHER
+(
+    B200symGaussSeidelSmoother, B200LS_SYM_GAUSS_SEIDEL, "B200symGaussSeidel"
+);
+B200_SMOOTHER(B200DICSmoother, B200LS_DIC, "B200DIC");
+B200_SMOOTHER(B200DILUSmoother, B200LS_DILU, "B200DILU");
+B200_SMOOTHER
+(
+    B200DICGaussSeidelSmoother, B200LS_DIC_GAUSS_SEIDEL, "B200DICGaussSeidel"
+);
+B200_SMOOTHER
+(
+    B200DILUGaussSeidelSmoother, B200LS_DILU_GAUSS_SEIDEL, "B200DILUGaussSeidel"
+);
+
+
+// ---------------------------------------------------------------------------
 // run-time selection
 // ---------------------------------------------------------------------------
 
@@ -641,5 +817,44 @@ lduMatrix::solver::addsymMatrixConstructorToTable<B200GAMG>
     addB200GAMGSymMatrixConstructorToTable_;
 lduMatrix::solver::addasymMatrixConstructorToTable<B200GAMG>
     addB200GAMGAsymMatrixConstructorToTable_;
+
+// preconditioners and smoothers register in the tables the reference's own
+// DIC/DILU/GaussSeidel use (DICPreconditioner.C:34-36, DILUPreconditioner.C:34-36,
+// GaussSeidelSmoother.C:34-38, DICSmoother.C:34-35, DILUSmoother.C:34-35)
+defineTypeNameAndDebug(B200DICPreconditioner, 0);
+lduMatrix::preconditioner::addsymMatrixConstructorToTable<B200DICPreconditioner>
+    addB200DICPreconditionerSymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200DILUPreconditioner, 0);
+lduMatrix::preconditioner::addasymMatrixConstructorToTable<B200DILUPreconditioner>
+    addB200DILUPreconditionerAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200GaussSeidelSmoother, 0);
+lduMatrix::smoother::addsymMatrixConstructorToTable<B200GaussSeidelSmoother>
+    addB200GaussSeidelSmootherSymMatrixConstructorToTable_;
+lduMatrix::smoother::addasymMatrixConstructorToTable<B200GaussSeidelSmoother>
+    addB200GaussSeidelSmootherAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200symGaussSeidelSmoother, 0);
+lduMatrix::smoother::addsymMatrixConstructorToTable<B200symGaussSeidelSmoother>
+    addB200symGaussSeidelSmootherSymMatrixConstructorToTable_;
+lduMatrix::smoother::addasymMatrixConstructorToTable<B200symGaussSeidelSmoother>
+    addB200symGaussSeidelSmootherAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200DICSmoother, 0);
+lduMatrix::smoother::addsymMatrixConstructorToTable<B200DICSmoother>
+    addB200DICSmootherSymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200DILUSmoother, 0);
+lduMatrix::smoother::addasymMatrixConstructorToTable<B200DILUSmoother>
+    addB200DILUSmootherAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200DICGaussSeidelSmoother, 0);
+lduMatrix::smoother::addsymMatrixConstructorToTable<B200DICGaussSeidelSmoother>
+    addB200DICGaussSeidelSmootherSymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200DILUGaussSeidelSmoother, 0);
+lduMatrix::smoother::addasymMatrixConstructorToTable<B200DILUGaussSeidelSmoother>
+    addB200DILUGaussSeidelSmootherAsymMatrixConstructorToTable_;
 
 } // End namespace Foam

@@ -50,3 +50,46 @@ def test_reference_selects_b200_solvers_by_name(name, tmp_path):
             assert abs(got[1] - want[1]) <= 1e-9 * abs(want[0]), ctx
             assert max_rel_diff(out[f"solve.{i}.psi"], ref[f"solve.{i}.psi"]) <= 1e-9, ctx
             assert got[3] == want[3], ctx
+
+
+@pytest.mark.parametrize("name", ["block_16x16x16_rand", "convdiff_9x8x7", "cyclic_xz_9x8x7_rand"])
+def test_reference_loops_with_b200_preconditioners_and_smoothers(name, tmp_path):
+    """Operator-level drop-ins: the reference keeps ITS solver loop (PCG / PBiCGStab / GAMG /
+    smoothSolver, on the CPU) and selects `preconditioner B200DIC|B200DILU` or `smoother B200<name>` from its
+    preconditioner / smoother tables.  The GPU operators are bit-exact, so every result must EQUAL the all-reference
+    run bit for bit."""
+    if not HARNESS.exists() or not PLUGIN.exists():
+        pytest.skip("oracle/_ref or the plugin was not built (needs /root/reference at build time)")
+    inp, ref = load_fixture(name)
+    e = {k: v for k, v in inp.items() if not k.startswith(("solve.", "agglomerate"))}
+    e["libs"] = f'"{PLUGIN}"'
+    i = 0
+    while f"smooth.{i}.dict" in inp:
+        e[f"smooth.{i}.dict"] = ldu_io.as_str(inp[f"smooth.{i}.dict"]).replace("smoother ", "smoother B200")
+        i += 1
+    n_smooth = i
+    assert n_smooth > 0
+    picked = []
+    for i, text in solve_keys(inp):
+        if "preconditioner {" in text or "nPreSweeps" in text:
+            continue
+        t = text.replace("preconditioner DIC", "preconditioner B200DIC").replace("preconditioner DILU",
+                                                                                 "preconditioner B200DILU")
+        t = t.replace("smoother ", "smoother B200")
+        if t != text:
+            e[f"solve.{len(picked)}.dict"] = t
+            picked.append((i, t))
+    assert len(picked) >= 5
+    ldu_io.write(str(tmp_path / "in.b2ls"), e)
+    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle/foam_env"), WM_PROJECT="OpenFOAM",
+               WM_PROJECT_VERSION="dev")
+    r = subprocess.run([str(HARNESS), str(tmp_path / "in.b2ls"), str(tmp_path / "out.b2ls"), str(tmp_path / "case")],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = ldu_io.read(str(tmp_path / "out.b2ls"))
+    for i in range(n_smooth):
+        assert np.array_equal(out[f"smooth.{i}.psi"], ref[f"smooth.{i}.psi"]), (name, e[f"smooth.{i}.dict"])
+    for k, (i, t) in enumerate(picked):
+        got, want = out[f"solve.{k}.perf"], ref[f"solve.{i}.perf"]
+        assert np.array_equal(got[:5], want[:5]), (name, t, got[:5], want[:5])
+        assert np.array_equal(out[f"solve.{k}.psi"], ref[f"solve.{i}.psi"]), (name, t)
