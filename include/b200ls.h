@@ -91,7 +91,23 @@ enum b200ls_i32_which {
     B200LS_FACE_FLIP_MAP = 9,       /* ::faceFlipMap(level) widened to int32 0/1         */
     B200LS_LOWER_ADDR = 10,         /* meshLevel(level).lduAddr().lowerAddr()            */
     B200LS_UPPER_ADDR = 11,         /* meshLevel(level).lduAddr().upperAddr()            */
-    B200LS_LEVEL_SIZES = 12         /* {nCells, nFaces} of meshLevel(level)              */
+    B200LS_LEVEL_SIZES = 12,        /* {nCells, nFaces} of meshLevel(level)              */
+    /* native device layout, exposed for the host-logic tests: rows live at "positions" */
+    B200LS_PERM = 13,               /* position -> cell (forward-wavefront-major)        */
+    B200LS_LPTR = 14,               /* CSR of the neighbour-side (lower) triangle, by position */
+    B200LS_LCOL = 15,               /*   column = position of the coupled row            */
+    B200LS_LFACE = 16,              /*   face of each entry                              */
+    B200LS_UPTR = 17,               /* CSR of the owner-side (upper) triangle            */
+    B200LS_UCOL = 18,
+    B200LS_UFACE = 19,
+    /* streamed sweep plans of structured blocks (empty arrays when the level has none): part offsets in steps,
+     * records {pos, ebase, ext0, ext1} per (step, lane), dependency descriptors per (step, lane) */
+    B200LS_STREAM_FWD_PART_START = 20,
+    B200LS_STREAM_FWD_REC = 21,
+    B200LS_STREAM_FWD_META = 22,
+    B200LS_STREAM_BWD_PART_START = 23,
+    B200LS_STREAM_BWD_REC = 24,
+    B200LS_STREAM_BWD_META = 25
 };
 /* level 0 = the finest mesh; level k>0 = k-th coarse mesh (= reference meshLevel(k)).
  * RESTRICT_ADDRESSING / FACE_RESTRICT_ADDRESSING / FACE_FLIP_MAP at `level` map level -> level+1,

@@ -326,6 +326,30 @@ int b200ls_mesh_get_i32(b200ls_mesh_t mesh, int which, int level, const int32_t*
             case B200LS_FACE_FLIP_MAP: v = &L.faceFlip; break;
             case B200LS_LOWER_ADDR: v = &L.lower; break;
             case B200LS_UPPER_ADDR: v = &L.upper; break;
+            case B200LS_PERM: v = &L.perm; break;
+            case B200LS_LPTR: v = &L.Lptr; break;
+            case B200LS_LCOL: v = &L.Lcol; break;
+            case B200LS_LFACE: v = &L.Lface; break;
+            case B200LS_UPTR: v = &L.Uptr; break;
+            case B200LS_UCOL: v = &L.Ucol; break;
+            case B200LS_UFACE: v = &L.Uface; break;
+            case B200LS_STREAM_FWD_PART_START: v = &L.fwdStream.partStart; break;
+            case B200LS_STREAM_BWD_PART_START: v = &L.bwdStream.partStart; break;
+            case B200LS_STREAM_FWD_REC:
+            case B200LS_STREAM_BWD_REC: {
+                const auto& r = which == B200LS_STREAM_FWD_REC ? L.fwdStream.rec : L.bwdStream.rec;
+                static_assert(sizeof(StreamRec) == 4 * sizeof(int32_t), "StreamRec layout");
+                *data = reinterpret_cast<const int32_t*>(r.data());
+                *n = int64_t(r.size()) * 4;
+                return;
+            }
+            case B200LS_STREAM_FWD_META:
+            case B200LS_STREAM_BWD_META: {
+                const auto& r = which == B200LS_STREAM_FWD_META ? L.fwdStream.meta : L.bwdStream.meta;
+                *data = reinterpret_cast<const int32_t*>(r.data());
+                *n = int64_t(r.size());
+                return;
+            }
             case B200LS_LEVEL_SIZES:
                 sizes = {L.nCells, L.nFaces};
                 v = &sizes;

@@ -58,7 +58,8 @@ struct DevBuf {
         if (count == n && p) return;
         release();
         n = count;
-        if (count) B2_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        // 16 bytes of slack: the streamed sweeps prefetch aligned 16-byte pairs of doubles
+        if (count) B2_CUDA(cudaMalloc(&p, count * sizeof(T) + 16));
     }
     void upload(const std::vector<T>& h, cudaStream_t s) {
         alloc(h.size());
@@ -136,6 +137,13 @@ struct DevLevel {
     std::map<int, DevBuf<int4>> multiSweepTasks;    // nSweeps -> tasks ordered by tau = level + 2*sweep
     DevBuf<int> bwdPos;
     int nFwdTasks = 0, nBwdTasks = 0;
+    // streamed sweep plans (structured blocks only)
+    bool hasStream = false;
+    int nStreamParts = 0;
+    DevBuf<int> sFwdPartStart, sBwdPartStart;
+    DevBuf<int4> sFwdRec, sBwdRec;          // {pos, ext0, ext1, meta} per (step, lane)
+    DevBuf<int> sFwdEbase, sBwdEbase;        // first CSR entry of the row (k_stream_pack)
+    size_t nStreamRec = 0;
     // interfaces
     int nIfaces = 0;
     std::vector<int> ifaceSize, ifaceNbr;

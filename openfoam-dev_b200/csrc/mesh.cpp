@@ -9,6 +9,8 @@
 #include "mesh.hpp"
 
 #include <algorithm>
+#include <array>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -178,6 +180,166 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         }
         if (!L.bRowPos.empty()) L.bRowPtr.push_back(int32_t(L.bEntryIface.size()));
     }
+
+    {
+        const char* e = getenv("B200LS_STREAM_MIN_CELLS");
+        buildStreamPlans(L, e ? int32_t(atoi(e)) : 4096);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// streamed sweep plans
+// ------------------------------------------------------------------------------------------------------------
+
+static bool detectBlock(const LevelHost& L, int32_t dims[3]) {
+    const int64_t n = L.nCells;
+    if (n < 2 || L.nFaces == 0) return false;
+    // strides of the owner-side faces of cell 0: {1, nx, nx*ny} (those that exist)
+    std::vector<int64_t> st;
+    for (int32_t f = L.ownerStart[0]; f < L.ownerStart[1]; f++) st.push_back(L.upper[f]);
+    if (st.empty() || st[0] != 1 || st.size() > 3) return false;
+    int64_t nx, ny = 1, nz = 1;
+    if (st.size() == 1) {
+        nx = n;
+    } else {
+        nx = st[1];
+        if (nx < 2 || n % nx) return false;
+        if (st.size() == 2) {
+            ny = n / nx;
+        } else {
+            if (st[2] % nx) return false;
+            ny = st[2] / nx;
+            if (ny < 2 || n % (nx * ny)) return false;
+            nz = n / (nx * ny);
+        }
+    }
+    if (nx * ny * nz != n) return false;
+    const int64_t expectFaces = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1);
+    if (expectFaces != L.nFaces) return false;
+    int64_t f = 0;
+    for (int64_t k = 0; k < nz; k++)
+        for (int64_t j = 0; j < ny; j++)
+            for (int64_t i = 0; i < nx; i++) {
+                const int64_t c = i + nx * (j + ny * k);
+                if (i < nx - 1) { if (L.lower[f] != c || L.upper[f] != c + 1) return false; f++; }
+                if (j < ny - 1) { if (L.lower[f] != c || L.upper[f] != c + nx) return false; f++; }
+                if (k < nz - 1) { if (L.lower[f] != c || L.upper[f] != c + nx * ny) return false; f++; }
+            }
+    dims[0] = int32_t(nx);
+    dims[1] = int32_t(ny);
+    dims[2] = int32_t(nz);
+    return true;
+}
+
+// parts[part][step][lane] = position or -1; dependencies from the CSR (ptr, col) in positions, processed in
+// ascending (desc = false) or descending entry order.  Fails (plan.valid = false) if a row has more than three
+// dependencies / more than two external ones, or if an external producer is not earlier in the launch order.
+static void emitStreamPlan(const std::vector<std::vector<std::array<int32_t, 32>>>& parts, int32_t nRows,
+                           const std::vector<int32_t>& ptr, const std::vector<int32_t>& col, bool desc,
+                           StreamPlan& plan) {
+    plan = StreamPlan();
+    std::vector<int32_t> wPart(nRows, -1), wStep(nRows, -1), wLane(nRows, -1);
+    plan.partStart.assign(1, 0);
+    for (size_t P = 0; P < parts.size(); P++) {
+        for (size_t s = 0; s < parts[P].size(); s++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int32_t pos = parts[P][s][lane];
+                if (pos < 0) continue;
+                if (wPart[pos] >= 0) return;   // a row scheduled twice
+                wPart[pos] = int32_t(P);
+                wStep[pos] = int32_t(s);
+                wLane[pos] = lane;
+            }
+        plan.partStart.push_back(plan.partStart.back() + int32_t(parts[P].size()));
+    }
+    for (int32_t p = 0; p < nRows; p++)
+        if (wPart[p] < 0) return;              // a row not scheduled
+    const size_t total = size_t(plan.partStart.back()) * 32;
+    plan.rec.assign(total, StreamRec{-1, 0, -1, -1});
+    plan.meta.assign(total, 0u);
+    for (size_t P = 0; P < parts.size(); P++)
+        for (size_t s = 0; s < parts[P].size(); s++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int32_t pos = parts[P][s][lane];
+                if (pos < 0) continue;
+                const size_t r = (size_t(plan.partStart[P]) + s) * 32 + size_t(lane);
+                StreamRec& R = plan.rec[r];
+                R.pos = pos;
+                R.ebase = ptr[pos];
+                const int32_t nd = ptr[pos + 1] - ptr[pos];
+                if (nd > 3) return;
+                uint32_t m = uint32_t(nd);
+                int nExt = 0;
+                for (int32_t k = 0; k < nd; k++) {
+                    const int32_t e = desc ? ptr[pos + 1] - 1 - k : ptr[pos] + k;
+                    const int32_t q = col[e];
+                    uint32_t field;
+                    if (wPart[q] == int32_t(P) && wStep[q] == int32_t(s) - 1) {
+                        field = uint32_t(wLane[q]) << 1;
+                    } else {
+                        const bool earlier = wPart[q] < int32_t(P) || (wPart[q] == int32_t(P) && wStep[q] < int32_t(s));
+                        if (!earlier || nExt == 2) return;
+                        (nExt == 0 ? R.ext0 : R.ext1) = q;
+                        field = 1u | (uint32_t(nExt) << 1);
+                        nExt++;
+                    }
+                    m |= field << (3 + 6 * k);
+                }
+                plan.meta[r] = m;
+            }
+    plan.nParts = int32_t(parts.size());
+    plan.valid = true;
+}
+
+void buildStreamPlans(LevelHost& L, int32_t minCells) {
+    L.fwdStream = StreamPlan();
+    L.bwdStream = StreamPlan();
+    L.blockDims[0] = L.blockDims[1] = L.blockDims[2] = 0;
+    int32_t d[3];
+    if (L.nCells < minCells || !detectBlock(L, d)) return;
+    const int32_t nx = d[0], ny = d[1], nz = d[2];
+    // tile of pencils (lines along i) owned by one warp: lane = jj + TJ*kk
+    const int32_t TK = nz >= 4 ? 4 : (nz >= 2 ? 2 : 1);
+    const int32_t TJ = 32 / TK;
+    const int32_t nJ = (ny + TJ - 1) / TJ, nK = (nz + TK - 1) / TK;
+    // launch order of the parts: tile wavefronts J + K (every tile depends on (J-1, K) and (J, K-1))
+    std::vector<std::pair<int32_t, int32_t>> tiles;
+    for (int32_t w = 0; w <= nJ + nK - 2; w++)
+        for (int32_t K = 0; K < nK; K++) {
+            const int32_t J = w - K;
+            if (J >= 0 && J < nJ) tiles.emplace_back(J, K);
+        }
+    std::vector<std::vector<std::array<int32_t, 32>>> fwd(tiles.size()), bwd(tiles.size());
+    for (size_t t = 0; t < tiles.size(); t++) {
+        const int32_t J = tiles[t].first, K = tiles[t].second;
+        const int32_t jn = std::min(TJ, ny - J * TJ), kn = std::min(TK, nz - K * TK);
+        const int32_t S = nx + (jn - 1) + (kn - 1);
+        auto& F = fwd[t];
+        F.resize(size_t(S));
+        for (int32_t s = 0; s < S; s++) {
+            F[s].fill(-1);
+            for (int32_t kk = 0; kk < kn; kk++)
+                for (int32_t jj = 0; jj < jn; jj++) {
+                    const int32_t i = s - jj - kk;
+                    if (i < 0 || i >= nx) continue;
+                    const int64_t c = i + int64_t(nx) * ((J * TJ + jj) + int64_t(ny) * (K * TK + kk));
+                    F[s][jj + TJ * kk] = L.ipos[size_t(c)];
+                }
+        }
+        // the backward sweep walks the same part from its last step to its first, parts in reverse order
+        auto& B = bwd[tiles.size() - 1 - t];
+        B.assign(F.rbegin(), F.rend());
+    }
+    emitStreamPlan(fwd, L.nCells, L.Lptr, L.Lcol, false, L.fwdStream);
+    emitStreamPlan(bwd, L.nCells, L.Uptr, L.Ucol, true, L.bwdStream);
+    if (!L.fwdStream.valid || !L.bwdStream.valid) {
+        L.fwdStream = StreamPlan();
+        L.bwdStream = StreamPlan();
+        return;
+    }
+    L.blockDims[0] = nx;
+    L.blockDims[1] = ny;
+    L.blockDims[2] = nz;
 }
 
 std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fine,

@@ -42,6 +42,29 @@ struct AgglomMaps {
     std::vector<std::vector<int32_t>> iPtr, iSrc;
 };
 
+// Streamed sweep plan (structured hex blocks): the rows are partitioned into PARTS of <=32 "pencils" (lines of cells
+// along the fastest index); one warp owns a part and walks it step by step, lane = pencil.  A dependency produced
+// by the same warp in the previous step is read from a shared-memory ring (no L2 round trip); every other
+// dependency is "external": its producer belongs to a part earlier in the launch order (or to an earlier step of
+// the same part) and is polled from global memory -- prefetched several steps ahead, which works because a part
+// naturally lags the parts it depends on.  Arithmetic and its order per row are those of the wavefront kernels.
+struct StreamRec {
+    int32_t pos;      // row position handled by this lane in this step, -1 = idle
+    int32_t ebase;    // first entry of the row in the triangle's CSR value array
+    int32_t ext0;     // positions of up to two external dependencies (-1 = none)
+    int32_t ext1;
+};
+struct StreamPlan {
+    bool valid = false;
+    int32_t nParts = 0;
+    std::vector<int32_t> partStart;   // [nParts + 1], in steps; record index = step*32 + lane
+    std::vector<StreamRec> rec;
+    // bits 0-2: number of dependencies nd (<= 3), in processing order n = 0..nd-1 (forward: ascending CSR
+    // entries; backward: descending).  Dependency n: bit 3+6n = 1 if external, bits 4+6n .. 8+6n = source lane
+    // (internal) or external slot 0/1.
+    std::vector<uint32_t> meta;
+};
+
 struct LevelHost {
     int32_t nCells = 0, nFaces = 0;
     std::vector<int32_t> lower, upper;                      // reference face order
@@ -57,6 +80,10 @@ struct LevelHost {
     std::vector<int32_t> Lidx, Uidx;          // face -> entry index in the L / U arrays
     std::vector<SweepTask> fwdTasks, bwdTasks;
     std::vector<int32_t> bwdPos;    // backward processing order -> position
+
+    // ---- streamed sweeps (empty unless the addressing is a structured block, see buildStreamPlans) ----
+    int32_t blockDims[3] = {0, 0, 0};
+    StreamPlan fwdStream, bwdStream;
 
     std::vector<HostInterface> interfaces;
     // rows touched by interfaces: boundary-row CSR in (patch, face) order
@@ -89,6 +116,10 @@ struct HostMesh {
 // Throws std::runtime_error on invalid input (not upper-triangular ordered, out-of-range labels).
 void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
                 std::vector<HostInterface> interfaces);
+
+// Detects an nx*ny*nz hex block numbered i-fastest (blockMesh single block) and builds the streamed sweep plans
+// for it; leaves them invalid otherwise.  minCells: do not bother below this size.
+void buildStreamPlans(LevelHost& L, int32_t minCells);
 
 // pairGAMGAgglomeration::agglomerate(nCoarseCells, addressing, weights) (pairGAMGAgglomerate.C:123-301).
 // `forward` is the reference's static forward_ flag: read, used, and toggled.

@@ -95,6 +95,34 @@ static void launchSweep(K kernel, SweepArgs& a) {
     c.launches++;
 }
 
+// Streamed sweeps: one loader/compute warp pair per part, all resident at once (cooperative launch guarantees co-residency of the grid,
+// which the cross-part polling needs).
+template <typename K>
+static void launchStream(K kernel, StreamArgs& a) {
+    if (a.nParts == 0) return;
+    static std::map<const void*, int> occCache;
+    Context& c = ctx();
+    const size_t smem = sizeof(StreamSmem);
+    int occ;
+    auto it = occCache.find((const void*)kernel);
+    if (it == occCache.end()) {
+        B2_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 64, smem));
+        occCache[(const void*)kernel] = occ;
+    } else {
+        occ = it->second;
+    }
+    if (occ < 1) throw CudaError("streamed sweep kernel does not fit on an SM");
+    const int blocks = std::max(1, std::min(occ * c.numSMs, a.nParts));
+    a.err = c.errFlag.p;
+    a.partials = c.partials.p;
+    a.ticket = c.ticket.p;
+    void* args[] = {&a};
+    B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(64), args, smem,
+                                        c.stream));
+    c.launches++;
+}
+
 void checkSweepError() {
     Context& c = ctx();
     int h = 0;
@@ -157,6 +185,26 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         D.hasLslot = fits && H.nFaces > 0;
         if (D.hasLslot) D.Lslot.upload(slot, s);
         B2_CUDA(cudaStreamSynchronize(s));   // ltou/slot are temporaries
+    }
+    // streamed sweep plans of structured blocks
+    D.hasStream = H.fwdStream.valid && H.bwdStream.valid;
+    D.nStreamParts = D.hasStream ? H.fwdStream.nParts : 0;
+    if (D.hasStream) {
+        D.sFwdPartStart.upload(H.fwdStream.partStart, s);
+        D.sBwdPartStart.upload(H.bwdStream.partStart, s);
+        D.nStreamRec = H.fwdStream.rec.size();
+        for (int dir = 0; dir < 2; dir++) {
+            const StreamPlan& pl = dir ? H.bwdStream : H.fwdStream;
+            std::vector<int4> rec(pl.rec.size());
+            std::vector<int> eb(pl.rec.size());
+            for (size_t i = 0; i < pl.rec.size(); i++) {
+                rec[i] = make_int4(pl.rec[i].pos, pl.rec[i].ext0, pl.rec[i].ext1, int(pl.meta[i]));
+                eb[i] = pl.rec[i].ebase;
+            }
+            (dir ? D.sBwdRec : D.sFwdRec).upload(rec, s);
+            (dir ? D.sBwdEbase : D.sFwdEbase).upload(eb, s);
+            B2_CUDA(cudaStreamSynchronize(s));
+        }
     }
     static_assert(sizeof(SweepTask) == sizeof(int2), "task layout");
     D.nFwdTasks = int(H.fwdTasks.size());
@@ -582,6 +630,7 @@ void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
     const int kind = (precond == B200LS_DIAGONAL) ? B200LS_DIAGONAL : B200LS_DIC;   // DIC and DILU share rD
     if (M.rDValid && M.rDKind == kind) return;
     M.rDKind = kind;
+    M.sPackValid = false;
     M.rD.alloc(D.nCells);
     if (precond == B200LS_DIAGONAL) {
         // rD = 1/diag (diagonalPreconditioner.C:59-62)
@@ -631,6 +680,44 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
     if (!M.tmpASentinel) {
         fillSentinel(M.tmpA.p, n);
         M.tmpASentinel = true;
+    }
+    static const bool noStream = getenv("B200LS_NO_STREAM") != nullptr;
+    if (D.hasStream && !noStream) {
+        // structured block: warp-owned pencil tiles, dependencies through shared memory (k_stream_sweep)
+        if (!M.sPackValid) {
+            // once per factorisation: coefficients in stream order, pre-multiplied by rD
+            M.sFwdPack.alloc(D.nStreamRec * 4);
+            M.sBwdPack.alloc(D.nStreamRec * 4);
+            const int grid = int(std::min<size_t>((D.nStreamRec + 255) / 256, size_t(8) * ctx().numSMs));
+            LAUNCH(k_stream_pack, grid, 256, M.sFwdPack.p, D.sFwdRec.p, D.sFwdEbase.p, M.rD.p, M.Lval(D.nFaces),
+                   D.nStreamRec, 0);
+            LAUNCH(k_stream_pack, grid, 256, M.sBwdPack.p, D.sBwdRec.p, D.sBwdEbase.p, M.rD.p, M.Uval(),
+                   D.nStreamRec, 1);
+            M.sPackValid = true;
+        }
+        StreamArgs f{};
+        f.partStart = D.sFwdPartStart.p;
+        f.nParts = D.nStreamParts;
+        f.rec = D.sFwdRec.p;
+        f.pack = M.sFwdPack.p;
+        f.in = rA;
+        f.out = M.tmpA.p;
+        f.clear = wA;
+        launchStream(k_stream_sweep<false>, f);
+        StreamArgs b{};
+        b.partStart = D.sBwdPartStart.p;
+        b.nParts = D.nStreamParts;
+        b.rec = D.sBwdRec.p;
+        b.pack = M.sBwdPack.p;
+        b.in = M.tmpA.p;
+        b.out = wA;
+        b.clear = M.tmpA.p;
+        if (dotOut) {
+            b.dotWith = rA;
+            b.dotOut = dotOut;
+        }
+        launchStream(k_stream_sweep<true>, b);
+        return;
     }
     SweepArgs f{};
     f.tasks = D.fwdTasks.p;

@@ -12,6 +12,8 @@ struct MatLevel {
     DevBuf<double> vals;            // [Uval (nFaces) | Lval (nFaces)]
     DevBuf<double> rD;              // DIC/DILU reciprocal diagonal
     bool rDValid = false;
+    b200ls::DevBuf<double> sFwdPack, sBwdPack;   // streamed sweeps: {rD, rD*c} in stream order (valid with rD)
+    bool sPackValid = false;
     int rDKind = -1;                // which preconditioner rD belongs to (DIC/DILU vs diagonal)
     DevBuf<double> dWork;           // factorisation scratch (pre-reciprocal diagonal, sentinel protocol)
     // interfaces: coefficients, send/recv buffers
