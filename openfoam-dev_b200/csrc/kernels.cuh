@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
 #define B200LS_STREAM_R 16
 #endif
 #ifndef B200LS_STREAM_E
-#define B200LS_STREAM_E 8
+#define B200LS_STREAM_E 4
 #endif
 static constexpr int kStreamR = B200LS_STREAM_R;   // stages of the shared-memory ring (power of two)
 static constexpr int kStreamG = 4;                 // stages handed over per mbarrier phase

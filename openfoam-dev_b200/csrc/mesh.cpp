@@ -181,9 +181,15 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         if (!L.bRowPos.empty()) L.bRowPtr.push_back(int32_t(L.bEntryIface.size()));
     }
 
-    {
-        const char* e = getenv("B200LS_STREAM_MIN_CELLS");
-        buildStreamPlans(L, e ? int32_t(atoi(e)) : 4096);
+    // streamed sweeps are experimental (slower than the wavefront kernels so far, profiles/experiments/README.md):
+    // plans are only built on request
+    L.fwdStream = StreamPlan();
+    L.bwdStream = StreamPlan();
+    if (const char* on = getenv("B200LS_STREAM")) {
+        if (on[0] == '1') {
+            const char* e = getenv("B200LS_STREAM_MIN_CELLS");
+            buildStreamPlans(L, e ? int32_t(atoi(e)) : 4096);
+        }
     }
 }
 

@@ -681,8 +681,9 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
         fillSentinel(M.tmpA.p, n);
         M.tmpASentinel = true;
     }
-    static const bool noStream = getenv("B200LS_NO_STREAM") != nullptr;
-    if (D.hasStream && !noStream) {
+    // experimental (profiles/experiments/README.md): opt-in until it beats the wavefront kernel
+    const char* streamEnv = getenv("B200LS_STREAM");
+    if (D.hasStream && streamEnv && streamEnv[0] == '1') {
         // structured block: warp-owned pencil tiles, dependencies through shared memory (k_stream_sweep)
         if (!M.sPackValid) {
             // once per factorisation: coefficients in stream order, pre-multiplied by rD

@@ -22,6 +22,7 @@ int main(int argc, char** argv) {
         if (k < N - 1) { lo.push_back(c); up.push_back(c + N * N); }
     }
     LevelHost L;
+    setenv("B200LS_STREAM", "1", 1);
     setenv("B200LS_STREAM_MIN_CELLS", "0", 1);
     buildLevel(L, N * N * N, int(lo.size()), lo.data(), up.data(), {});
     if (!L.fwdStream.valid) { printf("no plan\n"); return 1; }

@@ -156,6 +156,7 @@ def test_streamed_sweeps_of_structured_blocks_bit_exact(shape, sym, monkeypatch)
     """k_stream_sweep (warp-owned pencil tiles; structured blocks only) against the C oracle: precondition bit for
     bit -- twice, so that the sentinel re-arming between calls is exercised -- and a PCG / PBiCGStab solve."""
     monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
+    monkeypatch.setenv("B200LS_STREAM", "1")
     nx, ny, nz = shape
     s = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if sym else \
         cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)

@@ -302,6 +302,7 @@ def test_stream_plan_reproduces_the_precondition_bit_for_bit(shape, sym, monkeyp
     _sys.path.insert(0, str(ROOT / "oracle"))
     import ldu_oracle as orc
 
+    monkeypatch.setenv("B200LS_STREAM", "1")
     monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
     nx, ny, nz = shape
     s = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if sym else cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
@@ -313,6 +314,7 @@ def test_stream_plan_reproduces_the_precondition_bit_for_bit(shape, sym, monkeyp
 
 
 def test_no_stream_plan_for_unstructured_addressing(monkeypatch):
+    monkeypatch.setenv("B200LS_STREAM", "1")
     monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
     s = cases.random_graph(300, symmetric=True)
     mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
@@ -321,3 +323,6 @@ def test_no_stream_plan_for_unstructured_addressing(monkeypatch):
     lower, upper, _ = cases.block_addressing(6, 5, 4)
     mesh = capi.Mesh(120, np.delete(lower, 17), np.delete(upper, 17))
     assert mesh.get_i32(20, 0).size == 0
+    # and nothing is built unless asked for
+    monkeypatch.delenv("B200LS_STREAM")
+    assert capi.Mesh(120, lower, upper).get_i32(20, 0).size == 0
