@@ -38,6 +38,9 @@
 #include "b200ls.h"
 
 #include <map>
+#include <string>
+#include <cstdio>
+#include "OStringStream.H"
 #include <vector>
 #include <cstdlib>
 #include <cstdint>
@@ -793,6 +796,213 @@ B200_SMOOTHER
 
 
 // ---------------------------------------------------------------------------
+// B200dump: pass-through solver that serialises the system it receives at the
+// drop-in boundary (SURVEY.md 8(c) "capturing real matrices at the boundary")
+// and then delegates to the reference solver named by `delegate`:
+//     p { solver B200dump; delegate PCG; dumpFile "p"; preconditioner DIC; ... }
+// writes <dumpFile>.<n>.b2ls (addressing, coefficients, coupled patches, psi0,
+// source; format: openfoam-dev_b200/ldu_io.py), which replays through
+// oracle/ref_harness, the C oracle and the GPU path alike.  Uses no GPU.
+// ---------------------------------------------------------------------------
+
+class B200dump
+:
+    public lduMatrix::solver
+{
+    struct writer
+    {
+        FILE* f_;
+        std::vector<std::pair<std::string, std::vector<char>>> entries_;
+        std::vector<std::pair<int64_t, int64_t>> types_;
+
+        void put(const std::string& name, int64_t dtype, int64_t count, const void* data, size_t bytes)
+        {
+            entries_.push_back
+            (
+                std::make_pair
+                (
+                    name,
+                    std::vector<char>
+                    (
+                        static_cast<const char*>(data),
+                        static_cast<const char*>(data) + bytes
+                    )
+                )
+            );
+            types_.push_back(std::make_pair(dtype, count));
+        }
+        void putI32(const std::string& name, const labelUList& l)
+        {
+            std::vector<int32_t> v(l.size());
+            forAll(l, i) v[i] = l[i];
+            put(name, 0, v.size(), v.data(), v.size()*4);
+        }
+        void putI32(const std::string& name, const int32_t x)
+        {
+            put(name, 0, 1, &x, 4);
+        }
+        void putF64(const std::string& name, const scalarField& s)
+        {
+            put(name, 1, s.size(), s.begin(), size_t(s.size())*8);
+        }
+        void putStr(const std::string& name, const std::string& s)
+        {
+            put(name, 2, s.size(), s.data(), s.size());
+        }
+        bool write(const std::string& path)
+        {
+            FILE* f = fopen(path.c_str(), "wb");
+            if (!f) return false;
+            fwrite("B2LS0001", 1, 8, f);
+            int64_t n = entries_.size();
+            fwrite(&n, 8, 1, f);
+            for (size_t i = 0; i < entries_.size(); i++)
+            {
+                int64_t nameLen = entries_[i].first.size();
+                fwrite(&nameLen, 8, 1, f);
+                fwrite(entries_[i].first.data(), 1, nameLen, f);
+                fwrite(&types_[i].first, 8, 1, f);
+                fwrite(&types_[i].second, 8, 1, f);
+                if (entries_[i].second.size())
+                {
+                    fwrite(entries_[i].second.data(), 1, entries_[i].second.size(), f);
+                }
+            }
+            fclose(f);
+            return true;
+        }
+    };
+
+public:
+
+    TypeName("B200dump");
+
+    B200dump
+    (
+        const word& fieldName,
+        const lduMatrix& matrix,
+        const Field<Field<scalar>>& interfaceBouCoeffs,
+        const Field<Field<scalar>>& interfaceIntCoeffs,
+        const lduInterfaceFieldPtrsList& interfaces,
+        const dictionary& solverControls
+    )
+    :
+        lduMatrix::solver
+        (
+            fieldName,
+            matrix,
+            interfaceBouCoeffs,
+            interfaceIntCoeffs,
+            interfaces,
+            solverControls
+        )
+    {}
+
+    virtual solverPerformance solve
+    (
+        scalarField& psi,
+        const scalarField& source,
+        const direction cmpt = 0
+    ) const
+    {
+        static label nDumps = 0;
+
+        const lduAddressing& addr = matrix_.lduAddr();
+        writer w;
+        w.putI32("nCells", int32_t(addr.size()));
+        w.putI32("lower", addr.lowerAddr());
+        w.putI32("upper", addr.upperAddr());
+        w.putF64("diag", matrix_.diag());
+        w.putF64("upperCoeffs", matrix_.upper());
+        if (matrix_.asymmetric())
+        {
+            w.putF64("lowerCoeffs", matrix_.lower());
+        }
+        w.putF64("source", source);
+        w.putF64("psi0", psi);
+
+        // coupled patches, numbered among themselves as b200ls_mesh_create expects
+        std::vector<label> coupled;
+        forAll(interfaces_, patchi)
+        {
+            if (interfaces_.set(patchi)) coupled.push_back(patchi);
+        }
+        w.putI32("nIfaces", int32_t(coupled.size()));
+        for (size_t k = 0; k < coupled.size(); k++)
+        {
+            const label patchi = coupled[k];
+            const lduInterface& li = interfaces_[patchi].interface();
+            const std::string key = "iface." + std::to_string(k);
+            w.putI32(key + ".faceCells", li.faceCells());
+            w.putF64(key + ".bouCoeffs", interfaceBouCoeffs_[patchi]);
+            w.putF64(key + ".intCoeffs", interfaceIntCoeffs_[patchi]);
+            if (isA<cyclicLduInterface>(li))
+            {
+                const label nbr =
+                    refCast<const cyclicLduInterface>(li).nbrPatchIndex();
+                int32_t nbrK = -1;
+                for (size_t j = 0; j < coupled.size(); j++)
+                {
+                    if (coupled[j] == nbr) nbrK = j;
+                }
+                w.putI32(key + ".nbrPatch", nbrK);
+            }
+            else if (isA<processorLduInterface>(li))
+            {
+                w.putI32
+                (
+                    key + ".neighbProcNo",
+                    int32_t
+                    (
+                        refCast<const processorLduInterface>(li).neighbProcNo()
+                    )
+                );
+            }
+        }
+
+        // the solve as the delegate will see it
+        dictionary d(controlDict_);
+        const word delegate(controlDict_.lookup("delegate"));
+        d.set("solver", delegate);
+        d.remove("delegate");
+        d.remove("dumpFile");
+        {
+            OStringStream os;
+            d.write(os, false);
+            w.putStr("solve.0.dict", os.str());
+        }
+
+        const fileName base
+        (
+            controlDict_.lookupOrDefault<fileName>("dumpFile", fieldName_)
+        );
+        std::string path =
+            std::string(base) + "." + std::to_string(nDumps++);
+        if (Pstream::parRun())
+        {
+            path += ".proc" + std::to_string(Pstream::myProcNo());
+        }
+        path += ".b2ls";
+        if (!w.write(path))
+        {
+            FatalErrorInFunction
+                << "cannot write " << path << exit(FatalError);
+        }
+
+        return lduMatrix::solver::New
+        (
+            fieldName_,
+            matrix_,
+            interfaceBouCoeffs_,
+            interfaceIntCoeffs_,
+            interfaces_,
+            d
+        )->solve(psi, source, cmpt);
+    }
+};
+
+
+// ---------------------------------------------------------------------------
 // run-time selection
 // ---------------------------------------------------------------------------
 
@@ -817,6 +1027,12 @@ lduMatrix::solver::addsymMatrixConstructorToTable<B200GAMG>
     addB200GAMGSymMatrixConstructorToTable_;
 lduMatrix::solver::addasymMatrixConstructorToTable<B200GAMG>
     addB200GAMGAsymMatrixConstructorToTable_;
+
+defineTypeNameAndDebug(B200dump, 0);
+lduMatrix::solver::addsymMatrixConstructorToTable<B200dump>
+    addB200dumpSymMatrixConstructorToTable_;
+lduMatrix::solver::addasymMatrixConstructorToTable<B200dump>
+    addB200dumpAsymMatrixConstructorToTable_;
 
 // preconditioners and smoothers register in the tables the reference's own
 // DIC/DILU/GaussSeidel use (DICPreconditioner.C:34-36, DILUPreconditioner.C:34-36,
