@@ -242,3 +242,67 @@ def to_entries(sys_: LduSystem):
             e[f"iface.{k}.bouCoeffs"] = i.bou_coeffs.astype(np.float64)
             e[f"iface.{k}.intCoeffs"] = i.int_coeffs.astype(np.float64)
     return e
+
+
+# ---- systems on REAL meshes: geometry and addressing dumped by `ref_harness --polymesh` (the reference's own polyMesh
+# reader and geometry engine); coefficients as finiteVolume builds them -------------------------------------------
+
+def _polymesh_geometry(d):
+    n_cells, n_int, _ = (int(v) for v in d["sizes"])
+    Sf = d["faceAreas"].reshape(-1, 3)
+    Cf = d["faceCentres"].reshape(-1, 3)
+    C = d["cellCentres"].reshape(-1, 3)
+    lower, upper = d["lower"].astype(np.int32), d["upper"].astype(np.int32)
+    magSf = np.sqrt((Sf * Sf).sum(1))
+    nf = Sf / magSf[:, None]
+    # surfaceInterpolation::makeNonOrthDeltaCoeffs (finiteVolume/interpolation/surfaceInterpolation/
+    # surfaceInterpolation/surfaceInterpolation.C): 1/max(nf & delta, 0.05*mag(delta))
+    delta = C[upper] - C[lower]
+    dc = 1.0 / np.maximum((nf[:n_int] * delta).sum(1), 0.05 * np.sqrt((delta * delta).sum(1)))
+    # faceAreaPairGAMGAgglomeration.C:66-79
+    w = np.sqrt((((Sf[:n_int] / np.sqrt(magSf[:n_int])[:, None]) * np.array([1.0, 1.01, 1.02])) ** 2).sum(1))
+    patches = []
+    for i in range(int(d["nPatches"][0])):
+        name, typ = bytes(d[f"patch.{i}.nameType"].astype(np.uint8)).decode().split()
+        start, size = (int(v) for v in d[f"patch.{i}.startSize"])
+        patches.append((name, typ, start, size))
+    return n_cells, n_int, lower, upper, Sf, Cf, C, magSf, nf, dc, w, patches
+
+
+def _fixed_value_patches(patches):
+    sel = [p for p in patches if p[1] == "patch" and p[0].lower().startswith("outlet")]
+    return sel or [p for p in patches if p[1] == "patch"][:1]
+
+
+def polymesh_laplacian(d, rhs_kind="sin", seed=20261017):
+    """p-equation stand-in on a real mesh: fvm::laplacian with gamma = 1 (gaussLaplacianScheme.C:52-81:
+    upper = deltaCoeffs*magSf, negSumDiag), zeroGradient everywhere except fixedValue 0 on the outlet patch(es), whose
+    internalCoeffs = -magSf*deltaCoeffs go into the diagonal (fvMatrix::addBoundaryDiag, fvMatrix.C:112-131)."""
+    n, n_int, lower, upper, Sf, Cf, C, magSf, nf, dc, w, patches = _polymesh_geometry(d)
+    up = dc * magSf[:n_int]
+    diag = negsum_diag(n, lower, upper, up, None)
+    own = d["faceOwner"]
+    for name, typ, start, size in _fixed_value_patches(patches):
+        f = np.arange(start, start + size)
+        db = Cf[f] - C[own[f]]
+        dcb = 1.0 / np.maximum((nf[f] * db).sum(1), 0.05 * np.sqrt((db * db).sum(1)))
+        np.add.at(diag, own[f], -(magSf[f] * dcb))
+    return LduSystem(n_cells=n, lower=lower, upper=upper, diag=diag, upper_coeffs=up, source=rhs(n, rhs_kind, seed + 1),
+                     face_weights=w)
+
+
+def polymesh_convection_diffusion(d, nu=0.01, rhs_kind="sin", seed=20261017):
+    """U/k/epsilon stand-in on a real mesh: upwind convection of a smooth velocity field + diffusion + an implicit
+    time-derivative term (gaussConvectionScheme.C:140-142, gaussLaplacianScheme.C:52-81, EulerDdtScheme)."""
+    n, n_int, lower, upper, Sf, Cf, C, magSf, nf, dc, w, patches = _polymesh_geometry(d)
+    x, y = Cf[:n_int, 0], Cf[:n_int, 1]
+    span = max(np.ptp(C[:, 0]), np.ptp(C[:, 1]), 1e-30)
+    U = np.stack([1.0 + 0.3 * np.sin(3.0 * y / span), 0.2 * np.cos(2.0 * x / span), 0.1 * np.ones(n_int)], axis=1)
+    phi = (U * Sf[:n_int]).sum(1)
+    diff = nu * span * dc * magSf[:n_int]
+    lo = -np.maximum(phi, 0.0) - diff
+    up = np.minimum(phi, 0.0) - diff
+    vol = d["cellVolumes"]
+    diag = negsum_diag(n, lower, upper, up, lo) + vol / (0.05 * span)
+    return LduSystem(n_cells=n, lower=lower, upper=upper, diag=diag, upper_coeffs=up, lower_coeffs=lo,
+                     source=rhs(n, rhs_kind, seed + 1) * vol, face_weights=w)

@@ -25,6 +25,12 @@
       callers (Amul/residual/sumA/smoothers/solvers/GAMG) are the reference's.  This is the
       serial pin for the interface code that processor patches share.
 
+    * `ref_harness --polymesh <caseDir> <out.b2ls>`: reads constant/polyMesh of a real case with the reference's
+      polyMesh and writes what the synthetic generators need to build p-/U-like systems on it: LDU addressing
+      (faceOwner/faceNeighbour of the internal faces), face area vectors, cell and face centres (the reference's own
+      geometry engine, meshes/primitiveMesh/primitiveMeshFaceCentresAndAreas.C, ...CellCentresAndVols.C), cell
+      volumes and the boundary patches (name, type, start, size, faceCells).
+
   One mesh per process: pairGAMGAgglomeration::forward_ is a process-global static.
 
   File formats are documented in openfoam-dev_b200/ldu_io.py.
@@ -46,6 +52,7 @@
 #include "OSspecific.H"
 #include "clockTime.H"
 #include "dlLibraryTable.H"
+#include "polyMesh.H"
 
 #include <cstdio>
 #include <cstdint>
@@ -423,8 +430,89 @@ static scalarField toField(const Container& c, const std::string& k)
 
 // ---------------------------------------------------------------------------
 
+
+static int dumpPolyMesh(const char* caseDir, const char* outPath)
+{
+    fileName casePath(caseDir);
+    Time runTime
+    (
+        Time::controlDictName,
+        casePath.path(),
+        casePath.name(),
+        false
+    );
+    polyMesh mesh
+    (
+        IOobject
+        (
+            polyMesh::defaultRegion,
+            runTime.name(),
+            runTime,
+            IOobject::MUST_READ
+        )
+    );
+
+    Container out;
+    const label nInt = mesh.nInternalFaces();
+    labelList sizes(3);
+    sizes[0] = mesh.nCells();
+    sizes[1] = nInt;
+    sizes[2] = mesh.nFaces();
+    putI32(out, "sizes", sizes);
+    putI32(out, "lower", labelList(SubList<label>(mesh.faceOwner(), nInt)));
+    putI32(out, "upper", labelList(mesh.faceNeighbour()));
+    putI32(out, "faceOwner", mesh.faceOwner());
+
+    const vectorField& Sf = mesh.faceAreas();
+    const vectorField& Cf = mesh.faceCentres();
+    const vectorField& C = mesh.cellCentres();
+    scalarField buf(3*Sf.size());
+    forAll(Sf, i)
+    {
+        buf[3*i] = Sf[i].x(); buf[3*i + 1] = Sf[i].y(); buf[3*i + 2] = Sf[i].z();
+    }
+    putF64(out, "faceAreas", buf);
+    forAll(Cf, i)
+    {
+        buf[3*i] = Cf[i].x(); buf[3*i + 1] = Cf[i].y(); buf[3*i + 2] = Cf[i].z();
+    }
+    putF64(out, "faceCentres", buf);
+    scalarField cbuf(3*C.size());
+    forAll(C, i)
+    {
+        cbuf[3*i] = C[i].x(); cbuf[3*i + 1] = C[i].y(); cbuf[3*i + 2] = C[i].z();
+    }
+    putF64(out, "cellCentres", cbuf);
+    putF64(out, "cellVolumes", mesh.cellVolumes());
+
+    const polyBoundaryMesh& bm = mesh.boundary();
+    labelList nPatches(1, bm.size());
+    putI32(out, "nPatches", nPatches);
+    forAll(bm, pi)
+    {
+        const std::string k = "patch." + std::to_string(pi);
+        labelList ss(2);
+        ss[0] = bm[pi].start();
+        ss[1] = bm[pi].size();
+        putI32(out, k + ".startSize", ss);
+        Entry e;
+        const std::string desc = std::string(bm[pi].name()) + " " + std::string(bm[pi].type());
+        e.dtype = 2;
+        e.count = desc.size();
+        e.bytes.assign(desc.begin(), desc.end());
+        out[k + ".nameType"] = e;
+    }
+    writeContainer(outPath, out);
+    return 0;
+}
+
 int main(int argc, char* argv[])
 {
+    if (argc == 4 && std::string(argv[1]) == "--polymesh")
+    {
+        return dumpPolyMesh(argv[2], argv[3]);
+    }
+
     if (argc < 3)
     {
         fprintf

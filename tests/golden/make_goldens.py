@@ -81,6 +81,26 @@ def decomposed_case(kind, n_ranks):
     return decompose.as_cyclic_blocks(parts)
 
 
+def polymesh_dump(tutorial_mesh):
+    """`ref_harness --polymesh` on a mesh shipped with the reference (tutorials/.../constant/polyMesh)."""
+    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle/foam_env"), WM_PROJECT="OpenFOAM",
+               WM_PROJECT_VERSION="dev")
+    with tempfile.TemporaryDirectory() as td:
+        case = Path(td) / "case"
+        (case / "system").mkdir(parents=True)
+        (case / "constant").mkdir()
+        (case / "constant" / "polyMesh").symlink_to(tutorial_mesh)
+        (case / "system" / "controlDict").write_text(
+            "FoamFile{format ascii; class dictionary; object controlDict;}\napplication harness;\n"
+            "startFrom startTime;\nstartTime 0;\nstopAt endTime;\nendTime 1;\ndeltaT 1;\n"
+            "writeControl timeStep;\nwriteInterval 1000000;\n")
+        r = subprocess.run([str(ROOT / "oracle/_ref/ref_harness"), "--polymesh", str(case), f"{td}/mesh.b2ls"],
+                           env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
+        return ldu_io.read(f"{td}/mesh.b2ls")
+
+
 def with_coarsest(solves, n):
     return [(d.replace("solver GAMG;", f"solver GAMG; nCellsInCoarsestLevel {n};")
               .replace("preconditioner GAMG;", f"preconditioner GAMG; nCellsInCoarsestLevel {n};"), h)
@@ -149,6 +169,15 @@ def main():
         fixture(f"decomp{n_ranks}_{kind}", blk, with_coarsest(solves, 10 * n_ranks), sm,
                 agglom_dict=f"solver GAMG; nCellsInCoarsestLevel {10 * n_ranks};",
                 extra={"rankOffsets": offs.astype(np.int32)})
+    # real meshes shipped with the reference, read by the reference's own polyMesh (addressing + geometry):
+    # airFoil2D (10,720 cells, 2-D unstructured C-mesh) and tank3D (3-D)
+    tut = Path("/root/reference/tutorials")
+    af = polymesh_dump(tut / "incompressibleFluid/airFoil2D/constant/polyMesh")
+    fixture("airfoil2d_p", cases.polymesh_laplacian(af), SYM_SOLVES[:2] + SYM_SOLVES[4:7] + SYM_SOLVES[10:], sym_sm)
+    fixture("airfoil2d_U", cases.polymesh_convection_diffusion(af), ASYM_SOLVES[:1] + ASYM_SOLVES[3:], asym_sm)
+    tk = polymesh_dump(tut / "incompressibleDriftFlux/tank3D/constant/polyMesh")
+    fixture("tank3d_p", cases.polymesh_laplacian(tk, rhs_kind="uniform"), SYM_SOLVES[1:2] + SYM_SOLVES[5:6] + SYM_SOLVES[11:12],
+            sym_sm[:2], agglom=True)
 
 
 if __name__ == "__main__":
