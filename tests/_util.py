@@ -10,7 +10,8 @@ load_pkg()
 from b200ls import capi, cases, ldu_io  # noqa: E402
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-FIXTURES = sorted(p.stem for p in GOLDEN.glob("*.b2ls"))
+# icofoam_*.b2ls are application logs (tests/test_gpu_icofoam.py), not linear-system fixtures
+FIXTURES = sorted(p.stem for p in GOLDEN.glob("*.b2ls") if not p.stem.startswith("icofoam_"))
 
 
 def load_fixture(name):
