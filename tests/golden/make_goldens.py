@@ -101,6 +101,40 @@ def polymesh_dump(tutorial_mesh):
         return ldu_io.read(f"{td}/mesh.b2ls")
 
 
+def icofoam_dumps(nx, ny, nz, steps):
+    """Real p and Ux systems of the reference's icoFoam (oracle/_app, oracle/build_app.py) captured at the drop-in
+    boundary by the plugin's pass-through solver B200dump during the last time step; returns {field: LduSystem}."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import _icofoam as ico
+    from _util import system_from_entries
+    from b200ls import foam_case
+
+    if not ico.ICOFOAM.exists():
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        dump = f'solver B200dump; dumpFile "{td}/'
+        case = foam_case.write_cavity_case(
+            Path(td) / "case", nx=nx, ny=ny, nz=nz, end_time=steps * 0.005, libs=f'"{ico.PLUGIN}"',
+            p_solver=dump + 'p"; delegate PCG; preconditioner DIC; tolerance 1e-06; relTol 0.05;',
+            u_solver=dump + 'U"; delegate smoothSolver; smoother symGaussSeidel; tolerance 1e-05; relTol 0;')
+        ico.run_icofoam(case)
+        out = {}
+        lower, upper, fdir = cases.block_addressing(nx, ny, nz)
+        h = np.array([0.1 / nx, 0.1 / ny, 0.01 / nz])
+        area = np.array([h[1] * h[2], h[0] * h[2], h[0] * h[1]])
+        w = (area / np.sqrt(area) * np.array([1.0, 1.01, 1.02]))[fdir]       # faceAreaPair weights of this mesh
+        for fld in ("p", "U"):
+            files = sorted(Path(td).glob(f"{fld}.*.b2ls"), key=lambda q: int(q.name.split(".")[1]))
+            # the counter is shared by all B200dump solves of the run: take the last p solve / the last Ux solve
+            pick = files[-1] if fld == "p" else files[-(3 if nz > 1 else 2)]
+            d = ldu_io.read(str(pick))
+            s_ = system_from_entries(d)
+            assert np.array_equal(s_.lower, lower) and np.array_equal(s_.upper, upper)
+            s_.face_weights = w
+            out[fld] = (s_, d["psi0"])
+        return out
+
+
 def with_coarsest(solves, n):
     return [(d.replace("solver GAMG;", f"solver GAMG; nCellsInCoarsestLevel {n};")
               .replace("preconditioner GAMG;", f"preconditioner GAMG; nCellsInCoarsestLevel {n};"), h)
@@ -178,6 +212,15 @@ def main():
     tk = polymesh_dump(tut / "incompressibleDriftFlux/tank3D/constant/polyMesh")
     fixture("tank3d_p", cases.polymesh_laplacian(tk, rhs_kind="uniform"), SYM_SOLVES[1:2] + SYM_SOLVES[5:6] + SYM_SOLVES[11:12],
             sym_sm[:2], agglom=True)
+    # REAL matrices: the p and Ux equations the reference's icoFoam assembles on the cavity (time step 10), captured by
+    # B200dump inside the running application; psi0 = the field the application started that solve from
+    for nm, dims in (("icofoamsys_20x20x1", (20, 20, 1)), ("icofoamsys_12x12x6", (12, 12, 6))):
+        dumps = icofoam_dumps(*dims, steps=10)
+        if dumps is None:
+            print(f"{nm}: skipped (oracle/_app/icoFoam not built)")
+            continue
+        fixture(nm + "_p", dumps["p"][0], SYM_SOLVES, sym_sm, extra={"psi0": dumps["p"][1]})
+        fixture(nm + "_U", dumps["U"][0], ASYM_SOLVES, asym_sm, extra={"psi0": dumps["U"][1]})
 
 
 if __name__ == "__main__":

@@ -72,7 +72,7 @@ def test_solvers_bit_exact(fx):
             kw.update(precSmoother=sub.get("smoother", "GaussSeidel"), nVcycles=int(sub.get("nVcycles", 2)),
                       precTolerance=float(sub.get("tolerance", 1e-6)), precRelTol=float(sub.get("relTol", 0)))
         ctl = orc.controls(precond=pre, **kw)
-        psi, perf = orc.solve(S, d["solver"], ctl, s.source)
+        psi, perf = orc.solve(S, d["solver"], ctl, s.source, psi0=inp.get("psi0"))
         rperf = ref[f"solve.{i}.perf"]
         ctx = (name, text, perf["nIterations"], rperf[2], perf["finalResidual"], rperf[1])
         assert perf["nIterations"] == int(rperf[2]), ctx
