@@ -3,7 +3,7 @@
 lid-driven cavity, once with the reference's solvers and once with `libs ("libB200LinearSolvers.so")` + the B200
 solver names.  Prints the two solver logs side by side (summary) and the wall-clock time of each run.
 
-    python benchmarks/icofoam_dropin.py [N=64] [steps=3] [p: pcg|gamg]
+    python benchmarks/icofoam_dropin.py [N=64] [steps=3] [p: pcg|gamg] [U: symgs|bicg]
 """
 import sys
 import tempfile
@@ -27,7 +27,9 @@ def main():
     psel = sys.argv[3] if len(sys.argv) > 3 else "pcg"
     p_ref = {"pcg": "solver PCG; preconditioner DIC; tolerance 1e-06; relTol 0.05;",
              "gamg": "solver GAMG; smoother GaussSeidel; tolerance 1e-06; relTol 0.05;"}[psel]
-    u_ref = "solver smoothSolver; smoother symGaussSeidel; tolerance 1e-05; relTol 0;"
+    usel = sys.argv[4] if len(sys.argv) > 4 else "symgs"
+    u_ref = {"symgs": "solver smoothSolver; smoother symGaussSeidel; tolerance 1e-05; relTol 0;",
+             "bicg": "solver PBiCGStab; preconditioner DILU; tolerance 1e-05; relTol 0;"}[usel]
     dt = 0.005 * 20 / n          # keep the Courant number of the 20x20 tutorial
     kw = dict(nx=n, ny=n, nz=n, end_time=steps * dt, delta_t=dt)
     out = {}
@@ -41,7 +43,7 @@ def main():
             out[tag] = (time.time() - t0, ico.parse_log(log), log)
     tr, sr, _ = out["reference"]
     tb, sb, _ = out["B200"]
-    print(f"icoFoam cavity {n}^3 = {n**3} cells, {steps} time steps, p: {psel.upper()}, U: smoothSolver+symGaussSeidel")
+    print(f"icoFoam cavity {n}^3 = {n**3} cells, {steps} time steps, p: {psel.upper()}, U: {usel}")
     print(f"wall clock: reference solvers (1 host core) {tr:.2f} s | B200 plugin {tb:.2f} s (includes CUDA/plugin start-up, "
           f"mesh analysis, per-solve H2D/D2H) | ratio {tr / tb:.1f}x")
     print(f"{'#':>3} {'field':5} {'reference':>14} {'iters':>5} | {'B200':>14} {'iters':>5} | initial residual rel diff")
