@@ -149,7 +149,10 @@ int b200ls_amul(b200ls_matrix_t m, const double* psi, double* Apsi);
 int b200ls_residual(b200ls_matrix_t m, const double* psi, const double* source, double* rA);
 int b200ls_sum_a(b200ls_matrix_t m, double* sumA);
 
-enum b200ls_solver { B200LS_PCG = 0, B200LS_PBICGSTAB = 1, B200LS_GAMG = 2, B200LS_SMOOTH_SOLVER = 3 };
+enum b200ls_solver {
+    B200LS_PCG = 0, B200LS_PBICGSTAB = 1, B200LS_GAMG = 2, B200LS_SMOOTH_SOLVER = 3,
+    B200LS_DIAGONAL_SOLVER = 4      /* solvers/diagonalSolver/diagonalSolver.C:62-79: psi = source/diag, 0 iterations */
+};
 enum b200ls_precond {            /* preconditioner (Krylov) or smoother (GAMG / smoothSolver) */
     B200LS_NONE = 0, B200LS_DIAGONAL = 1, B200LS_DIC = 2, B200LS_DILU = 3, B200LS_GAUSS_SEIDEL = 4,
     B200LS_SYM_GAUSS_SEIDEL = 5,    /* smoothers/symGaussSeidel/symGaussSeidelSmoother.C:66-217                  */

@@ -18,7 +18,9 @@ LOWER_ADDR, UPPER_ADDR, LEVEL_SIZES = 10, 11, 12
 PCG, PBICGSTAB, GAMG, SMOOTH_SOLVER = 0, 1, 2, 3
 NONE, DIAGONAL, DIC, DILU, GAUSS_SEIDEL, SYM_GAUSS_SEIDEL, DIC_GAUSS_SEIDEL, DILU_GAUSS_SEIDEL, GAMG_PRECOND = range(9)
 
-SOLVERS = {"PCG": PCG, "PBiCGStab": PBICGSTAB, "GAMG": GAMG, "smoothSolver": SMOOTH_SOLVER}
+DIAGONAL_SOLVER = 4
+SOLVERS = {"PCG": PCG, "PBiCGStab": PBICGSTAB, "GAMG": GAMG, "smoothSolver": SMOOTH_SOLVER,
+           "diagonal": DIAGONAL_SOLVER}
 PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "GaussSeidel": GAUSS_SEIDEL,
             "symGaussSeidel": SYM_GAUSS_SEIDEL, "DICGaussSeidel": DIC_GAUSS_SEIDEL,
             "DILUGaussSeidel": DILU_GAUSS_SEIDEL, "GAMG": GAMG_PRECOND}

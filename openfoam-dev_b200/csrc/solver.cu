@@ -1717,6 +1717,14 @@ void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, con
             case B200LS_SMOOTH_SOLVER:
                 solveSmooth(m, c, vPsi.buf.p, vSpare.buf.p, source, perf, ev1);
                 break;
+            case B200LS_DIAGONAL_SOLVER: {
+                // diagonalSolver.C:62-79: psi = source/diag; reports zero residuals, zero iterations, converged
+                const int n = DL(m, 0).nCells;
+                B2_CUDA(cudaEventRecord(ev1, S()));
+                if (n) LAUNCH(k_div, gridStride(n), 256, vPsi.buf.p, source, m->levels[0].diag.p, n);
+                perf->converged = 1;
+                break;
+            }
             default:
                 throw CudaError("unknown solver");
         }

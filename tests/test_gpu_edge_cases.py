@@ -173,3 +173,12 @@ def test_streamed_sweeps_of_structured_blocks_bit_exact(shape, sym, monkeypatch)
     assert abs(perf.nIterations - po["nIterations"]) <= 1
     if perf.nIterations == po["nIterations"]:
         assert max_rel_diff(psi, xo) <= 1e-9
+
+
+def test_diagonal_solver():
+    """diagonalSolver.C:62-79: psi = source/diag, zero residuals, zero iterations, converged."""
+    s = cases.convection_diffusion(9, 7, 5, dt_coeff=50.0)
+    mesh, mat = capi.from_system(s)
+    psi, perf = mat.solve(capi.controls("diagonal"), s.source, psi0=np.ones(s.n_cells))
+    assert np.array_equal(psi, s.source / s.diag)
+    assert (perf.nIterations, perf.initialResidual, perf.finalResidual, perf.converged) == (0, 0.0, 0.0, 1)
