@@ -53,6 +53,25 @@ def decompose_system(sys_: LduSystem, cell_rank, n_ranks):
             coeff = np.where(own_side[sel], sys_.upper_coeffs[sel], lower_c[sel])
             ifaces.append(Interface(neighb_rank=int(s), face_cells=fc.astype(np.int32), bou_coeffs=-coeff,
                                     int_coeffs=-coeff))
+        # cyclic pairs of the undecomposed system stay cyclic on the rank that holds both cells of a face pair
+        # (decomposePar turns pairs that straddle ranks into processorCyclic patches: not generated here)
+        n_proc = len(ifaces)
+        kept = {}
+        for gi, itf in enumerate(sys_.interfaces):
+            if itf.nbr_patch < 0:
+                raise ValueError("decompose_system: the input system already has processor patches")
+            other = sys_.interfaces[itf.nbr_patch]
+            here, there = cell_rank[itf.face_cells] == r, cell_rank[other.face_cells] == r
+            if np.any(here != there):
+                raise ValueError("decompose_system: a cyclic face pair straddles two ranks")
+            if np.any(here):
+                kept[gi] = len(kept)
+        for gi, k in kept.items():
+            itf = sys_.interfaces[gi]
+            sel = cell_rank[itf.face_cells] == r
+            ifaces.append(Interface(neighb_rank=-1, face_cells=g2l[itf.face_cells[sel]].astype(np.int32),
+                                    bou_coeffs=itf.bou_coeffs[sel].copy(), int_coeffs=itf.int_coeffs[sel].copy(),
+                                    nbr_patch=n_proc + kept[itf.nbr_patch]))
         out.append(LduSystem(
             n_cells=int(cells.size), lower=g2l[lo[inner]].astype(np.int32), upper=g2l[up[inner]].astype(np.int32),
             diag=sys_.diag[cells].copy(), upper_coeffs=sys_.upper_coeffs[inner].copy(),

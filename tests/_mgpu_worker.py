@@ -64,6 +64,8 @@ def dense(sys_):
     lo_c = sys_.upper_coeffs if sys_.lower_coeffs is None else sys_.lower_coeffs
     a[sys_.upper, sys_.lower] += lo_c
     a[sys_.lower, sys_.upper] += sys_.upper_coeffs
+    for itf in sys_.interfaces:                      # cyclic pairs: row gets -bouCoeffs * psi[partner cell]
+        np.add.at(a, (itf.face_cells, sys_.interfaces[itf.nbr_patch].face_cells), -itf.bou_coeffs)
     return a
 
 
@@ -80,9 +82,11 @@ def main():
     split = decompose.simple_split(world)
     nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
     ok = True
-    for kind in ("sym", "asym"):
+    for kind in ("sym", "asym", "cyc"):
+        # "cyc": periodic in z on top of the decomposition -- every rank has processor patches AND a cyclic pair
         glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if kind == "sym" else \
-            cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
+            cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0) if kind == "asym" else \
+            cases.add_cyclic(cases.cavity_laplacian(nx, ny, nz, coeffs="random"), 2)
         parts, maps = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), world)
         part, cells = parts[rank], maps[rank]
         mesh, mat = capi.from_system(part)
@@ -126,10 +130,10 @@ def main():
                       f"max history diff {dh:.2e} solution rel diff {dpsi:.2e} {'OK' if good else 'FAIL'}", flush=True)
         ok &= check_against_reference_fixture(kind, world, rank, parts, mat, part)
         exact = np.linalg.solve(A, glob.source)
-        combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind == "sym" else [("PBiCGStab", "DILU")]
-        combos += [("GAMG", "GaussSeidel"), ("GAMG", "DIC" if kind == "sym" else "DILU")]
+        combos = [("PCG", "DIC"), ("PCG", "diagonal")] if kind in ("sym", "cyc") else [("PBiCGStab", "DILU")]
+        combos += [("GAMG", "GaussSeidel"), ("GAMG", "DILU" if kind == "asym" else "DIC")]
         # V-cycles as the preconditioner: the coarsest-level Krylov solve is nested inside the outer Krylov loop
-        combos.append(("PCG" if kind == "sym" else "PBiCGStab", "GAMG"))
+        combos.append(("PBiCGStab" if kind == "asym" else "PCG", "GAMG"))
         if kind == "asym":   # Gauss-Seidel alone converges far too slowly on the Laplacian to pin a solution
             combos.append(("smoothSolver", "GaussSeidel"))
         for solver, pre in combos:
