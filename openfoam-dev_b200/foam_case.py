@@ -30,9 +30,10 @@ def _list(items, fmt):
     return f"{len(items)}\n(\n" + "\n".join(fmt(x) for x in items) + "\n)\n"
 
 
-def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01):
+def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01, cyclic_z=False):
     """points / faces / owner / neighbour / boundary of the block; patches movingWall (y max), fixedWalls (x min,
-    x max, y min), frontAndBack (z min, z max; `empty` when nz == 1)."""
+    x max, y min), frontAndBack (z min, z max; `empty` when nz == 1) -- or, with cyclic_z, the cyclic pair
+    front (z min) / back (z max), face i of one coupled to face i of the other."""
     mesh_dir = Path(mesh_dir)
     P = lambda i, j, k: i + (nx + 1) * (j + (ny + 1) * k)   # noqa: E731
     C = lambda i, j, k: i + nx * (j + ny * k)               # noqa: E731
@@ -66,9 +67,13 @@ def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01):
           [(rev(fx(0, j, k)), C(0, j, k)) for k in range(nz) for j in range(ny)]
           + [(fx(nx, j, k), C(nx - 1, j, k)) for k in range(nz) for j in range(ny)]
           + [(rev(fy(i, 0, k)), C(i, 0, k)) for k in range(nz) for i in range(nx)])
-    patch("frontAndBack", "empty" if nz == 1 else "wall",
-          [(rev(fz(i, j, 0)), C(i, j, 0)) for j in range(ny) for i in range(nx)]
-          + [(fz(i, j, nz), C(i, j, nz - 1)) for j in range(ny) for i in range(nx)])
+    if cyclic_z:
+        patch("front", "cyclic", [(rev(fz(i, j, 0)), C(i, j, 0)) for j in range(ny) for i in range(nx)])
+        patch("back", "cyclic", [(fz(i, j, nz), C(i, j, nz - 1)) for j in range(ny) for i in range(nx)])
+    else:
+        patch("frontAndBack", "empty" if nz == 1 else "wall",
+              [(rev(fz(i, j, 0)), C(i, j, 0)) for j in range(ny) for i in range(nx)]
+              + [(fz(i, j, nz), C(i, j, nz - 1)) for j in range(ny) for i in range(nx)])
     _write(mesh_dir / "points", "vectorField", _list(pts, lambda p: f"({p[0]:.17g} {p[1]:.17g} {p[2]:.17g})"))
     _write(mesh_dir / "faces", "faceList", _list(faces, lambda f: f"4({f[0]} {f[1]} {f[2]} {f[3]})"))
     _write(mesh_dir / "owner", "labelList", _list(owner, str))
@@ -78,6 +83,9 @@ def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01):
         body += f"    {name}\n    {{\n        type            {typ};\n"
         if typ == "wall":
             body += "        inGroups        List<word> 1(wall);\n"
+        if typ == "cyclic":
+            body += ("        inGroups        List<word> 1(cyclic);\n"
+                     f"        neighbourPatch  {'back' if name == 'front' else 'front'};\n")
         body += f"        nFaces          {n};\n        startFace       {start};\n    }}\n"
     body += ")\n"
     _write(mesh_dir / "boundary", "polyBoundaryMesh", body)
@@ -86,20 +94,22 @@ def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01):
 
 def write_cavity_case(case_dir, nx=20, ny=20, nz=1, p_solver="solver PCG; preconditioner DIC; tolerance 1e-06; relTol 0.05;",
                       p_final="$p; relTol 0;", u_solver="solver smoothSolver; smoother symGaussSeidel; tolerance 1e-05; relTol 0;",
-                      libs=None, end_time=0.05, delta_t=0.005, write=False):
+                      libs=None, end_time=0.05, delta_t=0.005, write=False, cyclic_z=False):
     case_dir = Path(case_dir)
     fb = "empty" if nz == 1 else "noSlip"
-    write_block_polymesh(case_dir / "constant/polyMesh", nx, ny, nz)
+    write_block_polymesh(case_dir / "constant/polyMesh", nx, ny, nz, cyclic_z=cyclic_z)
     _write(case_dir / "constant/physicalProperties", "dictionary", "nu              [0 2 -1 0 0 0 0] 0.01;\n")
     _write(case_dir / "0/U", "volVectorField",
            "dimensions      [0 1 -1 0 0 0 0];\ninternalField   uniform (0 0 0);\nboundaryField\n{\n"
            "    movingWall { type fixedValue; value uniform (1 0 0); }\n    fixedWalls { type noSlip; }\n"
-           f"    frontAndBack {{ type {fb}; }}\n}}\n")
+           + (f"    frontAndBack {{ type {fb}; }}\n}}\n" if not cyclic_z else
+              "    front { type cyclic; }\n    back { type cyclic; }\n}\n"))
     fbp = "empty" if nz == 1 else "zeroGradient"
     _write(case_dir / "0/p", "volScalarField",
            "dimensions      [0 2 -2 0 0 0 0];\ninternalField   uniform 0;\nboundaryField\n{\n"
            "    movingWall { type zeroGradient; }\n    fixedWalls { type zeroGradient; }\n"
-           f"    frontAndBack {{ type {fbp}; }}\n}}\n")
+           + (f"    frontAndBack {{ type {fbp}; }}\n}}\n" if not cyclic_z else
+              "    front { type cyclic; }\n    back { type cyclic; }\n}\n"))
     libs_line = f"libs ({libs});\n" if libs else ""
     _write(case_dir / "system/controlDict", "dictionary",
            f"application     icoFoam;\n{libs_line}startFrom       startTime;\nstartTime       0;\nstopAt          endTime;\n"

@@ -30,6 +30,11 @@ CASES = {
     # 3-D, asymmetric U solve with PBiCGStab+DILU
     "cavity12x12x6_bicg": dict(nx=12, ny=12, nz=6, end_time=0.05,
                                u_solver="solver PBiCGStab; preconditioner DILU; tolerance 1e-05; relTol 0;"),
+    # periodic in z: real cyclicFvPatch / cyclicFvPatchField on the finest level, cyclicGAMGInterface on the coarse ones
+    "cavity12x12x6_cyclic_gamg": dict(nx=12, ny=12, nz=6, end_time=0.05, cyclic_z=True,
+                                      p_solver="solver GAMG; smoother GaussSeidel; tolerance 1e-06; relTol 0.05;"),
+    "cavity12x12x6_cyclic_pcg": dict(nx=12, ny=12, nz=6, end_time=0.05, cyclic_z=True,
+                                     u_solver="solver PBiCGStab; preconditioner DILU; tolerance 1e-05; relTol 0;"),
 }
 
 
