@@ -94,10 +94,10 @@ def write_block_polymesh(mesh_dir, nx, ny, nz, lx=0.1, ly=0.1, lz=0.01, cyclic_z
 
 def write_cavity_case(case_dir, nx=20, ny=20, nz=1, p_solver="solver PCG; preconditioner DIC; tolerance 1e-06; relTol 0.05;",
                       p_final="$p; relTol 0;", u_solver="solver smoothSolver; smoother symGaussSeidel; tolerance 1e-05; relTol 0;",
-                      libs=None, end_time=0.05, delta_t=0.005, write=False, cyclic_z=False):
+                      libs=None, end_time=0.05, delta_t=0.005, write=False, cyclic_z=False, lz=0.01):
     case_dir = Path(case_dir)
     fb = "empty" if nz == 1 else "noSlip"
-    write_block_polymesh(case_dir / "constant/polyMesh", nx, ny, nz, cyclic_z=cyclic_z)
+    write_block_polymesh(case_dir / "constant/polyMesh", nx, ny, nz, lz=lz, cyclic_z=cyclic_z)
     _write(case_dir / "constant/physicalProperties", "dictionary", "nu              [0 2 -1 0 0 0 0] 0.01;\n")
     _write(case_dir / "0/U", "volVectorField",
            "dimensions      [0 1 -1 0 0 0 0];\ninternalField   uniform (0 0 0);\nboundaryField\n{\n"

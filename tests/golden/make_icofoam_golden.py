@@ -31,9 +31,9 @@ CASES = {
     "cavity12x12x6_bicg": dict(nx=12, ny=12, nz=6, end_time=0.05,
                                u_solver="solver PBiCGStab; preconditioner DILU; tolerance 1e-05; relTol 0;"),
     # periodic in z: real cyclicFvPatch / cyclicFvPatchField on the finest level, cyclicGAMGInterface on the coarse ones
-    "cavity12x12x6_cyclic_gamg": dict(nx=12, ny=12, nz=6, end_time=0.05, cyclic_z=True,
+    "cavity12x12x6_cyclic_gamg": dict(nx=12, ny=12, nz=6, lz=0.05, end_time=0.05, cyclic_z=True,
                                       p_solver="solver GAMG; smoother GaussSeidel; tolerance 1e-06; relTol 0.05;"),
-    "cavity12x12x6_cyclic_pcg": dict(nx=12, ny=12, nz=6, end_time=0.05, cyclic_z=True,
+    "cavity12x12x6_cyclic_pcg": dict(nx=12, ny=12, nz=6, lz=0.05, end_time=0.05, cyclic_z=True,
                                      u_solver="solver PBiCGStab; preconditioner DILU; tolerance 1e-05; relTol 0;"),
 }
 
@@ -41,7 +41,10 @@ CASES = {
 def main():
     if not ico.ICOFOAM.exists():
         sys.exit("oracle/_app/icoFoam missing: run python oracle/build_app.py")
+    only = sys.argv[1:]
     for name, kw in CASES.items():
+        if only and not any(o in name for o in only):
+            continue
         with tempfile.TemporaryDirectory() as td:
             case = foam_case.write_cavity_case(Path(td) / "case", write=True, **kw)
             log = ico.run_icofoam(case)
