@@ -796,35 +796,6 @@ B200_SMOOTHER
 
 
 // ---------------------------------------------------------------------------
-// B200diagonal (diagonalSolver.C:62-79): psi = source/diag
-// ---------------------------------------------------------------------------
-
-class B200diagonal
-:
-    public B200SolverBase
-{
-public:
-
-    TypeName("B200diagonal");
-
-    using B200SolverBase::B200SolverBase;
-
-    virtual solverPerformance solve
-    (
-        scalarField& psi,
-        const scalarField& source,
-        const direction cmpt = 0
-    ) const
-    {
-        b200ls_controls c;
-        b200ls_controls_default(&c);
-        c.solver = B200LS_DIAGONAL_SOLVER;
-        return run("diagonal", c, psi, source);
-    }
-};
-
-
-// ---------------------------------------------------------------------------
 // B200dump: pass-through solver that serialises the system it receives at the
 // drop-in boundary (SURVEY.md 8(c) "capturing real matrices at the boundary")
 // and then delegates to the reference solver named by `delegate`:
@@ -1056,12 +1027,6 @@ lduMatrix::solver::addsymMatrixConstructorToTable<B200GAMG>
     addB200GAMGSymMatrixConstructorToTable_;
 lduMatrix::solver::addasymMatrixConstructorToTable<B200GAMG>
     addB200GAMGAsymMatrixConstructorToTable_;
-
-defineTypeNameAndDebug(B200diagonal, 0);
-lduMatrix::solver::addsymMatrixConstructorToTable<B200diagonal>
-    addB200diagonalSymMatrixConstructorToTable_;
-lduMatrix::solver::addasymMatrixConstructorToTable<B200diagonal>
-    addB200diagonalAsymMatrixConstructorToTable_;
 
 defineTypeNameAndDebug(B200dump, 0);
 lduMatrix::solver::addsymMatrixConstructorToTable<B200dump>

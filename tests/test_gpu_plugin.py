@@ -94,22 +94,3 @@ def test_reference_loops_with_b200_preconditioners_and_smoothers(name, tmp_path)
         assert np.array_equal(got[:5], want[:5]), (name, t, got[:5], want[:5])
         assert np.array_equal(out[f"solve.{k}.psi"], ref[f"solve.{i}.psi"]), (name, t)
 
-
-def test_b200_diagonal_solver_equals_the_reference_diagonal_solver(tmp_path):
-    if not HARNESS.exists() or not PLUGIN.exists():
-        pytest.skip("oracle/_ref or the plugin was not built (needs /root/reference at build time)")
-    inp, _ = load_fixture("convdiff_9x8x7")
-    e = {k: v for k, v in inp.items() if not k.startswith(("solve.", "smooth.", "agglomerate", "x"))}
-    e["libs"] = f'"{PLUGIN}"'
-    e["solve.0.dict"] = "solver diagonal;"
-    e["solve.1.dict"] = "solver B200diagonal;"
-    ldu_io.write(str(tmp_path / "in.b2ls"), e)
-    env = dict(os.environ, WM_PROJECT_DIR=str(ROOT / "oracle/foam_env"), WM_PROJECT="OpenFOAM",
-               WM_PROJECT_VERSION="dev")
-    r = subprocess.run([str(HARNESS), str(tmp_path / "in.b2ls"), str(tmp_path / "out.b2ls"), str(tmp_path / "case")],
-                       env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    out = ldu_io.read(str(tmp_path / "out.b2ls"))
-    assert np.array_equal(out["solve.0.psi"], out["solve.1.psi"])
-    assert np.array_equal(out["solve.0.perf"][:5], out["solve.1.perf"][:5])
-    assert ldu_io.as_str(out["solve.0.solverName"]) == ldu_io.as_str(out["solve.1.solverName"]) == "diagonal"
