@@ -64,7 +64,7 @@ int b200ls_set_host_comm(int32_t rank, int32_t nRanks, b200ls_exchange_fn exchan
 /* ---- mesh (cached per lduAddressing by the caller) ---------------------------------------------- */
 
 /* Host analysis only (no device work): losort/ownerStart/losortStart, forward/backward wavefronts,
- * wavefront-major permutation and the native row layout.  Interfaces: one entry per COUPLED patch, in patch order.
+ * the row permutation (wavefront-major, or tile-major on structured blocks) and the native row layout.  Interfaces: one entry per COUPLED patch, in patch order.
  * ifaceNeighbRank[i] >= 0: processor patch to that rank (processorLduInterface::neighbProcNo()).
  * ifaceNeighbRank[i] <  0: one half of a cyclic pair on this rank (lduAddressing/lduInterface/cyclicLduInterface.H):
  *   the value is B200LS_CYCLIC(p) = -(1 + p), p = cyclicLduInterface::nbrPatchIndex() counted among the coupled
@@ -93,21 +93,20 @@ enum b200ls_i32_which {
     B200LS_UPPER_ADDR = 11,         /* meshLevel(level).lduAddr().upperAddr()            */
     B200LS_LEVEL_SIZES = 12,        /* {nCells, nFaces} of meshLevel(level)              */
     /* native device layout, exposed for the host-logic tests: rows live at "positions" */
-    B200LS_PERM = 13,               /* position -> cell (forward-wavefront-major)        */
+    B200LS_PERM = 13,               /* position -> cell (forward-wavefront-major, or tile-major: see below) */
     B200LS_LPTR = 14,               /* CSR of the neighbour-side (lower) triangle, by position */
     B200LS_LCOL = 15,               /*   column = position of the coupled row            */
     B200LS_LFACE = 16,              /*   face of each entry                              */
     B200LS_UPTR = 17,               /* CSR of the owner-side (upper) triangle            */
     B200LS_UCOL = 18,
     B200LS_UFACE = 19,
-    /* streamed sweep plans of structured blocks (empty arrays when the level has none): part offsets in steps,
-     * records {pos, ebase, ext0, ext1} per (step, lane), dependency descriptors per (step, lane) */
-    B200LS_STREAM_FWD_PART_START = 20,
-    B200LS_STREAM_FWD_REC = 21,
-    B200LS_STREAM_FWD_META = 22,
-    B200LS_STREAM_BWD_PART_START = 23,
-    B200LS_STREAM_BWD_REC = 24,
-    B200LS_STREAM_BWD_META = 25
+    /* structured blocks (an nx*ny*nz hex block numbered i-fastest) are laid out tile-major for the pencil sweeps
+     * (DESIGN.md 3.2); all three are empty when the level keeps the wavefront-major layout */
+    B200LS_FWD_POS = 20,            /* forward processing order (wavefront by wavefront) -> position     */
+    B200LS_PENCIL_DIMS = 21,        /* {nx, ny, nz, WJ, WK, nJ, nK}                                      */
+    B200LS_PENCIL_TILES = 22,       /* per tile (memory order, J fastest): {base, w, wj, wk, j0, k0,
+                                       tile index of (J-1,K), (J,K-1), (J+1,K), (J,K+1) or -1}          */
+    B200LS_PENCIL_ORDER = 23        /* launch order of the forward sweeps (tile wavefronts)              */
 };
 /* level 0 = the finest mesh; level k>0 = k-th coarse mesh (= reference meshLevel(k)).
  * RESTRICT_ADDRESSING / FACE_RESTRICT_ADDRESSING / FACE_FLIP_MAP at `level` map level -> level+1,

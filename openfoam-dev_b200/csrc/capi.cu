@@ -333,23 +333,20 @@ int b200ls_mesh_get_i32(b200ls_mesh_t mesh, int which, int level, const int32_t*
             case B200LS_UPTR: v = &L.Uptr; break;
             case B200LS_UCOL: v = &L.Ucol; break;
             case B200LS_UFACE: v = &L.Uface; break;
-            case B200LS_STREAM_FWD_PART_START: v = &L.fwdStream.partStart; break;
-            case B200LS_STREAM_BWD_PART_START: v = &L.bwdStream.partStart; break;
-            case B200LS_STREAM_FWD_REC:
-            case B200LS_STREAM_BWD_REC: {
-                const auto& r = which == B200LS_STREAM_FWD_REC ? L.fwdStream.rec : L.bwdStream.rec;
-                static_assert(sizeof(StreamRec) == 4 * sizeof(int32_t), "StreamRec layout");
-                *data = reinterpret_cast<const int32_t*>(r.data());
-                *n = int64_t(r.size()) * 4;
+            case B200LS_FWD_POS: v = &L.fwdPos; break;
+            case B200LS_PENCIL_DIMS:
+                sizes.clear();
+                if (L.pencil.valid)
+                    sizes = {L.pencil.nx, L.pencil.ny, L.pencil.nz, L.pencil.WJ, L.pencil.WK, L.pencil.nJ, L.pencil.nK};
+                v = &sizes;
+                break;
+            case B200LS_PENCIL_TILES: {
+                static_assert(sizeof(PencilTile) == 10 * sizeof(int32_t), "PencilTile layout");
+                *data = reinterpret_cast<const int32_t*>(L.pencil.tiles.data());
+                *n = int64_t(L.pencil.tiles.size()) * 10;
                 return;
             }
-            case B200LS_STREAM_FWD_META:
-            case B200LS_STREAM_BWD_META: {
-                const auto& r = which == B200LS_STREAM_FWD_META ? L.fwdStream.meta : L.bwdStream.meta;
-                *data = reinterpret_cast<const int32_t*>(r.data());
-                *n = int64_t(r.size());
-                return;
-            }
+            case B200LS_PENCIL_ORDER: v = &L.pencil.fwdOrder; break;
             case B200LS_LEVEL_SIZES:
                 sizes = {L.nCells, L.nFaces};
                 v = &sizes;

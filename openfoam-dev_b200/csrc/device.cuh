@@ -122,6 +122,15 @@ struct Context {
 Context& ctx();
 void ensureInit();
 
+// device copy of mesh.hpp PencilTile plus what the helper warp needs of its four neighbours (pencil.cuh)
+struct PencilTileDev {
+    int base, w, wj, wk;
+    int j0, k0, pad0, pad1;
+    int nbrBase[4];     // (J-1,K), (J,K-1), (J+1,K), (J,K+1): first position or -1
+    int nbrW[4];        // row stride of that tile
+    int nbrWj[4];       // its pencils along j
+};
+
 // Addressing of one level in HBM (built once per mesh)
 struct DevLevel {
     int nCells = 0, nFaces = 0;
@@ -137,13 +146,14 @@ struct DevLevel {
     std::map<int, DevBuf<int4>> multiSweepTasks;    // nSweeps -> tasks ordered by tau = level + 2*sweep
     DevBuf<int> bwdPos;
     int nFwdTasks = 0, nBwdTasks = 0;
-    // streamed sweep plans (structured blocks only)
-    bool hasStream = false;
-    int nStreamParts = 0;
-    DevBuf<int> sFwdPartStart, sBwdPartStart;
-    DevBuf<int4> sFwdRec, sBwdRec;          // {pos, ext0, ext1, meta} per (step, lane)
-    DevBuf<int> sFwdEbase, sBwdEbase;        // first CSR entry of the row (k_stream_pack)
-    size_t nStreamRec = 0;
+    DevBuf<int> fwdPos;                             // forward processing order -> position (empty: identity)
+    // pencil sweeps (structured blocks only; pencil.cuh)
+    bool hasPencil = false;
+    int pNx = 0, pNy = 0, pNz = 0, pWJ = 0, pWK = 0;
+    int pCols = 0;                                  // neighbour values an interior tile needs per step (one side)
+    DevBuf<PencilTileDev> pTiles;
+    DevBuf<int> pOrder;
+    int nPencilTiles = 0;
     // interfaces
     int nIfaces = 0;
     std::vector<int> ifaceSize, ifaceNbr;

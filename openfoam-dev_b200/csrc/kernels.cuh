@@ -456,7 +456,7 @@ __global__ void k_iface_suma(double* __restrict__ sumA, const int* __restrict__ 
 struct SweepArgs {
     const int2* tasks;
     int nTasks;
-    const int* rowOf;       // backward sweeps: processing slot -> position (nullptr = identity)
+    const int* rowOf;       // processing slot -> position (nullptr = identity: forward sweeps on the wavefront-major layout)
     const int* ptr;         // Lptr (forward) / Uptr (backward)
     const int* col;
     const double* val;
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(256) k_factor(SweepArgs a) {
     SWEEP_TASK_LOOP(a) {
         const int2 next = SWEEP_NEXT_TASK(a);
         if (lane < task.y) {
-            const int p = task.x + lane;
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
             double acc = a.diag[p];
             const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
             for (int base = j0; base < j1; base += 4) {
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(256) k_sweep_fwd(SweepArgs a) {
     SWEEP_TASK_LOOP(a) {
         const int2 next = SWEEP_NEXT_TASK(a);
         if (lane < task.y) {
-            const int p = task.x + lane;
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
             const double rd = a.rD[p];
             const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
             double acc = rd * a.in[p];
@@ -632,314 +632,6 @@ __global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Streamed DIC/DILU sweeps for structured blocks (mesh.hpp StreamPlan).
-//
-// The wavefront kernels above pay one L2 round trip per wavefront (0.63 us measured) because every dependency
-// crosses SMs.  Here a WARP PAIR owns a tile of 32 pencils (lines of cells along the fastest index) and walks it
-// step by step, lane = pencil:
-//   * the compute warp keeps the previous step's results in registers: the three dependencies of a row are the same
-//     lane's previous row and the previous rows of two neighbouring lanes (warp shuffles) -- no memory on the
-//     critical path.  Only pencils on the low-j / low-k faces of the tile depend on other tiles; those values are
-//     loaded from L2 kStreamE steps ahead into registers (a tile naturally lags the tiles it depends on), and
-//     polled only if they are still the sentinel;
-//   * the loader warp streams everything else into a shared-memory ring of kStreamR stages with cp.async: the
-//     record {pos, ext0, ext1, meta}, the per-solve packed coefficients {rD, rD*c0, rD*c1, rD*c2}
-//     (k_stream_pack) and the gathered input value(s).  Full/empty mbarriers hand the stages over.
-// A first single-warp version spent ~1,000 cycles of instruction issue per step (profiles/experiments/README.md);
-// the split leaves the compute warp ~60 instructions per step.
-// Per-row arithmetic and its order are those of k_sweep_fwd / k_sweep_bwd (bit-identical results).
-// ------------------------------------------------------------------------------------------------------------
-
-#ifndef B200LS_STREAM_R
-#define B200LS_STREAM_R 16
-#endif
-#ifndef B200LS_STREAM_E
-#define B200LS_STREAM_E 4
-#endif
-static constexpr int kStreamR = B200LS_STREAM_R;   // stages of the shared-memory ring (power of two)
-static constexpr int kStreamG = 4;                 // stages handed over per mbarrier phase
-static constexpr int kStreamGroups = kStreamR / kStreamG;
-static constexpr int kStreamE = B200LS_STREAM_E;   // look-ahead of the external-dependency loads, in steps (< R - G)
-static constexpr int kStreamBatch = 8;             // records the loader fetches per batch
-
-struct StreamArgs {
-    const int* partStart;
-    int nParts;
-    const int4* rec;        // {pos, ext0, ext1, meta} per (step, lane)
-    const double* pack;     // {rD, rD*c0, rD*c1, rD*c2} per (step, lane), dependencies in processing order
-    const double* in;       // rA (forward) / forward result (backward)
-    double* out;            // sentinel-initialised result
-    double* clear;          // optional: entry p is reset to the sentinel once row p is done
-    const double* dotWith;  // optional fused dot product with the result
-    double* dotOut;
-    double* partials;
-    unsigned int* ticket;
-    int* err;
-#ifdef B200LS_STREAM_PROF
-    unsigned long long* prof;   // per CTA: total, full-wait, poll cycles, polls, steps (profiles/experiments)
-#endif
-};
-
-struct StreamStage {
-    int4 rec[32];
-    double2 pk01[32];
-    double2 pk23[32];
-    double in[32];
-    double dw[32];
-};
-struct StreamSmem {
-    StreamStage st[kStreamR];
-    unsigned long long full[kStreamGroups];
-    unsigned long long empty[kStreamGroups];
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-// arrive on the barrier once all cp.async issued so far by this thread have landed (count not incremented)
-__device__ __forceinline__ void mbar_arrive_on_cp_async(unsigned long long* b) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity, int* err) {
-    unsigned spins = 0;
-    while (!mbar_try_wait(b, parity)) {
-        if (++spins > kMaxSpins) {
-            *err = 1;
-            break;
-        }
-    }
-}
-
-// Per-solve packing of the coefficients in stream order: {rD, rD*c_n} with the dependencies in processing order.
-__global__ void k_stream_pack(double* __restrict__ pack, const int4* __restrict__ rec, const int* __restrict__ ebase,
-                              const double* __restrict__ rD, const double* __restrict__ val, size_t nRec, int desc) {
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nRec; i += size_t(gridDim.x) * blockDim.x) {
-        const int4 r = rec[i];
-        double o[4] = {0.0, 0.0, 0.0, 0.0};
-        if (r.x >= 0) {
-            const int nd = r.w & 7;
-            const int e = ebase[i];
-            const double rd = rD[r.x];
-            o[0] = rd;
-            for (int k = 0; k < nd; k++) o[1 + k] = rd * val[desc ? e + nd - 1 - k : e + k];
-        }
-        reinterpret_cast<double2*>(pack)[2 * i] = make_double2(o[0], o[1]);
-        reinterpret_cast<double2*>(pack)[2 * i + 1] = make_double2(o[2], o[3]);
-    }
-}
-
-template <bool BWD>
-__global__ void __launch_bounds__(64) k_stream_sweep(StreamArgs a) {
-    extern __shared__ __align__(16) unsigned char streamSmemRaw[];
-    StreamSmem& sm = *reinterpret_cast<StreamSmem*>(streamSmemRaw);
-    const int lane = threadIdx.x & 31;
-    const bool loader = threadIdx.x < 32;
-    double dsum[1] = {0.0};
-    if (threadIdx.x == 0) {
-        for (int q = 0; q < kStreamGroups; q++) {
-            mbar_init(&sm.full[q], 32);    // the 32 loader lanes, each when its copies of the group have landed
-            mbar_init(&sm.empty[q], 32);   // the 32 compute lanes, each when it has read its part of the group
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // Both warps count the stages alike: stage = g % R; the ring is handed over in groups of kStreamG stages
-    // (group = (g / G) % groups, use = g / R); a part always starts on a group boundary.
-    unsigned g = 0;
-    if (loader) {
-        for (int P = blockIdx.x; P < a.nParts; P += gridDim.x) {
-            const int base = a.partStart[P];
-            const int S = a.partStart[P + 1] - base;
-            for (int u0 = 0; u0 < S; u0 += kStreamBatch) {
-                int4 rb[kStreamBatch];
-#pragma unroll
-                for (int j = 0; j < kStreamBatch; j++)
-                    if (u0 + j < S) rb[j] = __ldg(a.rec + (size_t(base) + u0 + j) * 32 + lane);
-#pragma unroll
-                for (int j = 0; j < kStreamBatch; j++) {
-                    if (u0 + j < S) {
-                        const unsigned s = g & (kStreamR - 1), q = s / kStreamG, use = g / kStreamR;
-                        if ((g & (kStreamG - 1)) == 0 && use > 0) mbar_wait(&sm.empty[q], (use - 1) & 1, a.err);
-                        const size_t idx = (size_t(base) + u0 + j) * 32 + lane;
-                        StreamStage& st = sm.st[s];
-                        cp_async16(&st.rec[lane], a.rec + idx);
-                        if (rb[j].x >= 0) {
-                            cp_async16(&st.pk01[lane], a.pack + idx * 4);
-                            cp_async16(&st.pk23[lane], a.pack + idx * 4 + 2);
-                            cp_async8(&st.in[lane], a.in + rb[j].x);
-                            if (BWD && a.dotWith) cp_async8(&st.dw[lane], a.dotWith + rb[j].x);
-                        }
-                        g++;
-                        if ((g & (kStreamG - 1)) == 0 || u0 + j == S - 1) mbar_arrive_on_cp_async(&sm.full[q]);
-                    }
-                }
-            }
-            g = (g + kStreamG - 1) & ~unsigned(kStreamG - 1);
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
-        const double sent = sentinel();
-#ifdef B200LS_STREAM_PROF
-        unsigned long long pWait = 0, pPoll = 0, pPolls = 0, pSteps = 0;
-        const long long pT0 = clock64();
-#endif
-        for (int P = blockIdx.x; P < a.nParts; P += gridDim.x) {
-            const int S = a.partStart[P + 1] - a.partStart[P];
-            const unsigned g0 = g;
-            // the first look at a group of stages waits for the loader; stages are looked at in order
-            auto stageRec = [&](unsigned ge) -> int4 {
-                if ((ge & (kStreamG - 1)) == 0) {
-#ifdef B200LS_STREAM_PROF
-                    const long long w0 = clock64();
-#endif
-                    mbar_wait(&sm.full[(ge & (kStreamR - 1)) / kStreamG], (ge / kStreamR) & 1, a.err);
-#ifdef B200LS_STREAM_PROF
-                    pWait += clock64() - w0;
-#endif
-                }
-                return sm.st[ge & (kStreamR - 1)].rec[lane];
-            };
-            double e0r[kStreamE], e1r[kStreamE];
-            // external values of the first kStreamE steps: always a load (a row without external dependency reads
-            // out[0] and ignores it), so that nothing depends on the result before it is used
-#pragma unroll
-            for (int j = 0; j < kStreamE; j++) {
-                e0r[j] = 0.0;
-                e1r[j] = 0.0;
-                if (j < S) {
-                    const int4 r = stageRec(g0 + j);
-                    e0r[j] = ld_l2(a.out + max(r.y, 0));
-                    e1r[j] = ld_l2(a.out + max(r.z, 0));
-                }
-            }
-            // row data of step 0 in registers; every step loads the next one before its own arithmetic
-            int4 r = sm.st[g & (kStreamR - 1)].rec[lane];
-            double2 a01 = sm.st[g & (kStreamR - 1)].pk01[lane], a23 = sm.st[g & (kStreamR - 1)].pk23[lane];
-            double inv = sm.st[g & (kStreamR - 1)].in[lane];
-            double dwv = (BWD && a.dotWith) ? sm.st[g & (kStreamR - 1)].dw[lane] : 0.0;
-            double xprev = 0.0;
-            for (int t0 = 0; t0 < S; t0 += kStreamE) {
-#pragma unroll
-                for (int j = 0; j < kStreamE; j++) {
-                    const int t = t0 + j;
-                    if (t < S) {
-                        // next step's row data (its group was waited for by the look-ahead below)
-                        const StreamStage& sn = sm.st[(g + 1) & (kStreamR - 1)];
-                        int4 rN = r;
-                        double2 a01N = a01, a23N = a23;
-                        double invN = inv, dwN = dwv;
-                        if (t + 1 < S) {
-                            rN = sn.rec[lane];
-                            a01N = sn.pk01[lane];
-                            a23N = sn.pk23[lane];
-                            invN = sn.in[lane];
-                            if (BWD && a.dotWith) dwN = sn.dw[lane];
-                        }
-                        const bool act = r.x >= 0;
-                        const unsigned m = act ? unsigned(r.w) : 0u;
-                        const int nd = m & 7;
-                        double e0 = e0r[j], e1 = e1r[j];
-                        const bool h0 = act && r.y >= 0, h1 = act && r.z >= 0;
-                        if ((h0 && is_sentinel(e0)) || (h1 && is_sentinel(e1))) {
-                            // the producer tile is not far enough ahead yet: poll (all pending values per round)
-#ifdef B200LS_STREAM_PROF
-                            const long long q0 = clock64();
-                            pPolls++;
-#endif
-                            unsigned spins = 0;
-                            while (true) {
-                                if (h0 && is_sentinel(e0)) e0 = ld_l2(a.out + r.y);
-                                if (h1 && is_sentinel(e1)) e1 = ld_l2(a.out + r.z);
-                                if (!((h0 && is_sentinel(e0)) || (h1 && is_sentinel(e1)))) break;
-                                if (++spins > kMaxSpins) {
-                                    *a.err = 1;
-                                    break;
-                                }
-                            }
-#ifdef B200LS_STREAM_PROF
-                            pPoll += clock64() - q0;
-#endif
-                        }
-                        // dependencies: previous step of this warp (shuffle) or the external values
-                        const unsigned f0 = (m >> 3) & 63u, f1 = (m >> 9) & 63u, f2 = (m >> 15) & 63u;
-                        const double s0 = __shfl_sync(0xffffffffu, xprev, int(f0 >> 1));
-                        const double s1 = __shfl_sync(0xffffffffu, xprev, int(f1 >> 1));
-                        const double s2 = __shfl_sync(0xffffffffu, xprev, int(f2 >> 1));
-                        const double v0 = (f0 & 1u) ? ((f0 & 2u) ? e1 : e0) : s0;
-                        const double v1 = (f1 & 1u) ? ((f1 & 2u) ? e1 : e0) : s1;
-                        const double v2 = (f2 & 1u) ? ((f2 & 2u) ? e1 : e0) : s2;
-                        double acc = BWD ? inv : a01.x * inv;
-                        if (nd > 0) acc -= a01.y * v0;
-                        if (nd > 1) acc -= a23.x * v1;
-                        if (nd > 2) acc -= a23.y * v2;
-                        xprev = acc;
-                        if (act) {
-                            st_l2(a.out + r.x, acc);
-                            if (a.clear) a.clear[r.x] = sent;
-                            if (BWD && a.dotWith) dsum[0] += acc * dwv;
-                        }
-                        // this lane has read everything it needs from the stages up to g: hand finished groups back
-                        if (((g + 1) & (kStreamG - 1)) == 0 || t == S - 1) mbar_arrive(&sm.empty[(g & (kStreamR - 1)) / kStreamG]);
-                        // external values of step t + kStreamE (same register slot)
-                        if (t + kStreamE < S) {
-                            const int4 rn = stageRec(g + kStreamE);
-                            e0r[j] = ld_l2(a.out + max(rn.y, 0));
-                            e1r[j] = ld_l2(a.out + max(rn.z, 0));
-                        }
-                        r = rN;
-                        a01 = a01N;
-                        a23 = a23N;
-                        inv = invN;
-                        dwv = dwN;
-                        g++;
-#ifdef B200LS_STREAM_PROF
-                        pSteps++;
-#endif
-                    }
-                }
-            }
-            g = (g + kStreamG - 1) & ~unsigned(kStreamG - 1);
-        }
-#ifdef B200LS_STREAM_PROF
-        if (a.prof) {
-            for (int o = 16; o > 0; o >>= 1) {
-                pPoll = max(pPoll, __shfl_xor_sync(0xffffffffu, pPoll, o));
-                pPolls = max(pPolls, __shfl_xor_sync(0xffffffffu, pPolls, o));
-            }
-            if (lane == 0) {
-                unsigned long long* q = a.prof + size_t(blockIdx.x) * 9;
-                q[0] = clock64() - pT0; q[1] = pWait; q[2] = pPoll; q[3] = pPolls; q[4] = pSteps;
-                q[5] = q[6] = q[7] = q[8] = 0;
-            }
-        }
-#endif
-    }
-    if (BWD && a.dotWith) {
-        if (grid_reduce<1>(dsum, a.partials, a.ticket)) a.dotOut[0] = dsum[0];
-    }
-}
-
 // Gauss-Seidel sweep (GaussSeidelSmoother.C:151-176) in gather form:
 //   psi_new[c] = ( b'[c] - sum_{nbr faces asc} lower[f]*psi_new[l] - sum_{own faces asc} upper[f]*psi_old[u] ) / diag[c]
 __global__ void __launch_bounds__(256) k_gs_sweep(SweepArgs a) {
@@ -947,7 +639,7 @@ __global__ void __launch_bounds__(256) k_gs_sweep(SweepArgs a) {
     SWEEP_TASK_LOOP(a) {
         const int2 next = SWEEP_NEXT_TASK(a);
         if (lane < task.y) {
-            const int p = task.x + lane;
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
             const int j0 = a.ptr[p], j1 = a.ptr[p + 1];
             const int k0 = a.ptr2[p], k1 = a.ptr2[p + 1];
             const double dg = a.diag[p];
@@ -999,6 +691,7 @@ static constexpr int kMaxFusedSweeps = 8;
 struct MultiSweepArgs {
     const int4* tasks;      // (start, count, sweep, -)
     int nTasks;
+    const int* rowOf;       // processing slot -> position (nullptr = identity)
     const int* Lptr;
     const int* Lcol;
     const double* Lval;
@@ -1019,7 +712,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_multi(MultiSweepArgs a) {
     for (; t < a.nTasks; t += nW) {
         const int4 next = (t + nW) < a.nTasks ? a.tasks[t + nW] : make_int4(0, 0, 0, 0);
         if (lane < task.y) {
-            const int p = task.x + lane;
+            const int p = a.rowOf ? a.rowOf[task.x + lane] : task.x + lane;
             const int s = task.z;
             const double* xo = a.X[s];
             double* xn = a.X[s + 1];

@@ -101,10 +101,35 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
     bucketSort(lf, nFwd, L.fwdOffsets, L.fwdRows);
     bucketSort(lb, nBwd, L.bwdOffsets, L.bwdRows);
 
-    // native layout: position = rank in forward-wavefront-major order
-    L.perm = L.fwdRows;
+    // native layout: structured blocks are laid out tile-major for the pencil sweeps, everything else in
+    // forward-wavefront-major order (position = rank in that order)
+    L.pencil = PencilPlan();
+    L.fwdPos.clear();
+    {
+        const char* on = getenv("B200LS_PENCIL");
+        const char* mc = getenv("B200LS_PENCIL_MIN_CELLS");
+        const int32_t minCells = mc ? int32_t(atoi(mc)) : 16384;
+        if (!(on && on[0] == '0') && nCells >= minCells) buildPencilPlan(L, L.pencil);
+    }
+    if (L.pencil.valid) {
+        const PencilPlan& P = L.pencil;
+        L.perm.resize(nCells);
+        for (const PencilTile& t : P.tiles)
+            for (int32_t i = 0; i < P.nx; i++)
+                for (int32_t kk = 0; kk < t.wk; kk++)
+                    for (int32_t jj = 0; jj < t.wj; jj++)
+                        L.perm[size_t(t.base) + size_t(i) * t.w + jj + t.wj * kk] =
+                            int32_t(i + int64_t(P.nx) * ((t.j0 + jj) + int64_t(P.ny) * (t.k0 + kk)));
+    } else {
+        L.perm = L.fwdRows;
+    }
     L.ipos.resize(nCells);
     for (int32_t p = 0; p < nCells; p++) L.ipos[L.perm[p]] = p;
+    if (L.pencil.valid) {
+        // the wavefront kernels remain usable on this layout through the processing-order -> position map
+        L.fwdPos.resize(nCells);
+        for (int32_t k = 0; k < nCells; k++) L.fwdPos[k] = L.ipos[L.fwdRows[k]];
+    }
 
     L.Lptr.assign(size_t(nCells) + 1, 0);
     L.Uptr.assign(size_t(nCells) + 1, 0);
@@ -180,21 +205,10 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         }
         if (!L.bRowPos.empty()) L.bRowPtr.push_back(int32_t(L.bEntryIface.size()));
     }
-
-    // streamed sweeps are experimental (slower than the wavefront kernels so far, profiles/experiments/README.md):
-    // plans are only built on request
-    L.fwdStream = StreamPlan();
-    L.bwdStream = StreamPlan();
-    if (const char* on = getenv("B200LS_STREAM")) {
-        if (on[0] == '1') {
-            const char* e = getenv("B200LS_STREAM_MIN_CELLS");
-            buildStreamPlans(L, e ? int32_t(atoi(e)) : 4096);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// streamed sweep plans
+// structured blocks: tile-major layout for the pencil sweeps
 // ------------------------------------------------------------------------------------------------------------
 
 static bool detectBlock(const LevelHost& L, int32_t dims[3]) {
@@ -237,115 +251,57 @@ static bool detectBlock(const LevelHost& L, int32_t dims[3]) {
     return true;
 }
 
-// parts[part][step][lane] = position or -1; dependencies from the CSR (ptr, col) in positions, processed in
-// ascending (desc = false) or descending entry order.  Fails (plan.valid = false) if a row has more than three
-// dependencies / more than two external ones, or if an external producer is not earlier in the launch order.
-static void emitStreamPlan(const std::vector<std::vector<std::array<int32_t, 32>>>& parts, int32_t nRows,
-                           const std::vector<int32_t>& ptr, const std::vector<int32_t>& col, bool desc,
-                           StreamPlan& plan) {
-    plan = StreamPlan();
-    std::vector<int32_t> wPart(nRows, -1), wStep(nRows, -1), wLane(nRows, -1);
-    plan.partStart.assign(1, 0);
-    for (size_t P = 0; P < parts.size(); P++) {
-        for (size_t s = 0; s < parts[P].size(); s++)
-            for (int lane = 0; lane < 32; lane++) {
-                const int32_t pos = parts[P][s][lane];
-                if (pos < 0) continue;
-                if (wPart[pos] >= 0) return;   // a row scheduled twice
-                wPart[pos] = int32_t(P);
-                wStep[pos] = int32_t(s);
-                wLane[pos] = lane;
-            }
-        plan.partStart.push_back(plan.partStart.back() + int32_t(parts[P].size()));
-    }
-    for (int32_t p = 0; p < nRows; p++)
-        if (wPart[p] < 0) return;              // a row not scheduled
-    const size_t total = size_t(plan.partStart.back()) * 32;
-    plan.rec.assign(total, StreamRec{-1, 0, -1, -1});
-    plan.meta.assign(total, 0u);
-    for (size_t P = 0; P < parts.size(); P++)
-        for (size_t s = 0; s < parts[P].size(); s++)
-            for (int lane = 0; lane < 32; lane++) {
-                const int32_t pos = parts[P][s][lane];
-                if (pos < 0) continue;
-                const size_t r = (size_t(plan.partStart[P]) + s) * 32 + size_t(lane);
-                StreamRec& R = plan.rec[r];
-                R.pos = pos;
-                R.ebase = ptr[pos];
-                const int32_t nd = ptr[pos + 1] - ptr[pos];
-                if (nd > 3) return;
-                uint32_t m = uint32_t(nd);
-                int nExt = 0;
-                for (int32_t k = 0; k < nd; k++) {
-                    const int32_t e = desc ? ptr[pos + 1] - 1 - k : ptr[pos] + k;
-                    const int32_t q = col[e];
-                    uint32_t field;
-                    if (wPart[q] == int32_t(P) && wStep[q] == int32_t(s) - 1) {
-                        field = uint32_t(wLane[q]) << 1;
-                    } else {
-                        const bool earlier = wPart[q] < int32_t(P) || (wPart[q] == int32_t(P) && wStep[q] < int32_t(s));
-                        if (!earlier || nExt == 2) return;
-                        (nExt == 0 ? R.ext0 : R.ext1) = q;
-                        field = 1u | (uint32_t(nExt) << 1);
-                        nExt++;
-                    }
-                    m |= field << (3 + 6 * k);
-                }
-                plan.meta[r] = m;
-            }
-    plan.nParts = int32_t(parts.size());
-    plan.valid = true;
-}
-
-void buildStreamPlans(LevelHost& L, int32_t minCells) {
-    L.fwdStream = StreamPlan();
-    L.bwdStream = StreamPlan();
-    L.blockDims[0] = L.blockDims[1] = L.blockDims[2] = 0;
+void buildPencilPlan(const LevelHost& L, PencilPlan& plan) {
+    plan = PencilPlan();
     int32_t d[3];
-    if (L.nCells < minCells || !detectBlock(L, d)) return;
+    if (!detectBlock(L, d)) return;
     const int32_t nx = d[0], ny = d[1], nz = d[2];
-    // tile of pencils (lines along i) owned by one warp: lane = jj + TJ*kk
-    const int32_t TK = nz >= 4 ? 4 : (nz >= 2 ? 2 : 1);
-    const int32_t TJ = 32 / TK;
-    const int32_t nJ = (ny + TJ - 1) / TJ, nK = (nz + TK - 1) / TK;
-    // launch order of the parts: tile wavefronts J + K (every tile depends on (J-1, K) and (J, K-1))
-    std::vector<std::pair<int32_t, int32_t>> tiles;
-    for (int32_t w = 0; w <= nJ + nK - 2; w++)
+    // pencils of a full tile: 8 x 4 in 3-D, 32 x 1 in 2-D; thin blocks take all of j and fill up along k.  WK is kept
+    // even whenever there are several tiles along k, and WJ is even whenever there are several along j: then every
+    // tile base is even (16-byte aligned rows of doubles for the bulk copies) -- only the very last tile can be odd.
+    int32_t WJ, WK;
+    if (nz == 1) {
+        WJ = std::min<int32_t>(ny, 32);
+        WK = 1;
+    } else {
+        WJ = std::min<int32_t>(ny, 8);
+        WK = std::min<int32_t>(nz, 32 / WJ);
+        if (WK < nz && WK > 1 && (WK & 1)) WK--;
+    }
+    const int32_t nJ = (ny + WJ - 1) / WJ, nK = (nz + WK - 1) / WK;
+    plan.nx = nx;
+    plan.ny = ny;
+    plan.nz = nz;
+    plan.WJ = WJ;
+    plan.WK = WK;
+    plan.nJ = nJ;
+    plan.nK = nK;
+    plan.tiles.resize(size_t(nJ) * nK);
+    int64_t base = 0;
+    for (int32_t K = 0; K < nK; K++)
+        for (int32_t J = 0; J < nJ; J++) {
+            PencilTile& t = plan.tiles[size_t(J) + size_t(nJ) * K];
+            t.j0 = J * WJ;
+            t.k0 = K * WK;
+            t.wj = std::min(WJ, ny - t.j0);
+            t.wk = std::min(WK, nz - t.k0);
+            t.w = t.wj * t.wk;
+            if (base & 1) return;   // an odd-sized tile before the last one: keep the wavefront layout
+            t.base = int32_t(base);
+            base += int64_t(nx) * t.w;
+            t.nbr[0] = J > 0 ? (J - 1) + nJ * K : -1;
+            t.nbr[1] = K > 0 ? J + nJ * (K - 1) : -1;
+            t.nbr[2] = J + 1 < nJ ? (J + 1) + nJ * K : -1;
+            t.nbr[3] = K + 1 < nK ? J + nJ * (K + 1) : -1;
+        }
+    // launch order: tile wavefronts J + K (every tile only depends on (J-1, K) and (J, K-1))
+    plan.fwdOrder.reserve(plan.tiles.size());
+    for (int32_t wv = 0; wv <= nJ + nK - 2; wv++)
         for (int32_t K = 0; K < nK; K++) {
-            const int32_t J = w - K;
-            if (J >= 0 && J < nJ) tiles.emplace_back(J, K);
+            const int32_t J = wv - K;
+            if (J >= 0 && J < nJ) plan.fwdOrder.push_back(J + nJ * K);
         }
-    std::vector<std::vector<std::array<int32_t, 32>>> fwd(tiles.size()), bwd(tiles.size());
-    for (size_t t = 0; t < tiles.size(); t++) {
-        const int32_t J = tiles[t].first, K = tiles[t].second;
-        const int32_t jn = std::min(TJ, ny - J * TJ), kn = std::min(TK, nz - K * TK);
-        const int32_t S = nx + (jn - 1) + (kn - 1);
-        auto& F = fwd[t];
-        F.resize(size_t(S));
-        for (int32_t s = 0; s < S; s++) {
-            F[s].fill(-1);
-            for (int32_t kk = 0; kk < kn; kk++)
-                for (int32_t jj = 0; jj < jn; jj++) {
-                    const int32_t i = s - jj - kk;
-                    if (i < 0 || i >= nx) continue;
-                    const int64_t c = i + int64_t(nx) * ((J * TJ + jj) + int64_t(ny) * (K * TK + kk));
-                    F[s][jj + TJ * kk] = L.ipos[size_t(c)];
-                }
-        }
-        // the backward sweep walks the same part from its last step to its first, parts in reverse order
-        auto& B = bwd[tiles.size() - 1 - t];
-        B.assign(F.rbegin(), F.rend());
-    }
-    emitStreamPlan(fwd, L.nCells, L.Lptr, L.Lcol, false, L.fwdStream);
-    emitStreamPlan(bwd, L.nCells, L.Uptr, L.Ucol, true, L.bwdStream);
-    if (!L.fwdStream.valid || !L.bwdStream.valid) {
-        L.fwdStream = StreamPlan();
-        L.bwdStream = StreamPlan();
-        return;
-    }
-    L.blockDims[0] = nx;
-    L.blockDims[1] = ny;
-    L.blockDims[2] = nz;
+    plan.valid = true;
 }
 
 std::vector<int32_t> pairAgglomerate(int32_t& nCoarseCells, const LevelHost& fine,

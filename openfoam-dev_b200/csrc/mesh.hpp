@@ -42,27 +42,28 @@ struct AgglomMaps {
     std::vector<std::vector<int32_t>> iPtr, iSrc;
 };
 
-// Streamed sweep plan (structured hex blocks): the rows are partitioned into PARTS of <=32 "pencils" (lines of cells
-// along the fastest index); one warp owns a part and walks it step by step, lane = pencil.  A dependency produced
-// by the same warp in the previous step is read from a shared-memory ring (no L2 round trip); every other
-// dependency is "external": its producer belongs to a part earlier in the launch order (or to an earlier step of
-// the same part) and is polled from global memory -- prefetched several steps ahead, which works because a part
-// naturally lags the parts it depends on.  Arithmetic and its order per row are those of the wavefront kernels.
-struct StreamRec {
-    int32_t pos;      // row position handled by this lane in this step, -1 = idle
-    int32_t ebase;    // first entry of the row in the triangle's CSR value array
-    int32_t ext0;     // positions of up to two external dependencies (-1 = none)
-    int32_t ext1;
+// Pencil plan (structured hex blocks numbered i-fastest, e.g. a blockMesh single block or a `simple` subdomain of one).
+// The rows of the level are laid out TILE-MAJOR instead of wavefront-major: a tile is a bundle of wj x wk <= 32
+// "pencils" (lines of cells along i); position = tile.base + i*tile.w + (jj + wj*kk).  One warp owns a tile and walks
+// it along i with lane = pencil; lane (jj, kk) is skewed by jj + kk steps so that the three lower neighbours of a row
+// are the lane's own previous row and the previous rows of two neighbouring lanes (registers + shuffles).  Only lanes
+// on the low-j / low-k faces of a tile read values of other tiles (tile (J-1, K) and (J, K-1)), which were launched
+// earlier (tile-wavefront order J + K).  Every per-row array is then contiguous per (tile, i-range): the kernels
+// stream it with bulk async copies and need no per-row records.  (csrc/pencil.cuh)
+struct PencilTile {
+    int32_t base;       // first position of the tile
+    int32_t w;          // lanes in use = wj*wk (row stride of the tile)
+    int32_t wj, wk;     // pencils along j / along k
+    int32_t j0, k0;     // first pencil
+    int32_t nbr[4];     // tile index of (J-1,K), (J,K-1), (J+1,K), (J,K+1) or -1
 };
-struct StreamPlan {
+struct PencilPlan {
     bool valid = false;
-    int32_t nParts = 0;
-    std::vector<int32_t> partStart;   // [nParts + 1], in steps; record index = step*32 + lane
-    std::vector<StreamRec> rec;
-    // bits 0-2: number of dependencies nd (<= 3), in processing order n = 0..nd-1 (forward: ascending CSR
-    // entries; backward: descending).  Dependency n: bit 3+6n = 1 if external, bits 4+6n .. 8+6n = source lane
-    // (internal) or external slot 0/1.
-    std::vector<uint32_t> meta;
+    int32_t nx = 0, ny = 0, nz = 0;
+    int32_t WJ = 0, WK = 0;             // pencils of a full tile
+    int32_t nJ = 0, nK = 0;             // tiles along j / k
+    std::vector<PencilTile> tiles;      // memory order: J fastest
+    std::vector<int32_t> fwdOrder;      // launch order of the forward sweeps (tile wavefronts); backward = reversed
 };
 
 struct LevelHost {
@@ -72,7 +73,8 @@ struct LevelHost {
     std::vector<int32_t> fwdOffsets, fwdRows, bwdOffsets, bwdRows;   // canonical wavefronts (cells)
     int32_t maxFwdSpan = 1;         // max over faces of Lf[upper] - Lf[lower] (1 on structured blocks)
 
-    // ---- native layout: rows in forward-wavefront-major order ("positions") ----
+    // ---- native layout: rows at "positions": forward-wavefront-major order, or tile-major when the level has a
+    // pencil plan ----
     std::vector<int32_t> perm;      // position -> cell
     std::vector<int32_t> ipos;      // cell -> position
     std::vector<int32_t> Lptr, Lcol, Lface;   // neighbour-side entries of each row (ascending face)
@@ -80,10 +82,10 @@ struct LevelHost {
     std::vector<int32_t> Lidx, Uidx;          // face -> entry index in the L / U arrays
     std::vector<SweepTask> fwdTasks, bwdTasks;
     std::vector<int32_t> bwdPos;    // backward processing order -> position
+    std::vector<int32_t> fwdPos;    // forward processing order -> position (empty = identity: wavefront-major layout)
 
-    // ---- streamed sweeps (empty unless the addressing is a structured block, see buildStreamPlans) ----
-    int32_t blockDims[3] = {0, 0, 0};
-    StreamPlan fwdStream, bwdStream;
+    // ---- structured block: tile-major layout + pencil sweeps (invalid otherwise) ----
+    PencilPlan pencil;
 
     std::vector<HostInterface> interfaces;
     // rows touched by interfaces: boundary-row CSR in (patch, face) order
@@ -117,9 +119,10 @@ struct HostMesh {
 void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
                 std::vector<HostInterface> interfaces);
 
-// Detects an nx*ny*nz hex block numbered i-fastest (blockMesh single block) and builds the streamed sweep plans
-// for it; leaves them invalid otherwise.  minCells: do not bother below this size.
-void buildStreamPlans(LevelHost& L, int32_t minCells);
+// Detects an nx*ny*nz hex block numbered i-fastest with faces in upper-triangular order (blockMesh single block)
+// and chooses the pencil tiling; plan.valid stays false otherwise.  Called by buildLevel (B200LS_PENCIL=0 disables,
+// B200LS_PENCIL_MIN_CELLS sets the size below which the wavefront layout is kept).
+void buildPencilPlan(const LevelHost& L, PencilPlan& plan);
 
 // pairGAMGAgglomeration::agglomerate(nCoarseCells, addressing, weights) (pairGAMGAgglomerate.C:123-301).
 // `forward` is the reference's static forward_ flag: read, used, and toggled.

@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "kernels.cuh"
+#include "pencil.cuh"
 
 namespace b200ls {
 
@@ -95,32 +96,50 @@ static void launchSweep(K kernel, SweepArgs& a) {
     c.launches++;
 }
 
-// Streamed sweeps: one loader/compute warp pair per part, all resident at once (cooperative launch guarantees co-residency of the grid,
-// which the cross-part polling needs).
-template <typename K>
-static void launchStream(K kernel, StreamArgs& a) {
-    if (a.nParts == 0) return;
-    static std::map<const void*, int> occCache;
+// Pencil sweeps (pencil.cuh): one chain/helper warp pair per tile, persistent over the tile list.  Cooperative launch:
+// a tile polls values of tiles earlier in the launch order, which must be resident or finished.
+template <int MODE, int SKEW, int NS>
+static void launchPencilCfg(PencilArgs& a, int cols) {
+    if (a.nTiles == 0) return;
     Context& c = ctx();
-    const size_t smem = sizeof(StreamSmem);
+    constexpr bool GS = PencilTraits<MODE>::GS;
+    auto kernel = k_pencil<MODE, SKEW, NS>;
+    const int sideCols = std::max(1, cols) * (GS ? 2 : 1);
+    a.window = std::max(1, std::min(16, (32 * kPencilMaxE) / sideCols));
+    const size_t smem = size_t(pencilSmemBytes<MODE, NS>(a.extW));
+    static std::map<size_t, int> occCache;   // per instantiation (static in a template function), keyed by smem size
     int occ;
-    auto it = occCache.find((const void*)kernel);
+    auto it = occCache.find(smem);
     if (it == occCache.end()) {
         B2_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 64, smem));
-        occCache[(const void*)kernel] = occ;
+        occCache[smem] = occ;
     } else {
         occ = it->second;
     }
-    if (occ < 1) throw CudaError("streamed sweep kernel does not fit on an SM");
-    const int blocks = std::max(1, std::min(occ * c.numSMs, a.nParts));
+    if (occ < 1) throw CudaError("pencil sweep kernel does not fit on an SM");
+    static const int cap = getenv("B200LS_PENCIL_CTAS_PER_SM") ? atoi(getenv("B200LS_PENCIL_CTAS_PER_SM")) : 0;
+    if (cap > 0) occ = std::min(occ, cap);
+    const int blocks = std::max(1, std::min(occ * c.numSMs, a.nTiles));
     a.err = c.errFlag.p;
     a.partials = c.partials.p;
     a.ticket = c.ticket.p;
     void* args[] = {&a};
-    B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(64), args, smem,
-                                        c.stream));
+    B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(64), args, smem, c.stream));
     c.launches++;
+}
+
+// ring depth / skew per mode; B200LS_PENCIL_CFG=<skew><stages> (e.g. 18, 28, 14) overrides the substitution sweeps
+template <int MODE>
+static void launchPencil(PencilArgs& a, int cols) {
+    static const int cfg = getenv("B200LS_PENCIL_CFG") ? atoi(getenv("B200LS_PENCIL_CFG")) : 0;
+    if (MODE == PM_FWD || MODE == PM_BWD) {
+        if (cfg == 14) return launchPencilCfg<MODE, 1, 4>(a, cols);
+        if (cfg == 18) return launchPencilCfg<MODE, 1, 8>(a, cols);
+        return launchPencilCfg<MODE, 2, 8>(a, cols);
+    }
+    if (cfg / 10 == 2) return launchPencilCfg<MODE, 2, 4>(a, cols);
+    return launchPencilCfg<MODE, 1, 4>(a, cols);
 }
 
 void checkSweepError() {
@@ -186,25 +205,40 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         if (D.hasLslot) D.Lslot.upload(slot, s);
         B2_CUDA(cudaStreamSynchronize(s));   // ltou/slot are temporaries
     }
-    // streamed sweep plans of structured blocks
-    D.hasStream = H.fwdStream.valid && H.bwdStream.valid;
-    D.nStreamParts = D.hasStream ? H.fwdStream.nParts : 0;
-    if (D.hasStream) {
-        D.sFwdPartStart.upload(H.fwdStream.partStart, s);
-        D.sBwdPartStart.upload(H.bwdStream.partStart, s);
-        D.nStreamRec = H.fwdStream.rec.size();
-        for (int dir = 0; dir < 2; dir++) {
-            const StreamPlan& pl = dir ? H.bwdStream : H.fwdStream;
-            std::vector<int4> rec(pl.rec.size());
-            std::vector<int> eb(pl.rec.size());
-            for (size_t i = 0; i < pl.rec.size(); i++) {
-                rec[i] = make_int4(pl.rec[i].pos, pl.rec[i].ext0, pl.rec[i].ext1, int(pl.meta[i]));
-                eb[i] = pl.rec[i].ebase;
+    // structured blocks: tile table of the pencil sweeps
+    D.hasPencil = H.pencil.valid;
+    D.fwdPos.upload(H.fwdPos, s);
+    D.nPencilTiles = 0;
+    if (D.hasPencil) {
+        const PencilPlan& P = H.pencil;
+        D.pNx = P.nx;
+        D.pNy = P.ny;
+        D.pNz = P.nz;
+        D.pWJ = P.WJ;
+        D.pWK = P.WK;
+        D.pCols = (P.nJ > 1 ? P.WK : 0) + (P.nK > 1 ? P.WJ : 0);
+        std::vector<PencilTileDev> tiles(P.tiles.size());
+        for (size_t t = 0; t < P.tiles.size(); t++) {
+            const PencilTile& h = P.tiles[t];
+            PencilTileDev& d = tiles[t];
+            d.base = h.base;
+            d.w = h.w;
+            d.wj = h.wj;
+            d.wk = h.wk;
+            d.j0 = h.j0;
+            d.k0 = h.k0;
+            d.pad0 = d.pad1 = 0;
+            for (int q = 0; q < 4; q++) {
+                const int nb = h.nbr[q];
+                d.nbrBase[q] = nb >= 0 ? P.tiles[nb].base : -1;
+                d.nbrW[q] = nb >= 0 ? P.tiles[nb].w : 1;
+                d.nbrWj[q] = nb >= 0 ? P.tiles[nb].wj : 1;
             }
-            (dir ? D.sBwdRec : D.sFwdRec).upload(rec, s);
-            (dir ? D.sBwdEbase : D.sFwdEbase).upload(eb, s);
-            B2_CUDA(cudaStreamSynchronize(s));
         }
+        D.pTiles.upload(tiles, s);
+        D.pOrder.upload(P.fwdOrder, s);
+        D.nPencilTiles = int(tiles.size());
+        B2_CUDA(cudaStreamSynchronize(s));   // `tiles` is a temporary
     }
     static_assert(sizeof(SweepTask) == sizeof(int2), "task layout");
     D.nFwdTasks = int(H.fwdTasks.size());
@@ -485,7 +519,10 @@ void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, cons
     setupIfaceViews(m, 0);
     B2_CUDA(cudaStreamSynchronize(s));
     checkLaunch("matrixSet");
-    for (auto& L : m->levels) L.rDValid = false;
+    for (auto& L : m->levels) {
+        L.rDValid = false;
+        L.pPlanesValid = false;
+    }
     m->coarseValid = false;
     m->valuesSet = true;
 }
@@ -624,13 +661,48 @@ static void ensureLevelScratch(b200ls_matrix_s* m, int level) {
     }
 }
 
+// ---- pencil levels (structured blocks, pencil.cuh) ----
+
+static bool usePencil(const DevLevel& D) {
+    if (!D.hasPencil) return false;
+    const char* e = getenv("B200LS_PENCIL_SWEEPS");   // "0": run the wavefront kernels on the tile-major layout
+    return !(e && e[0] == '0');
+}
+// planes are [slot][position] with an even stride (16-byte aligned rows for the bulk copies)
+static size_t planeStride(const DevLevel& D) { return (size_t(D.nCells) + 1) & ~size_t(1); }
+static dim3 pencilGrid(const DevLevel& D) { return dim3(unsigned(std::max(1, (D.pNx * 32 + 255) / 256)), unsigned(D.nPencilTiles)); }
+
+static PencilArgs pencilArgs(const DevLevel& D, bool gs) {
+    PencilArgs a{};
+    a.tiles = D.pTiles.p;
+    a.order = D.pOrder.p;
+    a.nTiles = D.nPencilTiles;
+    a.nx = D.pNx;
+    a.ny = D.pNy;
+    a.nz = D.pNz;
+    a.extW = (D.pWJ + D.pWK) * (gs ? 2 : 1);
+    return a;
+}
+
+static void ensurePencilPlanes(b200ls_matrix_s* m, int level) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    if (M.pPlanesValid) return;
+    const size_t np = planeStride(D);
+    M.pcL.alloc(3 * np);
+    M.pcU.alloc(3 * np);
+    if (!m->symmetric) M.pcLu.alloc(3 * np);
+    LAUNCH(k_pencil_planes, pencilGrid(D), 256, M.pcL.p, m->symmetric ? nullptr : M.pcLu.p, M.pcU.p, D.pTiles.p, D.pNx,
+           D.pNy, D.pNz, np, D.Lptr.p, M.Lval(D.nFaces), D.LtoU.p, D.Uptr.p, M.Uval());
+    M.pPlanesValid = true;
+}
+
 void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     const int kind = (precond == B200LS_DIAGONAL) ? B200LS_DIAGONAL : B200LS_DIC;   // DIC and DILU share rD
     if (M.rDValid && M.rDKind == kind) return;
     M.rDKind = kind;
-    M.sPackValid = false;
     M.rD.alloc(D.nCells);
     if (precond == B200LS_DIAGONAL) {
         // rD = 1/diag (diagonalPreconditioner.C:59-62)
@@ -643,9 +715,30 @@ void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
     }
     M.dWork.alloc(D.nCells);
     fillSentinel(M.dWork.p, D.nCells);
+    if (usePencil(D)) {
+        // structured block: pencil factorisation, then the pre-multiplied substitution coefficients
+        ensurePencilPlanes(m, level);
+        const size_t np = planeStride(D);
+        PencilArgs a = pencilArgs(D, false);
+        a.plane[0] = M.diag.p;
+        for (int q = 0; q < 3; q++) {
+            a.plane[1 + q] = M.pcL.p + q * np;
+            a.plane[4 + q] = m->symmetric ? nullptr : M.pcLu.p + q * np;
+        }
+        a.out = M.dWork.p;
+        a.out2 = M.rD.p;
+        launchPencil<PM_FACTOR>(a, D.pCols);
+        M.ptL.alloc(3 * np);
+        M.ptU.alloc(3 * np);
+        LAUNCH(k_pencil_pack, pencilGrid(D), 256, M.ptL.p, M.ptU.p, M.pcL.p, M.pcU.p, M.rD.p, D.pTiles.p, D.pNx, D.pNy,
+               D.pNz, np);
+        M.rDValid = true;
+        return;
+    }
     SweepArgs a{};
     a.tasks = D.fwdTasks.p;
     a.nTasks = D.nFwdTasks;
+    a.rowOf = D.fwdPos.p;
     a.ptr = D.Lptr.p;
     a.col = D.Lcol.p;
     a.val = M.Lval(D.nFaces);
@@ -681,48 +774,31 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
         fillSentinel(M.tmpA.p, n);
         M.tmpASentinel = true;
     }
-    // experimental (profiles/experiments/README.md): opt-in until it beats the wavefront kernel
-    const char* streamEnv = getenv("B200LS_STREAM");
-    if (D.hasStream && streamEnv && streamEnv[0] == '1') {
-        // structured block: warp-owned pencil tiles, dependencies through shared memory (k_stream_sweep)
-        if (!M.sPackValid) {
-            // once per factorisation: coefficients in stream order, pre-multiplied by rD
-            M.sFwdPack.alloc(D.nStreamRec * 4);
-            M.sBwdPack.alloc(D.nStreamRec * 4);
-            const int grid = int(std::min<size_t>((D.nStreamRec + 255) / 256, size_t(8) * ctx().numSMs));
-            LAUNCH(k_stream_pack, grid, 256, M.sFwdPack.p, D.sFwdRec.p, D.sFwdEbase.p, M.rD.p, M.Lval(D.nFaces),
-                   D.nStreamRec, 0);
-            LAUNCH(k_stream_pack, grid, 256, M.sBwdPack.p, D.sBwdRec.p, D.sBwdEbase.p, M.rD.p, M.Uval(),
-                   D.nStreamRec, 1);
-            M.sPackValid = true;
-        }
-        StreamArgs f{};
-        f.partStart = D.sFwdPartStart.p;
-        f.nParts = D.nStreamParts;
-        f.rec = D.sFwdRec.p;
-        f.pack = M.sFwdPack.p;
-        f.in = rA;
+    if (usePencil(D)) {
+        const size_t np = planeStride(D);
+        PencilArgs f = pencilArgs(D, false);
+        f.plane[0] = rA;
+        f.plane[1] = M.rD.p;
+        for (int q = 0; q < 3; q++) f.plane[2 + q] = M.ptL.p + q * np;
         f.out = M.tmpA.p;
         f.clear = wA;
-        launchStream(k_stream_sweep<false>, f);
-        StreamArgs b{};
-        b.partStart = D.sBwdPartStart.p;
-        b.nParts = D.nStreamParts;
-        b.rec = D.sBwdRec.p;
-        b.pack = M.sBwdPack.p;
-        b.in = M.tmpA.p;
+        launchPencil<PM_FWD>(f, D.pCols);
+        PencilArgs b = pencilArgs(D, false);
+        b.plane[0] = M.tmpA.p;
+        for (int q = 0; q < 3; q++) b.plane[1 + q] = M.ptU.p + q * np;
         b.out = wA;
         b.clear = M.tmpA.p;
-        if (dotOut) {
-            b.dotWith = rA;
+        if (dotOut) {   // fused wA.rA
+            b.plane[4] = rA;
             b.dotOut = dotOut;
         }
-        launchStream(k_stream_sweep<true>, b);
+        launchPencil<PM_BWD>(b, D.pCols);
         return;
     }
     SweepArgs f{};
     f.tasks = D.fwdTasks.p;
     f.nTasks = D.nFwdTasks;
+    f.rowOf = D.fwdPos.p;
     f.ptr = D.Lptr.p;
     f.col = D.Lcol.p;
     f.val = M.Lval(D.nFaces);
@@ -767,8 +843,10 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
     // sweep must come earlier in the task order (deadlock freedom), so sweep s starts lag = maxFwdSpan + 1
     // wavefronts after sweep s-1 (2 on structured blocks)
     const int lag = D.maxFwdSpan + 1;
-    if (smoother == B200LS_GAUSS_SEIDEL && D.nIfaces == 0 && nSweeps >= 2 && nSweeps <= kMaxFusedSweeps && !noFusedGS &&
-        2 * lag <= D.nFwdLevels) {
+    const bool pencil = usePencil(D);
+    if (pencil) ensurePencilPlanes(m, level);
+    if (!pencil && smoother == B200LS_GAUSS_SEIDEL && D.nIfaces == 0 && nSweeps >= 2 && nSweeps <= kMaxFusedSweeps &&
+        !noFusedGS && 2 * lag <= D.nFwdLevels) {
         // all sweeps in one pipelined launch (k_gs_multi): chain of nLevels + lag*(nSweeps-1) hops instead of
         // nSweeps*nLevels.  Needs no communication between sweeps, so only levels without processor interfaces.
         auto it = D.multiSweepTasks.find(nSweeps);
@@ -803,6 +881,7 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
         MultiSweepArgs a{};
         a.tasks = it->second.p;
         a.nTasks = int(it->second.n);
+        a.rowOf = D.fwdPos.p;
         a.Lptr = D.Lptr.p;
         a.Lcol = D.Lcol.p;
         a.Lval = M.Lval(D.nFaces);
@@ -842,9 +921,36 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
             // earlier wavefront than row p), so only the first sweep of a call needs a fill kernel
             const bool rearm = (smoother == B200LS_GAUSS_SEIDEL);
             if (!(rearm && sweep > 0)) fillSentinel(spare, n);
+            if (pencil) {
+                const size_t np = planeStride(D);
+                PencilArgs a = pencilArgs(D, true);
+                a.plane[0] = bPrime;
+                a.plane[1] = M.diag.p;
+                for (int q = 0; q < 3; q++) {
+                    a.plane[2 + q] = M.pcL.p + q * np;
+                    a.plane[5 + q] = M.pcU.p + q * np;
+                }
+                a.plane[8] = psi;
+                a.out = spare;
+                a.clear = (rearm && sweep + 1 < nSweeps) ? psi : nullptr;
+                launchPencil<PM_GS_FWD>(a, D.pCols);
+                if (smoother == B200LS_GAUSS_SEIDEL) {
+                    std::swap(psi, spare);
+                    continue;
+                }
+                // symGaussSeidel: reverse loop over the forward result (symGaussSeidelSmoother.C:178-205)
+                fillSentinel(psi, n);
+                PencilArgs r = a;
+                r.plane[8] = spare;
+                r.out = psi;
+                r.clear = nullptr;
+                launchPencil<PM_GS_REV>(r, D.pCols);
+                continue;
+            }
             SweepArgs a{};
             a.tasks = D.fwdTasks.p;
             a.nTasks = D.nFwdTasks;
+            a.rowOf = D.fwdPos.p;
             a.ptr = D.Lptr.p;
             a.col = D.Lcol.p;
             a.val = M.Lval(D.nFaces);

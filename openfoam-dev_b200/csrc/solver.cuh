@@ -12,8 +12,10 @@ struct MatLevel {
     DevBuf<double> vals;            // [Uval (nFaces) | Lval (nFaces)]
     DevBuf<double> rD;              // DIC/DILU reciprocal diagonal
     bool rDValid = false;
-    b200ls::DevBuf<double> sFwdPack, sBwdPack;   // streamed sweeps: {rD, rD*c} in stream order (valid with rD)
-    bool sPackValid = false;
+    // pencil levels: coefficient planes [slot][position] (pencil.cuh k_pencil_planes / k_pencil_pack)
+    DevBuf<double> pcL, pcLu, pcU;  // lower-side (K-, J-, I-) lower / upper coefficients, upper-side (I+, J+, K+)
+    DevBuf<double> ptL, ptU;        // rD*lower in forward order, rD*upper in backward order (valid with rD)
+    bool pPlanesValid = false;
     int rDKind = -1;                // which preconditioner rD belongs to (DIC/DILU vs diagonal)
     DevBuf<double> dWork;           // factorisation scratch (pre-reciprocal diagonal, sentinel protocol)
     // interfaces: coefficients, send/recv buffers

@@ -150,31 +150,6 @@ def test_solve_dev_matches_host_pointer_solve():
     assert perf_d.kernelLaunches > 0 and perf_d.solveMs > 0
 
 
-@pytest.mark.parametrize("shape", [(12, 10, 9), (5, 40, 3), (7, 6, 1), (33, 1, 1), (9, 8, 2), (4, 37, 5), (40, 33, 17)])
-@pytest.mark.parametrize("sym", [True, False])
-def test_streamed_sweeps_of_structured_blocks_bit_exact(shape, sym, monkeypatch):
-    """k_stream_sweep (warp-owned pencil tiles; structured blocks only) against the C oracle: precondition bit for
-    bit -- twice, so that the sentinel re-arming between calls is exercised -- and a PCG / PBiCGStab solve."""
-    monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
-    monkeypatch.setenv("B200LS_STREAM", "1")
-    nx, ny, nz = shape
-    s = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if sym else \
-        cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
-    mesh, mat = capi.from_system(s)
-    assert mesh.get_i32(20, 0).size > 1          # the level has a stream plan
-    S = orc.System(s)
-    kind = "DIC" if sym else "DILU"
-    for seed in (0.37, 0.11):
-        rA = np.cos(seed * np.arange(s.n_cells)) + 0.1
-        assert np.array_equal(mat.precondition(kind, rA), orc.precondition(S, kind, rA))
-    solver = "PCG" if sym else "PBiCGStab"
-    psi, perf = mat.solve(capi.controls(solver, kind, tolerance=1e-10, relTol=0.0), s.source)
-    xo, po = orc.solve(S, solver, orc.controls(kind, tolerance=1e-10), s.source)
-    assert abs(perf.nIterations - po["nIterations"]) <= 1
-    if perf.nIterations == po["nIterations"]:
-        assert max_rel_diff(psi, xo) <= 1e-9
-
-
 def test_diagonal_solver():
     """diagonalSolver.C:62-79: psi = source/diag, zero residuals, zero iterations, converged."""
     s = cases.convection_diffusion(9, 7, 5, dt_coeff=50.0)

@@ -237,92 +237,151 @@ def test_cyclic_patch_validation():
     capi.Mesh(24, lower, upper, [a, b])
 
 
-def _emulate_stream_precondition(mesh, s, rA):
-    """Executes the streamed sweep plans (mesh.hpp StreamPlan) exactly as k_stream_sweep does, part after part in
-    launch order: internal dependencies come from the previous step of the same part, external ones must already
-    have been published (asserted).  Returns wA in cell order."""
+def _emulate_pencil_precondition(mesh, s, rA, skew=2):
+    """Executes the pencil schedule (mesh.hpp PencilPlan, csrc/pencil.cuh) step by step: tiles in launch order, lane =
+    pencil, lane (jj, kk) skewed by skew*(jj + kk) steps; the lower neighbours of a row are the lane's own previous
+    result, the results two neighbouring lanes produced `skew` steps earlier, or -- on the low faces of a tile --
+    values of tiles (J-1, K) / (J, K-1), which must already be complete (asserted).  The backward sweep runs the
+    same schedule on reflected coordinates.  Arithmetic order as in k_pencil.  Returns wA in cell order."""
     g = lambda w: mesh.get_i32(w, 0)   # noqa: E731
     perm = g(13)
-    lface, uface = g(16), g(19)
+    nx, ny, nz, WJ, WK, nJ, nK = g(21)
+    tiles = g(22).reshape(-1, 10)
+    order = g(23)
+    lptr, lface, uptr, uface = g(14), g(16), g(17), g(19)
     n = s.n_cells
-    rd_cell = np.empty(n)
     import sys as _sys
     _sys.path.insert(0, str(ROOT / "oracle"))
     import ldu_oracle as orc
-    S = orc.System(s)
-    rd_cell = orc.reciprocal_d(S)
+    rD = orc.reciprocal_d(orc.System(s))[perm]
     lower_c = s.upper_coeffs if s.lower_coeffs is None else s.lower_coeffs
-    rD = rd_cell[perm]
-    out = {}
-    for which, vals, face_of, desc, src in (("fwd", lower_c, lface, False, None), ("bwd", s.upper_coeffs, uface, True, "fwd")):
-        base = 20 if which == "fwd" else 23
-        part_start, rec, meta = g(base), g(base + 1).reshape(-1, 4), g(base + 2).view(np.uint32)
-        assert part_start.size > 1, "no stream plan"
-        x = np.full(n, np.nan)
-        inp = rA[perm] if which == "fwd" else out["fwd"]
-        for P in range(part_start.size - 1):
-            prev = np.full(32, np.nan)
-            for st in range(part_start[P], part_start[P + 1]):
-                cur = np.full(32, np.nan)
-                for lane in range(32):
-                    pos, ebase, e0, e1 = rec[st * 32 + lane]
-                    if pos < 0:
+    # coefficient planes exactly as k_pencil_planes / k_pencil_pack build them
+    tL = np.zeros((3, n))
+    tU = np.zeros((3, n))
+    ijk = np.empty((n, 3), np.int64)
+    for p in range(n):
+        c = perm[p]
+        i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+        ijk[p] = (i, j, k)
+        e = lptr[p]
+        for slot, has in enumerate((k > 0, j > 0, i > 0)):
+            if has:
+                tL[slot, p] = rD[p] * lower_c[lface[e]]
+                e += 1
+        assert e == lptr[p + 1]
+        e = uptr[p]
+        cu = [0.0, 0.0, 0.0]
+        for slot, has in enumerate((i < nx - 1, j < ny - 1, k < nz - 1)):
+            if has:
+                cu[slot] = s.upper_coeffs[uface[e]]
+                e += 1
+        assert e == uptr[p + 1]
+        for slot, has in enumerate((k < nz - 1, j < ny - 1, i < nx - 1)):
+            if has:
+                tU[slot, p] = rD[p] * cu[2 - slot]
+    fin = rA[perm]
+    y = np.full(n, np.nan)
+    z = np.full(n, np.nan)
+    for direction, src, dst, t in ((1, fin, y, tL), (-1, y, z, tU)):
+        done_tiles = set()
+        for ti in (order if direction > 0 else order[::-1]):
+            base, w, wj, wk, j0, k0, nJm, nKm, nJp, nKp = tiles[ti]
+            nbJ, nbK = (nJm, nKm) if direction > 0 else (nJp, nKp)
+            for nb in (nbJ, nbK):
+                assert nb < 0 or nb in done_tiles, "neighbour tile not launched earlier"
+            hist = {}   # step -> per-lane value
+            S = nx + skew * (wj - 1 + wk - 1)
+            for st in range(S):
+                cur = np.zeros(32)
+                for lane in range(w):
+                    jj, kk = lane % wj, lane // wj
+                    jr, kr = (jj, kk) if direction > 0 else (wj - 1 - jj, wk - 1 - kk)
+                    r = st - skew * (jr + kr)
+                    if not (0 <= r < nx):
                         continue
-                    m = int(meta[st * 32 + lane])
-                    nd = m & 7
-                    acc = rD[pos] * inp[pos] if which == "fwd" else inp[pos]
-                    for k in range(nd):
-                        fld = (m >> (3 + 6 * k)) & 63
-                        if fld & 1:
-                            q = (e0, e1)[(fld >> 1) & 1]
-                            assert q >= 0 and not np.isnan(x[q]), "external dependency not yet published"
-                            v = x[q]
+                    i = r if direction > 0 else nx - 1 - r
+                    p = base + i * w + lane
+                    assert tuple(ijk[p]) == (i, j0 + jj, k0 + kk)
+
+                    def nbr_value(is_j):
+                        ext = (jr == 0) if is_j else (kr == 0)
+                        if not ext:
+                            src_lane = lane - direction * (1 if is_j else wj)
+                            return hist[st - skew][src_lane]
+                        nb = nbJ if is_j else nbK
+                        if nb < 0:
+                            return 0.0
+                        b2, w2, wj2, wk2 = tiles[nb][:4]
+                        if is_j:
+                            l2 = (wj2 - 1 if direction > 0 else 0) + wj2 * kk
                         else:
-                            v = prev[fld >> 1]
-                            assert not np.isnan(v), "internal dependency missing in the previous step"
-                        e = ebase + (nd - 1 - k if desc else k)
-                        acc -= (rD[pos] * vals[face_of[e]]) * v
+                            l2 = jj + wj2 * (wk2 - 1 if direction > 0 else 0)
+                        v = dst[b2 + i * w2 + l2]
+                        assert not np.isnan(v)
+                        return v
+                    vK, vJ = nbr_value(False), nbr_value(True)
+                    y1 = hist[st - 1][lane] if st > 0 else 0.0
+                    acc = rD[p] * src[p] if direction > 0 else src[p]
+                    acc -= t[0, p] * vK
+                    acc -= t[1, p] * vJ
+                    acc -= t[2, p] * y1
                     cur[lane] = acc
-                    assert np.isnan(x[pos])
-                    x[pos] = acc
-                prev = cur
-        assert not np.isnan(x).any()
-        out[which] = x
+                    assert np.isnan(dst[p])
+                    dst[p] = acc
+                hist[st] = cur
+                hist.pop(st - skew - 1, None)
+            done_tiles.add(ti)
+        assert not np.isnan(dst).any()
     wA = np.empty(n)
-    wA[perm] = out["bwd"]
+    wA[perm] = z
     return wA
 
 
-@pytest.mark.parametrize("shape", [(12, 10, 9), (5, 40, 3), (7, 6, 1), (33, 1, 1), (9, 8, 2), (4, 37, 5)])
+@pytest.mark.parametrize("shape", [(12, 10, 9), (5, 40, 3), (7, 6, 1), (33, 1, 1), (9, 8, 2), (4, 37, 5), (16, 17, 13)])
 @pytest.mark.parametrize("sym", [True, False])
-def test_stream_plan_reproduces_the_precondition_bit_for_bit(shape, sym, monkeypatch):
-    """The streamed schedule of structured blocks (pencil tiles, parts in tile-wavefront order) is a valid
-    topological order and, with the kernel's arithmetic, reproduces DIC/DILU precondition exactly."""
+def test_pencil_schedule_reproduces_the_precondition_bit_for_bit(shape, sym, monkeypatch):
+    """The tile-major layout and the pencil schedule of structured blocks (tiles in tile-wavefront order, skewed
+    lanes) are a valid topological order and, with the kernel's arithmetic, reproduce DIC/DILU precondition exactly."""
     import sys as _sys
     _sys.path.insert(0, str(ROOT / "oracle"))
     import ldu_oracle as orc
 
-    monkeypatch.setenv("B200LS_STREAM", "1")
-    monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
+    monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
     nx, ny, nz = shape
     s = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if sym else cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0)
     mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
+    assert list(mesh.get_i32(21, 0)[:3]) == [nx, ny, nz]
+    perm = mesh.get_i32(13, 0)
+    assert np.array_equal(np.sort(perm), np.arange(s.n_cells))
+    # every tile starts on an even position (16-byte aligned rows for the bulk copies) and tiles are contiguous
+    tiles = mesh.get_i32(22, 0).reshape(-1, 10)
+    assert (tiles[:, 0] % 2 == 0).all()
+    assert np.array_equal(tiles[1:, 0], np.cumsum(nx * tiles[:-1, 1]))
+    # the forward processing order handed to the wavefront kernels visits the canonical wavefronts
+    fwd_pos = mesh.get_i32(20, 0)
+    assert np.array_equal(perm[fwd_pos], mesh.get_i32(4, 0))
     rA = np.cos(0.37 * np.arange(s.n_cells)) + 0.1
-    got = _emulate_stream_precondition(mesh, s, rA)
     want = orc.precondition(orc.System(s), "DIC" if sym else "DILU", rA)
-    assert np.array_equal(got, want)
+    for skew in (1, 2):
+        got = _emulate_pencil_precondition(mesh, s, rA, skew)
+        assert np.array_equal(got, want)
 
 
-def test_no_stream_plan_for_unstructured_addressing(monkeypatch):
-    monkeypatch.setenv("B200LS_STREAM", "1")
-    monkeypatch.setenv("B200LS_STREAM_MIN_CELLS", "0")
+def test_no_pencil_plan_for_unstructured_addressing(monkeypatch):
+    monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
     s = cases.random_graph(300, symmetric=True)
     mesh = capi.Mesh(s.n_cells, s.lower, s.upper)
-    assert mesh.get_i32(20, 0).size == 0
+    assert mesh.get_i32(21, 0).size == 0 and mesh.get_i32(20, 0).size == 0
     # a block with one face missing is not a block either
     lower, upper, _ = cases.block_addressing(6, 5, 4)
     mesh = capi.Mesh(120, np.delete(lower, 17), np.delete(upper, 17))
-    assert mesh.get_i32(20, 0).size == 0
-    # and nothing is built unless asked for
-    monkeypatch.delenv("B200LS_STREAM")
-    assert capi.Mesh(120, lower, upper).get_i32(20, 0).size == 0
+    assert mesh.get_i32(21, 0).size == 0
+    # small blocks keep the wavefront-major layout unless asked, and B200LS_PENCIL=0 switches the plan off
+    monkeypatch.delenv("B200LS_PENCIL_MIN_CELLS")
+    m0 = capi.Mesh(120, lower, upper)
+    assert m0.get_i32(21, 0).size == 0
+    assert np.array_equal(m0.get_i32(13, 0), m0.get_i32(4, 0))
+    monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
+    assert capi.Mesh(120, lower, upper).get_i32(21, 0).size == 7
+    monkeypatch.setenv("B200LS_PENCIL", "0")
+    assert capi.Mesh(120, lower, upper).get_i32(21, 0).size == 0
