@@ -151,6 +151,7 @@ struct DevLevel {
     bool hasPencil = false;
     int pNx = 0, pNy = 0, pNz = 0, pWJ = 0, pWK = 0;
     int pCols = 0;                                  // neighbour values an interior tile needs per step (one side)
+    int pSkewUnits = 0;                             // (WJ-1) + (WK-1): skew of the last lane of a full tile, in units of SKEW
     DevBuf<PencilTileDev> pTiles;
     DevBuf<int> pOrder;
     int nPencilTiles = 0;

@@ -55,12 +55,26 @@ struct PencilArgs {
     double* out;            // sentinel-armed result
     double* out2;           // PM_FACTOR: reciprocal
     double* clear;          // optional: entry p is re-armed with the sentinel once row p is done
-    // optional fused dot product of the result with plane[4] (PM_BWD)
+    // optional fused dot product of the result with plane[4] (PM_BWD; plane[4] must be set iff dotOut is)
     double* dotOut;
     double* partials;
     unsigned int* ticket;
     int* err;
+    // debugging aid (B200LS_PENCIL_PROF): 16 counters per tile in launch order --
+    // chain: start, end (globaltimer ns), cycles waiting for records, for result-ring space;
+    // prep: cycles waiting for operands, neighbour values, record slots; writer: cycles waiting for results;
+    // helper: polling rounds, cycles waiting for ring capacity
+    unsigned long long* prof;
+    int debug;              // B200LS_PENCIL_DEBUG bits: 1 = no record prefetch, 2 = slow helper rounds
+    double* trace;          // B200LS_PENCIL_TRACE: [role][tile][step] value handled by lane `traceLane`, 4096 steps per tile
+    int traceLane;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -127,40 +141,81 @@ __device__ __forceinline__ double ld_cg(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ double2 lds_v2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(unsigned addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
 template <int MODE>
 struct PencilTraits {
     static constexpr int DIR = (MODE == PM_BWD || MODE == PM_GS_REV) ? -1 : 1;
     static constexpr bool GS = (MODE == PM_GS_FWD || MODE == PM_GS_REV);
+    // operand planes streamed into the raw ring
     static constexpr int NP = MODE == PM_FWD ? 5 : MODE == PM_BWD ? 5 : MODE == PM_FACTOR ? 7 : 9;
     static constexpr int STAGE_BYTES = NP * kPencilPlaneBytes;
+    // 16-byte vectors of a step record (what the chain warp reads per lane and step)
+    static constexpr int NV = MODE == PM_GS_FWD ? 5 : MODE == PM_GS_REV ? 4 : 3;
+    // lane stride: an odd number of vectors keeps the 16-byte accesses of a quarter warp on distinct banks
+    static constexpr int REC_LANE_BYTES = (NV | 1) * 16;
+    static constexpr int REC_STEP_BYTES = 32 * REC_LANE_BYTES;
 };
 
-// shared-memory layout of a CTA (dynamic): [full[NS] | empty[NS] | extReady, chainProg | neighbour ring | data ring]
-__host__ __device__ constexpr int pencilHeaderBytes(int NS) { return ((2 * NS * 8 + 16) + 127) / 128 * 128; }
+// shared-memory layout of a CTA (dynamic):
+// [full[8] | empty[8] | progress words | neighbour ring | record ring | result ring | dot ring | raw ring]
+static constexpr int kPencilD = 8;          // steps held by the record ring
+static constexpr int kPencilOutRows = 64;   // steps held by the result ring (power of two, > largest skew + 26)
+static constexpr int kPencilHeaderBytes = 256;
 __host__ __device__ inline int pencilExtBytes(int extW) { return (kPencilE * extW * 8 + 127) / 128 * 128; }
+__host__ __device__ constexpr int pencilOutBytes() { return kPencilOutRows * 32 * 8; }
 template <int MODE, int NS>
-__host__ __device__ inline int pencilSmemBytes(int extW) {
-    return pencilHeaderBytes(NS) + pencilExtBytes(extW) + NS * PencilTraits<MODE>::STAGE_BYTES;
+__host__ __device__ inline int pencilSmemBytes(int extW, bool dot) {
+    return kPencilHeaderBytes + pencilExtBytes(extW) + kPencilD * PencilTraits<MODE>::REC_STEP_BYTES +
+           pencilOutBytes() * (dot ? 2 : 1) + NS * PencilTraits<MODE>::STAGE_BYTES;
+}
+// rows of the raw ring a step can touch at once: the skew of the tile, the chunk being loaded and the row read ahead
+__host__ __device__ constexpr bool pencilFits(int skewUnits, int SKEW, int NS, bool gs) {
+    return SKEW * skewUnits + kPencilR + (gs ? 2 : 1) <= NS * kPencilR && SKEW * skewUnits + 26 <= kPencilOutRows;
 }
 
+// One CTA = four warps working on one tile at a time:
+//   warp 0  CHAIN   the recurrence itself: per step one record (3-5 LDS.128), two shuffles, the arithmetic, one STS
+//   warp 1  HELPER  bulk copies of the operand planes into the raw ring; polls the neighbour tiles' face values in L2
+//   warp 2  PREP    reads the raw ring with the lane skew, does everything that does not depend on new values
+//                   (pre-multiplications, old-value terms of Gauss-Seidel, zero records for idle lanes) and writes the
+//                   step records
+//   warp 3  WRITER  takes the results from the result ring: face lanes are published at once (a neighbour tile waits
+//                   for them), whole rows are stored coalesced once the most skewed lane has finished them; re-arms
+//                   the other buffer with the sentinel; carries the fused dot product
+// Hand-overs inside the CTA are sentinel words in shared memory (the value is the flag), mbarriers for the bulk
+// copies, and three progress words.
 template <int MODE, int SKEW, int NS>
-__global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
+__global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
     using T = PencilTraits<MODE>;
     constexpr int DIR = T::DIR;
     constexpr bool GS = T::GS;
     constexpr int NP = T::NP;
+    constexpr int NV = T::NV;
     constexpr int R = kPencilR;
-    constexpr int LA = GS ? 2 : 1;   // the leading lane reads LA rows ahead (operand prefetch; + the old value of row r+1)
+    constexpr int LA = GS ? 1 : 0;   // Gauss-Seidel reads the old value of the next row
     constexpr int kNever = 0x7fffffff;
-    static_assert((NS & (NS - 1)) == 0, "ring stages must be a power of two");
+    static_assert((NS & (NS - 1)) == 0 && NS <= 8, "ring stages: a power of two, at most 8");
     extern __shared__ __align__(128) unsigned char pencilSmem[];
+    const bool doDot = MODE == PM_BWD && a.dotOut != nullptr;
     const unsigned smBase = smem_u32(pencilSmem);
-    const unsigned barFull = smBase, barEmpty = smBase + NS * 8;
-    const unsigned wExtReady = smBase + 2 * NS * 8, wChainProg = wExtReady + 4;
-    const unsigned extRing = smBase + pencilHeaderBytes(NS);
-    const unsigned dataRing = extRing + pencilExtBytes(a.extW);
+    const unsigned barFull = smBase;
+    const unsigned wExtReady = smBase + 128, wPrepProg = smBase + 132, wWriterProg = smBase + 136;
+    const unsigned extRing = smBase + kPencilHeaderBytes;
+    const unsigned recRing = extRing + pencilExtBytes(a.extW);
+    const unsigned outRing = recRing + kPencilD * T::REC_STEP_BYTES;
+    const unsigned dotRing = outRing + pencilOutBytes();
+    const unsigned dataRing = dotRing + (doDot ? pencilOutBytes() : 0);
     const int lane = threadIdx.x & 31;
-    const bool helper = threadIdx.x >= 32;
+    const int role = threadIdx.x >> 5;
+    const double sent = sentinel();
     const double NEUTRAL = MODE == PM_FACTOR ? 1.0 : 0.0;
     const int nx = a.nx;
     const int nChunks = (nx + R - 1) / R;
@@ -170,13 +225,18 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
     if (threadIdx.x == 0) {
         for (int q = 0; q < NS; q++) {
             mbar_init(barFull + q * 8, 1);
-            mbar_init(barEmpty + q * 8, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // every record vector and every result slot starts armed; consumers re-arm what they take.  (A record is complete
+    // when the first word of each of its 16-byte vectors is no longer the sentinel: every vector is written by one
+    // store per lane, so no ordering between the stores is assumed.)
+    for (int e = threadIdx.x; e < kPencilD * 32 * NV; e += blockDim.x)
+        sts_f64(recRing + unsigned(e / NV) * T::REC_LANE_BYTES + unsigned(e % NV) * 16, sent);
+    for (int e = threadIdx.x; e < kPencilOutRows * 32; e += blockDim.x) sts_f64(outRing + unsigned(e) * 8, sent);
     __syncthreads();
 
-    unsigned gchunk0 = 0;   // chunks handed over by earlier tiles of this CTA (same count in both warps)
+    unsigned gchunk0 = 0;   // chunks handed over by earlier tiles of this CTA (same count in every warp)
     for (int ti = blockIdx.x; ti < a.nTiles; ti += gridDim.x, gchunk0 += nChunks) {
         const PencilTileDev* tp = a.tiles + a.order[DIR > 0 ? ti : a.nTiles - 1 - ti];
         const int4 t0 = *reinterpret_cast<const int4*>(&tp->base);      // base, w, wj, wk
@@ -184,7 +244,8 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
         const int tbase = t0.x, w = t0.y, wj = t0.z, wk = t0.w;
         const int skewMax = SKEW * ((wj - 1) + (wk - 1));
         const int S = nx + skewMax;
-        // neighbour tiles: chain side = where the new values come from, static side = old values (Gauss-Seidel)
+        // neighbour tiles: chain side = where the new values come from, static side = old values (Gauss-Seidel) and
+        // the tiles that wait for our results
         const int baseCJ = DIR > 0 ? tB.x : tB.z, baseCK = DIR > 0 ? tB.y : tB.w;
         const int baseSJ = DIR > 0 ? tB.z : tB.x, baseSK = DIR > 0 ? tB.w : tB.y;
         const bool hasCJ = baseCJ >= 0, hasCK = baseCK >= 0;
@@ -193,16 +254,26 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
         // ring columns of a step: [chain J (wk) | chain K (wj) | static J (wk) | static K (wj)]
         const int colCK = wk, colSJ = wk + wj, colSK = 2 * wk + wj;
         const unsigned extRowB = unsigned(a.extW) * 8;
+        // lane geometry (chain, prep and writer warps)
+        const bool laneOn = lane < w;
+        const int jj = laneOn ? lane % wj : 0, kk = laneOn ? lane / wj : 0;
+        const int jr = DIR > 0 ? jj : wj - 1 - jj, kr = DIR > 0 ? kk : wk - 1 - kk;
+        const int skew = SKEW * (jr + kr);
+        const bool extJ = (jr == 0), extK = (kr == 0);   // chain-side values come from the neighbour ring
 
-        if (helper) {
+        if (role == 1) {
+            // ------------------------------------------------------------------------------------------------
+            // helper warp: neighbour values
+            // ------------------------------------------------------------------------------------------------
             if (lane == 0) {
                 st_release_cta(wExtReady, anyExt ? 0 : kNever);
-                st_release_cta(wChainProg, 0);
+                st_release_cta(wPrepProg, 0);
+                st_release_cta(wWriterProg, 0);
             }
             // columns without a source tile hold a constant for the whole tile
             for (int e = lane; e < kPencilE * a.extW; e += 32)
                 sts_f64(extRing + unsigned(e) * 8, (e % a.extW) < colSJ ? NEUTRAL : 0.0);
-            __syncthreads();   // tile start: ring initialised, progress words reset
+            __syncthreads();   // tile start: rings initialised, progress words reset
 
             // ---- neighbour-value entries of this lane: (step offset, column) pairs over the present columns ----
             const int4 tW = *reinterpret_cast<const int4*>(tp->nbrW);
@@ -235,68 +306,42 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
                     const int nW = isJ ? (lowSide ? tW.x : tW.z) : (lowSide ? tW.y : tW.w);
                     const int nWj = isJ ? (lowSide ? tJ.x : tJ.z) : (lowSide ? tJ.y : tJ.w);
                     const int nWk = nW / nWj;
-                    int jj, kk, srcLane;
+                    int ej, ek, srcLane;
                     if (isJ) {
-                        kk = idx;
-                        jj = lowSide ? 0 : wj - 1;
-                        srcLane = (lowSide ? nWj - 1 : 0) + nWj * kk;
+                        ek = idx;
+                        ej = lowSide ? 0 : wj - 1;
+                        srcLane = (lowSide ? nWj - 1 : 0) + nWj * ek;
                     } else {
-                        jj = idx;
-                        kk = lowSide ? 0 : wk - 1;
-                        srcLane = jj + nWj * (lowSide ? nWk - 1 : 0);
+                        ej = idx;
+                        ek = lowSide ? 0 : wk - 1;
+                        srcLane = ej + nWj * (lowSide ? nWk - 1 : 0);
                     }
-                    const int jr = DIR > 0 ? jj : wj - 1 - jj, kr = DIR > 0 ? kk : wk - 1 - kk;
+                    const int ejr = DIR > 0 ? ej : wj - 1 - ej, ekr = DIR > 0 ? ek : wk - 1 - ek;
                     const int col = (grp == 0 ? 0 : grp == 1 ? colCK : grp == 2 ? colSJ : colSK) + idx;
                     eOff[k] = nBase + srcLane;
                     eStride[k] = nW;
-                    eInfo[k] = stepOff | ((SKEW * (jr + kr)) << 8) | (col << 16) | (isChain ? (1 << 24) : 0);
+                    eInfo[k] = stepOff | ((SKEW * (ejr + ekr)) << 8) | (col << 16) | (isChain ? (1 << 24) : 0);
                 }
             }
             const double* chainSrc = a.out;
             const double* staticSrc = a.plane[8];
 
-            int cL = 0;   // chunks issued
-            auto serviceLoader = [&](bool block) {
-                while (cL < nChunks) {
-                    const unsigned gc = gchunk0 + unsigned(cL);
-                    const unsigned st = gc & (NS - 1), use = gc / NS;
-                    if (use > 0) {
-                        if (block) mbar_wait(barEmpty + st * 8, (use - 1) & 1, a.err);
-                        else if (!mbar_test_wait(barEmpty + st * 8, (use - 1) & 1)) return;
-                    }
-                    if (lane == 0) {
-                        // rows of this chunk in memory order
-                        const int i0 = (DIR > 0 ? cL : nChunks - 1 - cL) * R;
-                        const int rows = min(R, nx - i0);
-                        const unsigned bytes = (unsigned(rows) * unsigned(w) * 8u + 15u) & ~15u;
-                        int np = 0;
-#pragma unroll
-                        for (int p = 0; p < NP; p++) np += a.plane[p] ? 1 : 0;
-                        mbar_arrive_expect_tx(barFull + st * 8, bytes * unsigned(np));
-                        const size_t e0 = size_t(tbase) + size_t(i0) * size_t(w);
-#pragma unroll
-                        for (int p = 0; p < NP; p++)
-                            if (a.plane[p])
-                                bulk_g2s(dataRing + st * T::STAGE_BYTES + p * kPencilPlaneBytes, a.plane[p] + e0, bytes,
-                                         barFull + st * 8);
-                    }
-                    cL++;
-                }
-            };
-
-            serviceLoader(false);
+            unsigned long long pRounds = 0, pCap = 0;
             if (nCols > 0) {
-                int chainProg = 0;
+                int prepProg = 0;
                 for (int s0 = 0; s0 < S; s0 += W) {
-                    // ring capacity: the window may only overwrite steps the chain warp has left behind
+                    // ring capacity: the window may only overwrite steps the prep warp has left behind
                     unsigned spins = 0;
-                    while (s0 + W - kPencilE > chainProg) {
-                        serviceLoader(false);
-                        chainProg = ld_acquire_cta(wChainProg);
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
+                    if (s0 + W - kPencilE > prepProg) {
+                        const long long c0 = a.prof ? clock64() : 0;
+                        while (s0 + W - kPencilE > prepProg) {
+                            prepProg = ld_acquire_cta(wPrepProg);
+                            if (++spins > kMaxSpins) {
+                                *a.err = 1;
+                                break;
+                            }
                         }
+                        if (a.prof) pCap += clock64() - c0;
                     }
                     // entries of this window: constants are deposited at once, the others are polled
                     unsigned pend = 0;
@@ -318,6 +363,8 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
                     while (true) {
                         // one polling round: every value still missing, all loads in flight together
                         double v[kPencilMaxE];
+                        pRounds++;
+                        if (a.debug & 2) __nanosleep(1000);
 #pragma unroll
                         for (int k = 0; k < kPencilMaxE; k++) {
                             if (pend & (1u << k)) {
@@ -347,193 +394,388 @@ __global__ void __launch_bounds__(64, 2) k_pencil(PencilArgs a) {
                             if (lane == 0) st_release_cta(wExtReady, s0 + published);
                         }
                         if (firstMissing == nE) break;
-                        serviceLoader(false);
                         if (++spins > kMaxSpins) {
                             *a.err = 1;
                             break;
                         }
                     }
-                    serviceLoader(false);
                 }
             }
-            serviceLoader(true);
+            if (a.prof && lane == 0) {
+                unsigned long long* q = a.prof + size_t(ti) * 16;
+                q[8] = pRounds;
+                q[9] = pCap;
+            }
             __syncthreads();   // tile end
-        } else {
+        } else if (role == 2) {
             // ------------------------------------------------------------------------------------------------
-            // chain warp
+            // prep warp: raw ring (skewed rows) + neighbour ring -> step records
             // ------------------------------------------------------------------------------------------------
-            const bool laneOn = lane < w;
-            const int jj = laneOn ? lane % wj : 0, kk = laneOn ? lane / wj : 0;
-            const int jr = DIR > 0 ? jj : wj - 1 - jj, kr = DIR > 0 ? kk : wk - 1 - kk;
-            const int skew = SKEW * (jr + kr);
-            const bool extJ = (jr == 0), extK = (kr == 0);            // chain-side values come from the ring
-            const int srcJ = (extJ || !laneOn) ? lane : lane - DIR;   // shuffle sources
-            const int srcK = (extK || !laneOn) ? lane : lane - DIR * wj;
-            // Gauss-Seidel: the old values of the other side live in the data ring (same tile) or the neighbour ring
+            // Gauss-Seidel: the old values of the other side live in the raw ring (same tile) or the neighbour ring
             const bool sExtJ = (jr == wj - 1), sExtK = (kr == wk - 1);
             const int oJoff = sExtJ ? 0 : DIR * 8, oKoff = sExtK ? 0 : DIR * wj * 8;
             const unsigned wB = unsigned(w) * 8;
             const unsigned ringLane = dataRing + unsigned(lane) * 8;
             const unsigned eJaddr = extRing + unsigned(kk) * 8, eKaddr = extRing + unsigned(colCK + jj) * 8;
             const unsigned sJaddr = extRing + unsigned(colSJ + kk) * 8, sKaddr = extRing + unsigned(colSK + jj) * 8;
-            const bool doClear = a.clear != nullptr;
-            const bool doDot = MODE == PM_BWD && a.plane[4] != nullptr;
+            const unsigned recLane = recRing + unsigned(lane) * T::REC_LANE_BYTES;
+            const unsigned dotLane = dotRing + unsigned(lane) * 8;
             const bool asym = MODE == PM_FACTOR && a.plane[4] != nullptr;
-            const double sent = sentinel();
+            __syncthreads();   // tile start
 
-            __syncthreads();   // tile start (helper has reset the progress words and the ring)
-
-            // ring address of the operands of processing row r (any r: the result of an inactive step is discarded)
+            // raw-ring address of the operands of processing row r (any r: an idle lane's record is zeroed anyway)
             auto rowOff = [&](int r) -> unsigned {
                 const int i = DIR > 0 ? r : nx - 1 - r;
                 const unsigned st = (gchunk0 + unsigned((r + pad) >> 3)) & (NS - 1);
                 return ringLane + st * T::STAGE_BYTES + unsigned(i & (R - 1)) * wB;
             };
-            struct Ops {
-                double c[NP];
-                double eJ, eK, esJ, esK, oI, oJ, oK;
-            };
-            auto loadOps = [&](Ops& o, int s, unsigned off, unsigned offNext) {
+            // bulk copies of one chunk of every operand plane into its ring stage (one lane; the stage is free: either it
+            // has never been used by this tile or this warp has just finished reading its previous occupant)
+            auto issueChunk = [&](int cL) {
+                const unsigned gc = gchunk0 + unsigned(cL);
+                const unsigned st = gc & (NS - 1);
+                const int i0 = (DIR > 0 ? cL : nChunks - 1 - cL) * R;   // rows of the chunk in memory order
+                const int rows = min(R, nx - i0);
+                const unsigned bytes = (unsigned(rows) * unsigned(w) * 8u + 15u) & ~15u;
+                int np = 0;
 #pragma unroll
-                for (int p = 0; p < NP; p++) o.c[p] = lds_f64(off + p * kPencilPlaneBytes);
-                const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
-                o.eJ = lds_f64(eJaddr + er);
-                o.eK = lds_f64(eKaddr + er);
-                if (GS) {
-                    o.esJ = lds_f64(sJaddr + er);
-                    o.esK = lds_f64(sKaddr + er);
-                    o.oJ = lds_f64(off + 8 * kPencilPlaneBytes + oJoff);
-                    o.oK = lds_f64(off + 8 * kPencilPlaneBytes + oKoff);
-                    o.oI = lds_f64(offNext + 8 * kPencilPlaneBytes);
-                }
+                for (int p = 0; p < NP; p++) np += a.plane[p] ? 1 : 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads of the stage precede the copy
+                mbar_arrive_expect_tx(barFull + st * 8, bytes * unsigned(np));
+                const size_t e0 = size_t(tbase) + size_t(i0) * size_t(w);
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    if (a.plane[p])
+                        bulk_g2s(dataRing + st * T::STAGE_BYTES + p * kPencilPlaneBytes, a.plane[p] + e0, bytes,
+                                 barFull + st * 8);
             };
-
-            // waits, as step numbers at which they fall due
+            if (lane == 0)
+                for (int cL = 0; cL < min(NS, nChunks); cL++) issueChunk(cL);
             int waitRow = 0;                          // first processing row of the next chunk to wait for
-            int waitStep = -1;                        // ... needed by the loads issued at this step
+            int waitStep = 0;                         // step at which that wait falls due
             int relChunk = 0;
-            int relStep = min(nx - 1, R - pad - 1) + skewMax;   // last step that reads the chunk
+            int relStep = min(nx - 1, R - pad - 1) + skewMax;   // last step that reads the oldest chunk
             int extAvail = anyExt ? 0 : kNever;
-            auto waitData = [&](int s) {              // chunks holding processing rows <= s + LA
-                while (waitRow < nx && waitRow <= s + LA) {
-                    const unsigned gc = gchunk0 + unsigned((waitRow + pad) >> 3);
-                    mbar_wait(barFull + (gc & (NS - 1)) * 8, (gc / NS) & 1, a.err);
-                    waitRow = (((waitRow + pad) >> 3) + 1) * R - pad;
-                }
-                waitStep = waitRow < nx ? waitRow - LA : kNever;
-            };
-            auto waitExt = [&](int step) {            // neighbour values of `step` are in the ring
-                unsigned spins = 0;
-                while (extAvail <= step && step < S) {
-                    extAvail = ld_acquire_cta(wExtReady);
-                    if (++spins > kMaxSpins) {
-                        *a.err = 1;
-                        break;
-                    }
-                }
-            };
-
-            double y1 = NEUTRAL, sJ = NEUTRAL, sK = NEUTRAL;
-            int elem = tbase + lane + (DIR > 0 ? -skew : nx - 1 + skew) * w;   // position of the row of step 0
-            int r = -skew;
-
-            // one step: operands in `cur`, prefetch of the next step's into `nxt`
-            auto step = [&](int s, Ops& cur, Ops& nxt, unsigned& offNext) {
+            unsigned long long pData = 0, pExt = 0, pSlot = 0;
+            unsigned recOff = 0;
+            for (int s = 0; s < S; s++) {
+                const int r = s - skew;
                 const bool act = laneOn && unsigned(r) < unsigned(nx);
-                if (s >= waitStep) waitData(s);
-                if (s + 1 >= extAvail) waitExt(s + 1);
-                const unsigned off = offNext;
-                offNext = rowOff(r + 2);
-                loadOps(nxt, s + 1, off, offNext);
-
-                if (SKEW == 1) {
-                    sJ = __shfl_sync(0xffffffffu, y1, srcJ);
-                    sK = __shfl_sync(0xffffffffu, y1, srcK);
+                if (s >= waitStep) {                  // chunks holding processing rows <= s + LA
+                    const long long c0 = a.prof ? clock64() : 0;
+                    while (waitRow < nx && waitRow <= s + LA) {
+                        const unsigned gc = gchunk0 + unsigned((waitRow + pad) >> 3);
+                        mbar_wait(barFull + (gc & (NS - 1)) * 8, (gc / NS) & 1, a.err);
+                        waitRow = (((waitRow + pad) >> 3) + 1) * R - pad;
+                    }
+                    waitStep = waitRow < nx ? waitRow - LA : kNever;
+                    if (a.prof) pData += clock64() - c0;
                 }
-                const double vJ = extJ ? cur.eJ : sJ, vK = extK ? cur.eK : sK;
-                const double* c = cur.c;
-                double acc, y;
+                if (s >= extAvail) {                  // neighbour values of this step are in the ring
+                    const long long c0 = a.prof ? clock64() : 0;
+                    unsigned spins = 0;
+                    while (extAvail <= s) {
+                        extAvail = ld_acquire_cta(wExtReady);
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
+                    }
+                    if (a.prof) pExt += clock64() - c0;
+                }
+                const unsigned off = rowOff(r);
+                double c[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++) c[p] = lds_f64(off + p * kPencilPlaneBytes);
+                const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
+                double eJ = lds_f64(eJaddr + er), eK = lds_f64(eKaddr + er);
+                double oI = 0.0, oJ = 0.0, oK = 0.0;
+                if (GS) {
+                    const double esJ = lds_f64(sJaddr + er), esK = lds_f64(sKaddr + er);
+                    oJ = lds_f64(off + 8 * kPencilPlaneBytes + oJoff);
+                    oK = lds_f64(off + 8 * kPencilPlaneBytes + oKoff);
+                    oI = lds_f64(rowOff(r + 1) + 8 * kPencilPlaneBytes);
+                    if (sExtJ) oJ = esJ;
+                    if (sExtK) oK = esK;
+                    if (!(unsigned(r + 1) < unsigned(nx))) oI = 0.0;   // no such row: exact +0
+                }
+                // the record: everything of the step that does not depend on new values
+                double rec[2 * NV];
                 if (MODE == PM_FWD) {
-                    // planes: in, rD, t_K, t_J, t_I  (t = rD*lower, +0 where there is no face)
-                    acc = c[1] * c[0];
-                    acc -= c[2] * vK;
-                    acc -= c[3] * vJ;
-                    acc -= c[4] * y1;
-                    y = acc;
+                    // planes: in, rD, t_K, t_J, t_I (t = rD*lower, +0 where there is no face)
+                    rec[0] = c[1] * c[0];
+                    rec[1] = c[2];
+                    rec[2] = c[3];
+                    rec[3] = c[4];
                 } else if (MODE == PM_BWD) {
                     // planes: in, t_K, t_J, t_I (t = rD*upper), dotWith
-                    acc = c[0];
-                    acc -= c[1] * vK;
-                    acc -= c[2] * vJ;
-                    acc -= c[3] * y1;
-                    y = acc;
+                    rec[0] = c[0];
+                    rec[1] = c[1];
+                    rec[2] = c[2];
+                    rec[3] = c[3];
                 } else if (MODE == PM_FACTOR) {
-                    // planes: diag, l_K, l_J, l_I, u_K, u_J, u_I (coefficients of the lower-side faces; symmetric
-                    // matrices pass no u planes)
-                    acc = c[0];
-                    acc -= ((asym ? c[4] : c[1]) * c[1]) / vK;
-                    acc -= ((asym ? c[5] : c[2]) * c[2]) / vJ;
-                    acc -= ((asym ? c[6] : c[3]) * c[3]) / y1;
-                    y = acc;
+                    // planes: diag, l_K, l_J, l_I, u_K, u_J, u_I of the lower-side faces (symmetric: no u planes)
+                    rec[0] = c[0];
+                    rec[1] = (asym ? c[4] : c[1]) * c[1];
+                    rec[2] = (asym ? c[5] : c[2]) * c[2];
+                    rec[3] = (asym ? c[6] : c[3]) * c[3];
+                } else if (MODE == PM_GS_FWD) {
+                    // planes: b, diag, l_K, l_J, l_I, u_I, u_J, u_K, old
+                    rec[0] = c[0];
+                    rec[1] = c[2];
+                    rec[2] = c[3];
+                    rec[3] = c[4];
+                    rec[4] = c[5] * oI;
+                    rec[5] = c[6] * oJ;
+                    rec[6] = c[7] * oK;
+                    rec[7] = c[1];
                 } else {
-                    // Gauss-Seidel planes: b, diag, l_K, l_J, l_I, u_I, u_J, u_K, old
-                    const double oI = (unsigned(r + 1) < unsigned(nx)) ? cur.oI : 0.0;   // no such row: exact +0
-                    const double oJ = sExtJ ? cur.esJ : cur.oJ, oK = sExtK ? cur.esK : cur.oK;
-                    acc = c[0];
-                    if (MODE == PM_GS_FWD) {
-                        acc -= c[2] * vK;
-                        acc -= c[3] * vJ;
-                        acc -= c[4] * y1;
-                        acc -= c[5] * oI;
-                        acc -= c[6] * oJ;
-                        acc -= c[7] * oK;
-                    } else {
-                        // reverse half of symGaussSeidel: lower terms with the forward values, then the new upper ones
-                        acc -= c[2] * oK;
-                        acc -= c[3] * oJ;
-                        acc -= c[4] * oI;
-                        acc -= c[5] * y1;
-                        acc -= c[6] * vJ;
-                        acc -= c[7] * vK;
+                    // reverse half of symGaussSeidel: the lower terms use the forward values, summed here in order
+                    double acc = c[0];
+                    acc -= c[2] * oK;
+                    acc -= c[3] * oJ;
+                    acc -= c[4] * oI;
+                    rec[0] = acc;
+                    rec[1] = c[5];
+                    rec[2] = c[6];
+                    rec[3] = c[7];
+                    rec[4] = c[1];
+                    rec[5] = 0.0;
+                }
+                if (!act) {
+                    // idle lane: a record whose result is NEUTRAL whatever the neighbours hold
+#pragma unroll
+                    for (int q = 0; q < 2 * NV - 2; q++) rec[q] = 0.0;
+                    if (MODE == PM_FACTOR) rec[0] = 1.0;
+                    if (MODE == PM_GS_FWD) rec[7] = 1.0;
+                    if (MODE == PM_GS_REV) rec[4] = 1.0;
+                    eJ = NEUTRAL;
+                    eK = NEUTRAL;
+                }
+                rec[2 * NV - 2] = eK;
+                rec[2 * NV - 1] = eJ;
+                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(0) * a.nTiles + ti) * 4096 + s] = rec[0];
+                // wait until the chain warp has taken the previous occupant of the slot (every vector re-armed), then write
+                const unsigned ra = recLane + recOff;
+                {
+                    unsigned spins = 0;
+                    bool waited = false;
+                    long long c0 = 0;
+                    auto busy = [&]() {
+                        bool b = false;
+#pragma unroll
+                        for (int q = 0; q < NV; q++) b = b || !is_sentinel(lds_f64(ra + q * 16));
+                        return b;
+                    };
+                    while (__any_sync(0xffffffffu, busy())) {
+                        if (!waited && a.prof) c0 = clock64();
+                        waited = true;
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
                     }
-                    y = acc / c[1];
+                    if (waited && a.prof) pSlot += clock64() - c0;
                 }
-                if (SKEW == 2) {
-                    sJ = __shfl_sync(0xffffffffu, y1, srcJ);
-                    sK = __shfl_sync(0xffffffffu, y1, srcK);
-                }
-                y1 = act ? y : NEUTRAL;
-                if (act) {
-                    st_l2(a.out + elem, y);
-                    if (MODE == PM_FACTOR) a.out2[elem] = 1.0 / y;
-                    if (doClear) a.clear[elem] = sent;
-                    if (doDot) dsum[0] += y * c[4];
-                }
-                elem += DIR * w;
-                r++;
-                // hand the chunk back to the helper once its last row has been read by the most skewed lane
+#pragma unroll
+                for (int q = NV - 1; q >= 0; q--) sts_v2(ra + q * 16, rec[2 * q], rec[2 * q + 1]);
+                if (doDot) sts_f64(dotLane + unsigned(s & (kPencilOutRows - 1)) * 256u, act ? c[4] : 0.0);
+                recOff = recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES;
+                // once the most skewed lane has read the last row of the oldest chunk, its stage takes the next chunk
                 if (s == relStep) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(barEmpty + ((gchunk0 + unsigned(relChunk)) & (NS - 1)) * 8);
+                    if (lane == 0 && relChunk + NS < nChunks) issueChunk(relChunk + NS);
                     relChunk++;
                     const int nextFirst = relChunk * R - pad;
                     relStep = nextFirst < nx ? min(nx - 1, nextFirst + R - 1) + skewMax : kNever;
                 }
                 // tell the helper how far the neighbour ring has been consumed
-                if ((s & 7) == 7 && anyExt && lane == 0) st_release_cta(wChainProg, s);
+                if ((s & 7) == 7 && anyExt && lane == 0) st_release_cta(wPrepProg, s);
+            }
+            if (a.prof && lane == 0) {
+                unsigned long long* q = a.prof + size_t(ti) * 16;
+                q[4] = pData;
+                q[5] = pExt;
+                q[6] = pSlot;
+            }
+            __syncthreads();   // tile end
+        } else if (role == 0) {
+            // ------------------------------------------------------------------------------------------------
+            // chain warp
+            // ------------------------------------------------------------------------------------------------
+            const int srcJ = (extJ || !laneOn) ? lane : lane - DIR;   // shuffle sources
+            const int srcK = (extK || !laneOn) ? lane : lane - DIR * wj;
+            const unsigned recLane = recRing + unsigned(lane) * T::REC_LANE_BYTES;
+            const unsigned outLane = outRing + unsigned(lane) * 8;
+            __syncthreads();   // tile start
+            const unsigned long long pStart = a.prof ? globaltimer_ns() : 0;
+            unsigned long long pRec = 0, pOut = 0;
+            double y1 = NEUTRAL, sJ = NEUTRAL, sK = NEUTRAL;
+            unsigned recOff = 0, outOff = 0;
+            int writerProg = 0;
+            // records are read one step ahead (two register sets): the loads of step s+1 are in flight during step s
+            auto loadRec = [&](double2 (&v)[NV], unsigned ra) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) v[q] = lds_v2(ra + q * 16);
             };
-
-            Ops A, B;
-            waitData(-1);
-            if (anyExt) waitExt(0);
-            unsigned offNext = rowOff(1 - skew);
-            loadOps(A, 0, rowOff(-skew), offNext);
+            auto missing = [&](const double2 (&v)[NV]) {
+                bool m = false;
+#pragma unroll
+                for (int q = 0; q < NV; q++) m = m || is_sentinel(v[q].x);
+                return m;
+            };
+            auto takeRec = [&](double2 (&v)[NV], unsigned ra) {   // make sure the record is there, then free its slot
+                if (__any_sync(0xffffffffu, missing(v))) {
+                    const long long c0 = a.prof ? clock64() : 0;
+                    unsigned spins = 0;
+                    do {
+                        loadRec(v, ra);
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
+                    } while (__any_sync(0xffffffffu, missing(v)));
+                    if (a.prof) pRec += clock64() - c0;
+                }
+#pragma unroll
+                for (int q = 0; q < NV; q++) sts_f64(ra + q * 16, sent);
+            };
+            auto step = [&](int s, const double2 (&v)[NV], double2 (&vn)[NV]) {
+                const unsigned raNext = recLane + (recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES);
+                if (s + 1 < S) loadRec(vn, raNext);
+                if ((a.debug & 1) && s + 1 < S) takeRec(vn, raNext);
+                if (SKEW == 1) {
+                    sJ = __shfl_sync(0xffffffffu, y1, srcJ);
+                    sK = __shfl_sync(0xffffffffu, y1, srcK);
+                }
+                const double vK = extK ? v[NV - 1].x : sK, vJ = extJ ? v[NV - 1].y : sJ;
+                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(1) * a.nTiles + ti) * 4096 + s] = v[0].x;
+                double acc, y;
+                if (MODE == PM_FWD || MODE == PM_BWD) {
+                    // record: {rD*in | in, t_K} {t_J, t_I}
+                    acc = v[0].x;
+                    acc -= v[0].y * vK;
+                    acc -= v[1].x * vJ;
+                    acc -= v[1].y * y1;
+                    y = acc;
+                } else if (MODE == PM_FACTOR) {
+                    // record: {diag, u_K*l_K} {u_J*l_J, u_I*l_I}
+                    acc = v[0].x;
+                    acc -= v[0].y / vK;
+                    acc -= v[1].x / vJ;
+                    acc -= v[1].y / y1;
+                    y = acc;
+                } else if (MODE == PM_GS_FWD) {
+                    // record: {b, l_K} {l_J, l_I} {u_I*old_I, u_J*old_J} {u_K*old_K, diag}
+                    acc = v[0].x;
+                    acc -= v[0].y * vK;
+                    acc -= v[1].x * vJ;
+                    acc -= v[1].y * y1;
+                    acc -= v[2].x;
+                    acc -= v[2].y;
+                    acc -= v[3].x;
+                    y = acc / v[3].y;
+                } else {
+                    // record: {b - lower terms, u_I} {u_J, u_K} {diag, -}
+                    acc = v[0].x;
+                    acc -= v[0].y * y1;
+                    acc -= v[1].x * vJ;
+                    acc -= v[1].y * vK;
+                    y = acc / v[2].x;
+                }
+                if (SKEW == 2) {
+                    sJ = __shfl_sync(0xffffffffu, y1, srcJ);
+                    sK = __shfl_sync(0xffffffffu, y1, srcK);
+                }
+                y1 = y;
+                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(2) * a.nTiles + ti) * 4096 + s] = y;
+                sts_f64(outLane + outOff, y);
+                recOff = recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES;
+                outOff = (outOff + 256u) & (kPencilOutRows * 256u - 1u);
+                if (!(a.debug & 1) && s + 1 < S) takeRec(vn, raNext);
+                // result ring capacity: the slots of the next eight steps must have been re-armed by the writer
+                if ((s & 7) == 7 && writerProg < s + 9 + skewMax - kPencilOutRows) {
+                    const long long c0 = a.prof ? clock64() : 0;
+                    unsigned spins = 0;
+                    while (writerProg < s + 9 + skewMax - kPencilOutRows) {
+                        writerProg = ld_acquire_cta(wWriterProg);
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
+                    }
+                    if (a.prof) pOut += clock64() - c0;
+                }
+            };
+            double2 vA[NV], vB[NV];
+            loadRec(vA, recLane);
+            takeRec(vA, recLane);
             int s = 0;
             for (; s + 1 < S; s += 2) {
-                step(s, A, B, offNext);
-                step(s + 1, B, A, offNext);
+                step(s, vA, vB);
+                step(s + 1, vB, vA);
             }
-            if (s < S) step(s, A, B, offNext);
+            if (s < S) step(s, vA, vB);
+            if (a.prof && lane == 0) {
+                unsigned long long* q = a.prof + size_t(ti) * 16;
+                q[0] = pStart;
+                q[1] = globaltimer_ns();
+                q[2] = pRec;
+                q[3] = pOut;
+            }
+            __syncthreads();   // tile end
+        } else {
+            // ------------------------------------------------------------------------------------------------
+            // writer warp
+            // ------------------------------------------------------------------------------------------------
+            // the lanes on the high faces of the tile, whose values a neighbour tile is waiting for, publish at once
+            const bool faceLane = laneOn && ((jr == wj - 1 && baseSJ >= 0) || (kr == wk - 1 && baseSK >= 0));
+            const int delay = skewMax - skew;   // steps between this lane's result of a row and the row being complete
+            const unsigned outLane = outRing + unsigned(lane) * 8;
+            const unsigned dotLane = dotRing + unsigned(lane) * 8;
+            const bool doClear = a.clear != nullptr;
+            int elem = tbase + lane + (DIR > 0 ? -skew : nx - 1 + skew) * w;            // position of this lane's row of step 0
+            int elemRow = tbase + lane + (DIR > 0 ? -skewMax : nx - 1 + skewMax) * w;   // ... of the row completed at step 0
+            __syncthreads();   // tile start
+            unsigned long long pWait = 0;
+            for (int s = 0; s < S; s++) {
+                const unsigned slotS = outLane + unsigned(s & (kPencilOutRows - 1)) * 256u;
+                double v = lds_f64(slotS);
+                if (__any_sync(0xffffffffu, is_sentinel(v))) {
+                    const long long c0 = a.prof ? clock64() : 0;
+                    unsigned spins = 0;
+                    do {
+                        v = lds_f64(slotS);
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
+                    } while (__any_sync(0xffffffffu, is_sentinel(v)));
+                    if (a.prof) pWait += clock64() - c0;
+                }
+                const int r = s - skew;
+                const bool act = laneOn && unsigned(r) < unsigned(nx);
+                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(3) * a.nTiles + ti) * 4096 + s] = v;
+                if (act) {
+                    if (faceLane) st_l2(a.out + elem, v);
+                } else {
+                    sts_f64(slotS, sent);   // an idle lane's slot is free again at once
+                }
+                const int q = s - skewMax;   // processing row every lane has finished now
+                if (laneOn && q >= 0) {
+                    const unsigned slotQ = outLane + unsigned((s - delay) & (kPencilOutRows - 1)) * 256u;
+                    const double vq = lds_f64(slotQ);   // this lane's own result `delay` steps ago (== v when delay is 0)
+                    st_l2(a.out + elemRow, vq);
+                    if (MODE == PM_FACTOR) a.out2[elemRow] = 1.0 / vq;
+                    if (doClear) a.clear[elemRow] = sent;
+                    if (doDot) dsum[0] += vq * lds_f64(dotLane + unsigned((s - delay) & (kPencilOutRows - 1)) * 256u);
+                    sts_f64(slotQ, sent);
+                }
+                elem += DIR * w;
+                elemRow += DIR * w;
+                if ((s & 7) == 7 && lane == 0) st_release_cta(wWriterProg, s + 1);
+            }
+            if (a.prof && lane == 0) a.prof[size_t(ti) * 16 + 7] = pWait;
             __syncthreads();   // tile end
         }
     }

@@ -96,8 +96,8 @@ static void launchSweep(K kernel, SweepArgs& a) {
     c.launches++;
 }
 
-// Pencil sweeps (pencil.cuh): one chain/helper warp pair per tile, persistent over the tile list.  Cooperative launch:
-// a tile polls values of tiles earlier in the launch order, which must be resident or finished.
+// Pencil sweeps (pencil.cuh): one four-warp CTA per tile, persistent over the tile list.  Cooperative launch: a tile
+// polls values of tiles earlier in the launch order, which must be resident or finished.
 template <int MODE, int SKEW, int NS>
 static void launchPencilCfg(PencilArgs& a, int cols) {
     if (a.nTiles == 0) return;
@@ -105,14 +105,20 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     constexpr bool GS = PencilTraits<MODE>::GS;
     auto kernel = k_pencil<MODE, SKEW, NS>;
     const int sideCols = std::max(1, cols) * (GS ? 2 : 1);
-    a.window = std::max(1, std::min(16, (32 * kPencilMaxE) / sideCols));
-    const size_t smem = size_t(pencilSmemBytes<MODE, NS>(a.extW));
-    static std::map<size_t, int> occCache;   // per instantiation (static in a template function), keyed by smem size
+    static const int maxWindow = getenv("B200LS_PENCIL_WINDOW") ? atoi(getenv("B200LS_PENCIL_WINDOW")) : 8;
+    a.window = std::max(1, std::min(maxWindow, (32 * kPencilMaxE) / sideCols));
+    const size_t smem = size_t(pencilSmemBytes<MODE, NS>(a.extW, a.dotOut != nullptr));
+    // per instantiation: the dynamic shared-memory limit only ever grows; occupancy per size
+    static size_t smemLimit = 0;
+    static std::map<size_t, int> occCache;
+    if (smem > smemLimit) {
+        B2_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        smemLimit = smem;
+    }
     int occ;
     auto it = occCache.find(smem);
     if (it == occCache.end()) {
-        B2_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 64, smem));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 128, smem));
         occCache[smem] = occ;
     } else {
         occ = it->second;
@@ -124,22 +130,83 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     a.err = c.errFlag.p;
     a.partials = c.partials.p;
     a.ticket = c.ticket.p;
+    static const int dbg = getenv("B200LS_PENCIL_DEBUG") ? atoi(getenv("B200LS_PENCIL_DEBUG")) : 0;
+    a.debug = dbg;
+    // debugging aid: B200LS_PENCIL_PROF=<file> dumps 16 counters per tile of every pencil launch (pencil.cuh PencilArgs::prof)
+    static const char* profFile = getenv("B200LS_PENCIL_PROF");
+    static DevBuf<unsigned long long> profBuf;
+    if (profFile) {
+        profBuf.alloc(size_t(a.nTiles) * 16);
+        B2_CUDA(cudaMemsetAsync(profBuf.p, 0, size_t(a.nTiles) * 128, c.stream));
+        a.prof = profBuf.p;
+    }
+    // debugging aid: B200LS_PENCIL_TRACE=<file> records, per tile and step, the value one lane handles in each warp
+    static const char* traceFile = getenv("B200LS_PENCIL_TRACE");
+    static DevBuf<double> traceBuf;
+    if (traceFile) {
+        traceBuf.alloc(size_t(4) * a.nTiles * 4096);
+        B2_CUDA(cudaMemsetAsync(traceBuf.p, 0, traceBuf.n * 8, c.stream));
+        a.trace = traceBuf.p;
+        a.traceLane = getenv("B200LS_PENCIL_TRACE_LANE") ? atoi(getenv("B200LS_PENCIL_TRACE_LANE")) : 0;
+    }
     void* args[] = {&a};
-    B2_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(64), args, smem, c.stream));
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(128), args, smem, c.stream);
+    if (le != cudaSuccess)
+        throw CudaError(std::string("pencil sweep launch failed: ") + cudaGetErrorString(le) + " (mode " +
+                        std::to_string(MODE) + ", " + std::to_string(blocks) + " CTAs, " + std::to_string(smem) +
+                        " B shared memory, occupancy " + std::to_string(occ) + "/SM)");
     c.launches++;
+    if (traceFile) {
+        std::vector<double> h(traceBuf.n);
+        B2_CUDA(cudaMemcpyAsync(h.data(), traceBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        if (FILE* f = fopen(traceFile, "ab")) {
+            const int hdr[4] = {MODE, a.nTiles, a.nx, 0};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+    }
+    if (profFile) {
+        std::vector<unsigned long long> h(size_t(a.nTiles) * 16);
+        B2_CUDA(cudaMemcpyAsync(h.data(), profBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        if (FILE* f = fopen(profFile, "a")) {
+            fprintf(f, "# mode %d skew %d stages %d tiles %d ctas %d window %d\n", MODE, SKEW, NS, a.nTiles, blocks, a.window);
+            for (int t = 0; t < a.nTiles; t++) {
+                for (int q = 0; q < 16; q++) fprintf(f, "%llu ", h[size_t(t) * 16 + q]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
 }
 
-// ring depth / skew per mode; B200LS_PENCIL_CFG=<skew><stages> (e.g. 18, 28, 14) overrides the substitution sweeps
-template <int MODE>
-static void launchPencil(PencilArgs& a, int cols) {
-    static const int cfg = getenv("B200LS_PENCIL_CFG") ? atoi(getenv("B200LS_PENCIL_CFG")) : 0;
-    if (MODE == PM_FWD || MODE == PM_BWD) {
-        if (cfg == 14) return launchPencilCfg<MODE, 1, 4>(a, cols);
-        if (cfg == 18) return launchPencilCfg<MODE, 1, 8>(a, cols);
-        return launchPencilCfg<MODE, 2, 8>(a, cols);
+// (skew, ring stages) of a pencil launch: the first configuration of the mode's list whose raw ring holds the rows a
+// step can touch (pencilFits); B200LS_PENCIL_CFG=<skew><stages> (14, 18, 24, 28) moves one to the front.
+static bool pencilConfig(int skewUnits, bool gs, int& skew, int& stages) {
+    static const int forced = getenv("B200LS_PENCIL_CFG") ? atoi(getenv("B200LS_PENCIL_CFG")) : 0;
+    const int order[5] = {forced, 14, 18, 24, 28};
+    for (int q = forced ? 0 : 1; q < 5; q++) {
+        const int sk = order[q] / 10, ns = order[q] % 10;
+        if ((sk == 1 || sk == 2) && (ns == 4 || ns == 8) && pencilFits(skewUnits, sk, ns, gs)) {
+            skew = sk;
+            stages = ns;
+            return true;
+        }
     }
-    if (cfg / 10 == 2) return launchPencilCfg<MODE, 2, 4>(a, cols);
-    return launchPencilCfg<MODE, 1, 4>(a, cols);
+    return false;
+}
+
+template <int MODE>
+static void launchPencil(PencilArgs& a, const DevLevel& D) {
+    int skew = 0, stages = 0;
+    if (!pencilConfig(D.pSkewUnits, PencilTraits<MODE>::GS, skew, stages))
+        throw CudaError("pencil sweep: no ring configuration fits this tile shape");
+    if (skew == 1 && stages == 4) return launchPencilCfg<MODE, 1, 4>(a, D.pCols);
+    if (skew == 1) return launchPencilCfg<MODE, 1, 8>(a, D.pCols);
+    if (stages == 4) return launchPencilCfg<MODE, 2, 4>(a, D.pCols);
+    return launchPencilCfg<MODE, 2, 8>(a, D.pCols);
 }
 
 void checkSweepError() {
@@ -217,6 +284,7 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         D.pWJ = P.WJ;
         D.pWK = P.WK;
         D.pCols = (P.nJ > 1 ? P.WK : 0) + (P.nK > 1 ? P.WJ : 0);
+        D.pSkewUnits = (P.WJ - 1) + (P.WK - 1);
         std::vector<PencilTileDev> tiles(P.tiles.size());
         for (size_t t = 0; t < P.tiles.size(); t++) {
             const PencilTile& h = P.tiles[t];
@@ -666,7 +734,9 @@ static void ensureLevelScratch(b200ls_matrix_s* m, int level) {
 static bool usePencil(const DevLevel& D) {
     if (!D.hasPencil) return false;
     const char* e = getenv("B200LS_PENCIL_SWEEPS");   // "0": run the wavefront kernels on the tile-major layout
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return false;
+    int skew, stages;
+    return pencilConfig(D.pSkewUnits, true, skew, stages);
 }
 // planes are [slot][position] with an even stride (16-byte aligned rows for the bulk copies)
 static size_t planeStride(const DevLevel& D) { return (size_t(D.nCells) + 1) & ~size_t(1); }
@@ -727,7 +797,7 @@ void ensureFactor(b200ls_matrix_s* m, int level, int precond) {
         }
         a.out = M.dWork.p;
         a.out2 = M.rD.p;
-        launchPencil<PM_FACTOR>(a, D.pCols);
+        launchPencil<PM_FACTOR>(a, D);
         M.ptL.alloc(3 * np);
         M.ptU.alloc(3 * np);
         LAUNCH(k_pencil_pack, pencilGrid(D), 256, M.ptL.p, M.ptU.p, M.pcL.p, M.pcU.p, M.rD.p, D.pTiles.p, D.pNx, D.pNy,
@@ -782,7 +852,7 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
         for (int q = 0; q < 3; q++) f.plane[2 + q] = M.ptL.p + q * np;
         f.out = M.tmpA.p;
         f.clear = wA;
-        launchPencil<PM_FWD>(f, D.pCols);
+        launchPencil<PM_FWD>(f, D);
         PencilArgs b = pencilArgs(D, false);
         b.plane[0] = M.tmpA.p;
         for (int q = 0; q < 3; q++) b.plane[1 + q] = M.ptU.p + q * np;
@@ -792,7 +862,7 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
             b.plane[4] = rA;
             b.dotOut = dotOut;
         }
-        launchPencil<PM_BWD>(b, D.pCols);
+        launchPencil<PM_BWD>(b, D);
         return;
     }
     SweepArgs f{};
@@ -933,7 +1003,7 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
                 a.plane[8] = psi;
                 a.out = spare;
                 a.clear = (rearm && sweep + 1 < nSweeps) ? psi : nullptr;
-                launchPencil<PM_GS_FWD>(a, D.pCols);
+                launchPencil<PM_GS_FWD>(a, D);
                 if (smoother == B200LS_GAUSS_SEIDEL) {
                     std::swap(psi, spare);
                     continue;
@@ -944,7 +1014,7 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
                 r.plane[8] = spare;
                 r.out = psi;
                 r.clear = nullptr;
-                launchPencil<PM_GS_REV>(r, D.pCols);
+                launchPencil<PM_GS_REV>(r, D);
                 continue;
             }
             SweepArgs a{};
