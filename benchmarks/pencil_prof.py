@@ -40,6 +40,8 @@ for blk in blocks[-2:]:
              "prep: wait record slot", "writer: wait results", "helper: polling rounds", "helper: wait ring capacity"]
     for k, nm in enumerate(names):
         print(f"  {nm:28s} mean {a[:, 2 + k].mean():10.0f}  max {a[:, 2 + k].max():10d}")
+    mhz = a[:, 10] / np.maximum(1e-9, (a[:, 1] - a[:, 0]) / 1e3)
+    print(f"  chain warp: SM clock seen = cycles / globaltimer: median {np.median(mhz):.0f} MHz (min {mhz.min():.0f}, max {mhz.max():.0f})")
     for i in [0, 1, 2, 3, 16, 100, 255, 300, len(a) - 1]:
         if i < len(a):
             print(f"  tile {i:4d}: start {start[i]:8.1f} end {end[i]:8.1f} us | " + " ".join(f"{v:8d}" for v in a[i, 2:10]))

@@ -65,9 +65,7 @@ struct PencilArgs {
     // prep: cycles waiting for operands, neighbour values, record slots; writer: cycles waiting for results;
     // helper: polling rounds, cycles waiting for ring capacity
     unsigned long long* prof;
-    int debug;              // B200LS_PENCIL_DEBUG bits: 1 = no record prefetch, 2 = slow helper rounds
-    double* trace;          // B200LS_PENCIL_TRACE: [role][tile][step] value handled by lane `traceLane`, 4096 steps per tile
-    int traceLane;
+    int debug;              // B200LS_PENCIL_DEBUG bits: 2 = slow helper rounds
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -167,8 +165,10 @@ struct PencilTraits {
 // shared-memory layout of a CTA (dynamic):
 // [full[8] | empty[8] | progress words | neighbour ring | record ring | result ring | dot ring | raw ring]
 static constexpr int kPencilD = 8;          // steps held by the record ring
+static constexpr int kPencilPrep = 2;       // prep warps (step s is prepared by warp s % kPencilPrep)
+static constexpr int kPencilThreads = 32 * (3 + kPencilPrep);   // chain, helper, writer + the prep warps
 static constexpr int kPencilOutRows = 64;   // steps held by the result ring (power of two, > largest skew + 26)
-static constexpr int kPencilHeaderBytes = 256;
+static constexpr int kPencilHeaderBytes = 768;
 __host__ __device__ inline int pencilExtBytes(int extW) { return (kPencilE * extW * 8 + 127) / 128 * 128; }
 __host__ __device__ constexpr int pencilOutBytes() { return kPencilOutRows * 32 * 8; }
 template <int MODE, int NS>
@@ -193,7 +193,7 @@ __host__ __device__ constexpr bool pencilFits(int skewUnits, int SKEW, int NS, b
 // Hand-overs inside the CTA are sentinel words in shared memory (the value is the flag), mbarriers for the bulk
 // copies, and three progress words.
 template <int MODE, int SKEW, int NS>
-__global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
+__global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     using T = PencilTraits<MODE>;
     constexpr int DIR = T::DIR;
     constexpr bool GS = T::GS;
@@ -206,15 +206,20 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
     extern __shared__ __align__(128) unsigned char pencilSmem[];
     const bool doDot = MODE == PM_BWD && a.dotOut != nullptr;
     const unsigned smBase = smem_u32(pencilSmem);
-    const unsigned barFull = smBase;
-    const unsigned wExtReady = smBase + 128, wPrepProg = smBase + 132, wWriterProg = smBase + 136;
+    // mbarriers: raw stages [8], record full / empty [8 each], result written [16], neighbour values of a step [32]
+    const unsigned barFull = smBase, recFull = smBase + 64, recEmpty = smBase + 128, outFull = smBase + 192;
+    const unsigned extFull = smBase + 320, rawDone = smBase + 576;   // + raw stage read by every prep warp [8]
+    const unsigned wPrepProg = smBase + 640, wWriterProg = smBase + 656;   // prep progress: one word per prep warp
     const unsigned extRing = smBase + kPencilHeaderBytes;
     const unsigned recRing = extRing + pencilExtBytes(a.extW);
     const unsigned outRing = recRing + kPencilD * T::REC_STEP_BYTES;
     const unsigned dotRing = outRing + pencilOutBytes();
     const unsigned dataRing = dotRing + (doDot ? pencilOutBytes() : 0);
     const int lane = threadIdx.x & 31;
-    const int role = threadIdx.x >> 5;
+    const int wid = threadIdx.x >> 5;
+    // warp roles: 0 chain, 1 helper, 2 .. 1+kPencilPrep prep, last writer
+    const int role = wid == 0 ? 0 : wid == 1 ? 1 : wid == 2 + kPencilPrep ? 3 : 2;
+    const int prepId = wid - 2;
     const double sent = sentinel();
     const double NEUTRAL = MODE == PM_FACTOR ? 1.0 : 0.0;
     const int nx = a.nx;
@@ -225,18 +230,19 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
     if (threadIdx.x == 0) {
         for (int q = 0; q < NS; q++) {
             mbar_init(barFull + q * 8, 1);
+            mbar_init(rawDone + q * 8, kPencilPrep);
         }
+        for (int q = 0; q < kPencilD; q++) {
+            mbar_init(recFull + q * 8, 32);    // every prep lane arrives after its stores (release)
+            mbar_init(recEmpty + q * 8, 32);   // every chain lane arrives after its loads
+        }
+        for (int q = 0; q < 16; q++) mbar_init(outFull + q * 8, 32);   // every chain lane arrives after its result store
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // every record vector and every result slot starts armed; consumers re-arm what they take.  (A record is complete
-    // when the first word of each of its 16-byte vectors is no longer the sentinel: every vector is written by one
-    // store per lane, so no ordering between the stores is assumed.)
-    for (int e = threadIdx.x; e < kPencilD * 32 * NV; e += blockDim.x)
-        sts_f64(recRing + unsigned(e / NV) * T::REC_LANE_BYTES + unsigned(e % NV) * 16, sent);
-    for (int e = threadIdx.x; e < kPencilOutRows * 32; e += blockDim.x) sts_f64(outRing + unsigned(e) * 8, sent);
     __syncthreads();
 
-    unsigned gchunk0 = 0;   // chunks handed over by earlier tiles of this CTA (same count in every warp)
+    unsigned gchunk0 = 0;   // chunks / record groups handed over by earlier tiles of this CTA (same count in every warp)
+    unsigned ggroup0 = 0;
     for (int ti = blockIdx.x; ti < a.nTiles; ti += gridDim.x, gchunk0 += nChunks) {
         const PencilTileDev* tp = a.tiles + a.order[DIR > 0 ? ti : a.nTiles - 1 - ti];
         const int4 t0 = *reinterpret_cast<const int4*>(&tp->base);      // base, w, wj, wk
@@ -244,6 +250,9 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
         const int tbase = t0.x, w = t0.y, wj = t0.z, wk = t0.w;
         const int skewMax = SKEW * ((wj - 1) + (wk - 1));
         const int S = nx + skewMax;
+        const int S8 = (S + kPencilD - 1) & ~(kPencilD - 1);   // the pipeline runs whole record groups; the extra steps are idle
+        const unsigned group0 = ggroup0;
+        ggroup0 += unsigned(S8 / kPencilD);
         // neighbour tiles: chain side = where the new values come from, static side = old values (Gauss-Seidel) and
         // the tiles that wait for our results
         const int baseCJ = DIR > 0 ? tB.x : tB.z, baseCK = DIR > 0 ? tB.y : tB.w;
@@ -266,8 +275,10 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
             // helper warp: neighbour values
             // ------------------------------------------------------------------------------------------------
             if (lane == 0) {
-                st_release_cta(wExtReady, anyExt ? 0 : kNever);
-                st_release_cta(wPrepProg, 0);
+                // the per-step "neighbour values are in the ring" barriers start every tile in phase 0
+                for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                for (int q = 0; q < kPencilPrep; q++) st_release_cta(wPrepProg + q * 4, 0);
                 st_release_cta(wWriterProg, 0);
             }
             // columns without a source tile hold a constant for the whole tile
@@ -335,7 +346,10 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                     if (s0 + W - kPencilE > prepProg) {
                         const long long c0 = a.prof ? clock64() : 0;
                         while (s0 + W - kPencilE > prepProg) {
+                            __nanosleep(100);
                             prepProg = ld_acquire_cta(wPrepProg);
+#pragma unroll
+                            for (int q = 1; q < kPencilPrep; q++) prepProg = min(prepProg, ld_acquire_cta(wPrepProg + q * 4));
                             if (++spins > kMaxSpins) {
                                 *a.err = 1;
                                 break;
@@ -390,8 +404,10 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                         const int ready = firstMissing == nE ? min(W, S - s0) : firstMissing / nCols;
                         __syncwarp();
                         if (ready > published) {
+                            // one barrier per step: the prep warp sleeps on it (arrive = release of the ring stores above)
+                            if (lane == 0)
+                                for (int q = published; q < ready; q++) mbar_arrive(extFull + unsigned((s0 + q) & (kPencilE - 1)) * 8);
                             published = ready;
-                            if (lane == 0) st_release_cta(wExtReady, s0 + published);
                         }
                         if (firstMissing == nE) break;
                         if (++spins > kMaxSpins) {
@@ -449,18 +465,23 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                         bulk_g2s(dataRing + st * T::STAGE_BYTES + p * kPencilPlaneBytes, a.plane[p] + e0, bytes,
                                  barFull + st * 8);
             };
-            if (lane == 0)
+            if (prepId == 0 && lane == 0)
                 for (int cL = 0; cL < min(NS, nChunks); cL++) issueChunk(cL);
             int waitRow = 0;                          // first processing row of the next chunk to wait for
             int waitStep = 0;                         // step at which that wait falls due
             int relChunk = 0;
             int relStep = min(nx - 1, R - pad - 1) + skewMax;   // last step that reads the oldest chunk
-            int extAvail = anyExt ? 0 : kNever;
             unsigned long long pData = 0, pExt = 0, pSlot = 0;
-            unsigned recOff = 0;
-            for (int s = 0; s < S; s++) {
+            for (int s = prepId; s < S8; s += kPencilPrep) {
                 const int r = s - skew;
                 const bool act = laneOn && unsigned(r) < unsigned(nx);
+                // barrier tests first (their latency hides behind the loads): neighbour values of this step in the ring,
+                // record slot taken by the chain warp
+                const unsigned eb = extFull + unsigned(s & (kPencilE - 1)) * 8, ep = unsigned(s >> 5) & 1;
+                const unsigned grp = group0 + unsigned(s >> 3), slot = unsigned(s & 7);
+                const bool needExt = anyExt && s < S;
+                const bool extOk = !needExt || mbar_test_wait(eb, ep);
+                const bool slotOk = grp == 0 || mbar_test_wait(recEmpty + slot * 8, (grp - 1) & 1);
                 if (s >= waitStep) {                  // chunks holding processing rows <= s + LA
                     const long long c0 = a.prof ? clock64() : 0;
                     while (waitRow < nx && waitRow <= s + LA) {
@@ -471,22 +492,15 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                     waitStep = waitRow < nx ? waitRow - LA : kNever;
                     if (a.prof) pData += clock64() - c0;
                 }
-                if (s >= extAvail) {                  // neighbour values of this step are in the ring
-                    const long long c0 = a.prof ? clock64() : 0;
-                    unsigned spins = 0;
-                    while (extAvail <= s) {
-                        extAvail = ld_acquire_cta(wExtReady);
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
-                        }
-                    }
-                    if (a.prof) pExt += clock64() - c0;
-                }
                 const unsigned off = rowOff(r);
                 double c[NP];
 #pragma unroll
                 for (int p = 0; p < NP; p++) c[p] = lds_f64(off + p * kPencilPlaneBytes);
+                if (!extOk) {
+                    const long long c0 = a.prof ? clock64() : 0;
+                    mbar_wait(eb, ep, a.err);
+                    if (a.prof) pExt += clock64() - c0;
+                }
                 const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
                 double eJ = lds_f64(eJaddr + er), eK = lds_f64(eKaddr + er);
                 double oI = 0.0, oJ = 0.0, oK = 0.0;
@@ -554,45 +568,38 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                 }
                 rec[2 * NV - 2] = eK;
                 rec[2 * NV - 1] = eJ;
-                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(0) * a.nTiles + ti) * 4096 + s] = rec[0];
-                // wait until the chain warp has taken the previous occupant of the slot (every vector re-armed), then write
-                const unsigned ra = recLane + recOff;
+                // wait until the chain warp has taken the previous occupant of the slot, write, hand over (release)
+                const unsigned ra = recLane + slot * T::REC_STEP_BYTES;
                 {
-                    unsigned spins = 0;
-                    bool waited = false;
-                    long long c0 = 0;
-                    auto busy = [&]() {
-                        bool b = false;
-#pragma unroll
-                        for (int q = 0; q < NV; q++) b = b || !is_sentinel(lds_f64(ra + q * 16));
-                        return b;
-                    };
-                    while (__any_sync(0xffffffffu, busy())) {
-                        if (!waited && a.prof) c0 = clock64();
-                        waited = true;
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
-                        }
+                    if (!slotOk) {
+                        const long long c0 = a.prof ? clock64() : 0;
+                        mbar_wait(recEmpty + slot * 8, (grp - 1) & 1, a.err);
+                        if (a.prof) pSlot += clock64() - c0;
                     }
-                    if (waited && a.prof) pSlot += clock64() - c0;
-                }
 #pragma unroll
-                for (int q = NV - 1; q >= 0; q--) sts_v2(ra + q * 16, rec[2 * q], rec[2 * q + 1]);
+                    for (int q = 0; q < NV; q++) sts_v2(ra + q * 16, rec[2 * q], rec[2 * q + 1]);
+                    mbar_arrive(recFull + slot * 8);
+                }
                 if (doDot) sts_f64(dotLane + unsigned(s & (kPencilOutRows - 1)) * 256u, act ? c[4] : 0.0);
-                recOff = recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES;
-                // once the most skewed lane has read the last row of the oldest chunk, its stage takes the next chunk
-                if (s == relStep) {
+                // Once the most skewed lane has read the last row of the oldest chunk (step relStep) no step of this warp
+                // touches the chunk any more; when that holds for every prep warp its stage takes the next chunk.
+                while (s + kPencilPrep > relStep) {
+                    const unsigned gc = gchunk0 + unsigned(relChunk);
+                    const unsigned db = rawDone + (gc & (NS - 1)) * 8;
                     __syncwarp();
-                    if (lane == 0 && relChunk + NS < nChunks) issueChunk(relChunk + NS);
+                    if (lane == 0) mbar_arrive(db);
+                    if (prepId == 0 && relChunk + NS < nChunks) {
+                        mbar_wait(db, (gc / NS) & 1, a.err);
+                        if (lane == 0) issueChunk(relChunk + NS);
+                    }
                     relChunk++;
                     const int nextFirst = relChunk * R - pad;
                     relStep = nextFirst < nx ? min(nx - 1, nextFirst + R - 1) + skewMax : kNever;
                 }
-                // tell the helper how far the neighbour ring has been consumed
-                if ((s & 7) == 7 && anyExt && lane == 0) st_release_cta(wPrepProg, s);
+                // tell the helper how far the neighbour ring has been consumed (by this warp)
+                if ((s & 7) >= 8 - kPencilPrep && anyExt && lane == 0) st_release_cta(wPrepProg + prepId * 4, s);
             }
-            if (a.prof && lane == 0) {
+            if (a.prof && lane == 0 && prepId == 0) {
                 unsigned long long* q = a.prof + size_t(ti) * 16;
                 q[4] = pData;
                 q[5] = pExt;
@@ -609,47 +616,27 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
             const unsigned outLane = outRing + unsigned(lane) * 8;
             __syncthreads();   // tile start
             const unsigned long long pStart = a.prof ? globaltimer_ns() : 0;
+            const long long pClk0 = a.prof ? clock64() : 0;
             unsigned long long pRec = 0, pOut = 0;
             double y1 = NEUTRAL, sJ = NEUTRAL, sK = NEUTRAL;
-            unsigned recOff = 0, outOff = 0;
             int writerProg = 0;
-            // records are read one step ahead (two register sets): the loads of step s+1 are in flight during step s
-            auto loadRec = [&](double2 (&v)[NV], unsigned ra) {
-#pragma unroll
-                for (int q = 0; q < NV; q++) v[q] = lds_v2(ra + q * 16);
-            };
-            auto missing = [&](const double2 (&v)[NV]) {
-                bool m = false;
-#pragma unroll
-                for (int q = 0; q < NV; q++) m = m || is_sentinel(v[q].x);
-                return m;
-            };
-            auto takeRec = [&](double2 (&v)[NV], unsigned ra) {   // make sure the record is there, then free its slot
-                if (__any_sync(0xffffffffu, missing(v))) {
+            // Records are taken one step ahead: the wait and the loads of step s+1 are in flight during step s.  The
+            // loop is unrolled over the eight slots of the record ring, so slot and barrier addresses are immediates.
+            auto fetch = [&](double2 (&v)[NV], int slot, unsigned parity) {
+                if (!mbar_test_wait(recFull + slot * 8, parity)) {
                     const long long c0 = a.prof ? clock64() : 0;
-                    unsigned spins = 0;
-                    do {
-                        loadRec(v, ra);
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
-                        }
-                    } while (__any_sync(0xffffffffu, missing(v)));
+                    mbar_wait(recFull + slot * 8, parity, a.err);
                     if (a.prof) pRec += clock64() - c0;
                 }
 #pragma unroll
-                for (int q = 0; q < NV; q++) sts_f64(ra + q * 16, sent);
+                for (int q = 0; q < NV; q++) v[q] = lds_v2(recLane + slot * T::REC_STEP_BYTES + q * 16);
             };
-            auto step = [&](int s, const double2 (&v)[NV], double2 (&vn)[NV]) {
-                const unsigned raNext = recLane + (recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES);
-                if (s + 1 < S) loadRec(vn, raNext);
-                if ((a.debug & 1) && s + 1 < S) takeRec(vn, raNext);
+            auto step = [&](const double2 (&v)[NV], int slot, unsigned outBase, int o16) {
                 if (SKEW == 1) {
                     sJ = __shfl_sync(0xffffffffu, y1, srcJ);
                     sK = __shfl_sync(0xffffffffu, y1, srcK);
                 }
                 const double vK = extK ? v[NV - 1].x : sK, vJ = extJ ? v[NV - 1].y : sJ;
-                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(1) * a.nTiles + ti) * 4096 + s] = v[0].x;
                 double acc, y;
                 if (MODE == PM_FWD || MODE == PM_BWD) {
                     // record: {rD*in | in, t_K} {t_J, t_I}
@@ -688,16 +675,22 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                     sK = __shfl_sync(0xffffffffu, y1, srcK);
                 }
                 y1 = y;
-                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(2) * a.nTiles + ti) * 4096 + s] = y;
-                sts_f64(outLane + outOff, y);
-                recOff = recOff + T::REC_STEP_BYTES == kPencilD * T::REC_STEP_BYTES ? 0u : recOff + T::REC_STEP_BYTES;
-                outOff = (outOff + 256u) & (kPencilOutRows * 256u - 1u);
-                if (!(a.debug & 1) && s + 1 < S) takeRec(vn, raNext);
-                // result ring capacity: the slots of the next eight steps must have been re-armed by the writer
-                if ((s & 7) == 7 && writerProg < s + 9 + skewMax - kPencilOutRows) {
+                sts_f64(outBase + slot * 256, y);
+                mbar_arrive(outFull + (o16 + slot) * 8);   // result written (release): the writer sleeps on this barrier
+                mbar_arrive(recEmpty + slot * 8);           // the loads of this record have long completed
+            };
+            double2 vA[NV], vB[NV];
+            fetch(vA, 0, group0 & 1);
+            for (int s0 = 0; s0 < S8; s0 += kPencilD) {
+                const unsigned par = (group0 + unsigned(s0 >> 3)) & 1;
+                const unsigned outBase = outLane + unsigned(s0 & (kPencilOutRows - 1)) * 256u;
+                const int o16 = int((group0 + unsigned(s0 >> 3)) & 1) * 8;   // result barriers of this group
+                // the writer waits on 16 result barriers by phase parity: it must have finished the group before last
+                if (writerProg < s0 - 8) {
                     const long long c0 = a.prof ? clock64() : 0;
                     unsigned spins = 0;
-                    while (writerProg < s + 9 + skewMax - kPencilOutRows) {
+                    while (writerProg < s0 - 8) {
+                        __nanosleep(40);
                         writerProg = ld_acquire_cta(wWriterProg);
                         if (++spins > kMaxSpins) {
                             *a.err = 1;
@@ -706,22 +699,22 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
                     }
                     if (a.prof) pOut += clock64() - c0;
                 }
-            };
-            double2 vA[NV], vB[NV];
-            loadRec(vA, recLane);
-            takeRec(vA, recLane);
-            int s = 0;
-            for (; s + 1 < S; s += 2) {
-                step(s, vA, vB);
-                step(s + 1, vB, vA);
+#pragma unroll
+                for (int k = 0; k < kPencilD; k += 2) {
+                    fetch(vB, k + 1, par);
+                    step(vA, k, outBase, o16);
+                    if (k + 2 < kPencilD) fetch(vA, k + 2, par);
+                    else if (s0 + kPencilD < S8) fetch(vA, 0, par ^ 1);
+                    step(vB, k + 1, outBase, o16);
+                }
             }
-            if (s < S) step(s, vA, vB);
             if (a.prof && lane == 0) {
                 unsigned long long* q = a.prof + size_t(ti) * 16;
                 q[0] = pStart;
                 q[1] = globaltimer_ns();
                 q[2] = pRec;
                 q[3] = pOut;
+                q[10] = (unsigned long long)(clock64() - pClk0);
             }
             __syncthreads();   // tile end
         } else {
@@ -738,38 +731,30 @@ __global__ void __launch_bounds__(128, 1) k_pencil(PencilArgs a) {
             int elemRow = tbase + lane + (DIR > 0 ? -skewMax : nx - 1 + skewMax) * w;   // ... of the row completed at step 0
             __syncthreads();   // tile start
             unsigned long long pWait = 0;
-            for (int s = 0; s < S; s++) {
+            for (int s = 0; s < S8; s++) {
                 const unsigned slotS = outLane + unsigned(s & (kPencilOutRows - 1)) * 256u;
-                double v = lds_f64(slotS);
-                if (__any_sync(0xffffffffu, is_sentinel(v))) {
-                    const long long c0 = a.prof ? clock64() : 0;
-                    unsigned spins = 0;
-                    do {
-                        v = lds_f64(slotS);
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
-                        }
-                    } while (__any_sync(0xffffffffu, is_sentinel(v)));
-                    if (a.prof) pWait += clock64() - c0;
+                {
+                    // sleep until the chain warp has stored the results of this step
+                    const unsigned gs = group0 * kPencilD + unsigned(s);
+                    const unsigned ob = outFull + (gs & 15) * 8, op = (gs >> 4) & 1;
+                    if (!mbar_test_wait(ob, op)) {
+                        const long long c0 = a.prof ? clock64() : 0;
+                        mbar_wait(ob, op, a.err);
+                        if (a.prof) pWait += clock64() - c0;
+                    }
                 }
+                const double v = lds_f64(slotS);
                 const int r = s - skew;
                 const bool act = laneOn && unsigned(r) < unsigned(nx);
-                if (a.trace && lane == a.traceLane && s < 4096) a.trace[(size_t(3) * a.nTiles + ti) * 4096 + s] = v;
-                if (act) {
-                    if (faceLane) st_l2(a.out + elem, v);
-                } else {
-                    sts_f64(slotS, sent);   // an idle lane's slot is free again at once
-                }
+                if (act && faceLane) st_l2(a.out + elem, v);
                 const int q = s - skewMax;   // processing row every lane has finished now
-                if (laneOn && q >= 0) {
+                if (laneOn && unsigned(q) < unsigned(nx)) {
                     const unsigned slotQ = outLane + unsigned((s - delay) & (kPencilOutRows - 1)) * 256u;
                     const double vq = lds_f64(slotQ);   // this lane's own result `delay` steps ago (== v when delay is 0)
                     st_l2(a.out + elemRow, vq);
                     if (MODE == PM_FACTOR) a.out2[elemRow] = 1.0 / vq;
                     if (doClear) a.clear[elemRow] = sent;
                     if (doDot) dsum[0] += vq * lds_f64(dotLane + unsigned((s - delay) & (kPencilOutRows - 1)) * 256u);
-                    sts_f64(slotQ, sent);
                 }
                 elem += DIR * w;
                 elemRow += DIR * w;

@@ -118,7 +118,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     int occ;
     auto it = occCache.find(smem);
     if (it == occCache.end()) {
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 128, smem));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPencilThreads, smem));
         occCache[smem] = occ;
     } else {
         occ = it->second;
@@ -140,33 +140,13 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
         B2_CUDA(cudaMemsetAsync(profBuf.p, 0, size_t(a.nTiles) * 128, c.stream));
         a.prof = profBuf.p;
     }
-    // debugging aid: B200LS_PENCIL_TRACE=<file> records, per tile and step, the value one lane handles in each warp
-    static const char* traceFile = getenv("B200LS_PENCIL_TRACE");
-    static DevBuf<double> traceBuf;
-    if (traceFile) {
-        traceBuf.alloc(size_t(4) * a.nTiles * 4096);
-        B2_CUDA(cudaMemsetAsync(traceBuf.p, 0, traceBuf.n * 8, c.stream));
-        a.trace = traceBuf.p;
-        a.traceLane = getenv("B200LS_PENCIL_TRACE_LANE") ? atoi(getenv("B200LS_PENCIL_TRACE_LANE")) : 0;
-    }
     void* args[] = {&a};
-    cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(128), args, smem, c.stream);
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(kPencilThreads), args, smem, c.stream);
     if (le != cudaSuccess)
         throw CudaError(std::string("pencil sweep launch failed: ") + cudaGetErrorString(le) + " (mode " +
                         std::to_string(MODE) + ", " + std::to_string(blocks) + " CTAs, " + std::to_string(smem) +
                         " B shared memory, occupancy " + std::to_string(occ) + "/SM)");
     c.launches++;
-    if (traceFile) {
-        std::vector<double> h(traceBuf.n);
-        B2_CUDA(cudaMemcpyAsync(h.data(), traceBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
-        B2_CUDA(cudaStreamSynchronize(c.stream));
-        if (FILE* f = fopen(traceFile, "ab")) {
-            const int hdr[4] = {MODE, a.nTiles, a.nx, 0};
-            fwrite(hdr, sizeof(int), 4, f);
-            fwrite(h.data(), 8, h.size(), f);
-            fclose(f);
-        }
-    }
     if (profFile) {
         std::vector<unsigned long long> h(size_t(a.nTiles) * 16);
         B2_CUDA(cudaMemcpyAsync(h.data(), profBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
