@@ -40,6 +40,10 @@ for blk in blocks[-2:]:
              "prep: wait record slot", "writer: wait results", "helper: polling rounds", "helper: wait ring capacity"]
     for k, nm in enumerate(names):
         print(f"  {nm:28s} mean {a[:, 2 + k].mean():10.0f}  max {a[:, 2 + k].max():10d}")
+    # time at which the chain warp starts each group of eight steps, for the first tiles
+    for i in [0, 1, 2, 3, 4, 17]:
+        g = a[i, 16:16 + 19]
+        print(f"  tile {i:3d} group starts (us): " + " ".join(f"{(v - t0) / 1e3:6.1f}" if v else "   -  " for v in g))
     mhz = a[:, 10] / np.maximum(1e-9, (a[:, 1] - a[:, 0]) / 1e3)
     print(f"  chain warp: SM clock seen = cycles / globaltimer: median {np.median(mhz):.0f} MHz (min {mhz.min():.0f}, max {mhz.max():.0f})")
     for i in [0, 1, 2, 3, 16, 100, 255, 300, len(a) - 1]:

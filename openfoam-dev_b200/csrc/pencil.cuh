@@ -41,7 +41,8 @@ static constexpr int kPencilMaxPlanes = 9;
 static constexpr int kPencilR = 8;                          // rows per bulk copy / ring stage
 static constexpr int kPencilPlaneBytes = kPencilR * 32 * 8; // one plane of one stage
 static constexpr int kPencilE = 32;                         // steps held by the neighbour-value ring
-static constexpr int kPencilMaxE = 6;                       // neighbour values per helper lane and window
+static constexpr int kPencilCPL = 3;                        // ring columns per helper lane (up to 96 columns)
+static constexpr int kPencilLook = 6;                       // steps per column a helper round looks ahead
 
 struct PencilArgs {
     const PencilTileDev* tiles;
@@ -49,7 +50,6 @@ struct PencilArgs {
     int nTiles;
     int nx, ny, nz;
     int extW;               // doubles per step of the neighbour-value ring (full tile)
-    int window;             // steps per helper window
     // operand planes in position order (see k_pencil for the meaning per mode); unused entries are null
     const double* plane[kPencilMaxPlanes];
     double* out;            // sentinel-armed result
@@ -156,7 +156,7 @@ struct PencilTraits {
     static constexpr int NP = MODE == PM_FWD ? 5 : MODE == PM_BWD ? 5 : MODE == PM_FACTOR ? 7 : 9;
     static constexpr int STAGE_BYTES = NP * kPencilPlaneBytes;
     // 16-byte vectors of a step record (what the chain warp reads per lane and step)
-    static constexpr int NV = MODE == PM_GS_FWD ? 5 : MODE == PM_GS_REV ? 4 : 3;
+    static constexpr int NV = MODE == PM_GS_FWD ? 4 : MODE == PM_GS_REV ? 3 : 2;
     // lane stride: an odd number of vectors keeps the 16-byte accesses of a quarter warp on distinct banks
     static constexpr int REC_LANE_BYTES = (NV | 1) * 16;
     static constexpr int REC_STEP_BYTES = 32 * REC_LANE_BYTES;
@@ -164,6 +164,7 @@ struct PencilTraits {
 
 // shared-memory layout of a CTA (dynamic):
 // [full[8] | empty[8] | progress words | neighbour ring | record ring | result ring | dot ring | raw ring]
+static constexpr int kPencilProfWords = 64;  // debugging counters per tile (B200LS_PENCIL_PROF)
 static constexpr int kPencilD = 8;          // steps held by the record ring
 static constexpr int kPencilPrep = 2;       // prep warps (step s is prepared by warp s % kPencilPrep)
 static constexpr int kPencilThreads = 32 * (3 + kPencilPrep);   // chain, helper, writer + the prep warps
@@ -205,11 +206,12 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     static_assert((NS & (NS - 1)) == 0 && NS <= 8, "ring stages: a power of two, at most 8");
     extern __shared__ __align__(128) unsigned char pencilSmem[];
     const bool doDot = MODE == PM_BWD && a.dotOut != nullptr;
-    const unsigned smBase = smem_u32(pencilSmem);
+    unsigned smBase = smem_u32(pencilSmem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smBase));   // opaque: keep the base in a register (not re-derived from SR_CgaCtaId)
     // mbarriers: raw stages [8], record full / empty [8 each], result written [16], neighbour values of a step [32]
     const unsigned barFull = smBase, recFull = smBase + 64, recEmpty = smBase + 128, outFull = smBase + 192;
     const unsigned extFull = smBase + 320, rawDone = smBase + 576;   // + raw stage read by every prep warp [8]
-    const unsigned wPrepProg = smBase + 640, wWriterProg = smBase + 656;   // prep progress: one word per prep warp
+    const unsigned wChainProg = smBase + 640, wWriterProg = smBase + 656;
     const unsigned extRing = smBase + kPencilHeaderBytes;
     const unsigned recRing = extRing + pencilExtBytes(a.extW);
     const unsigned outRing = recRing + kPencilD * T::REC_STEP_BYTES;
@@ -233,10 +235,11 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             mbar_init(rawDone + q * 8, kPencilPrep);
         }
         for (int q = 0; q < kPencilD; q++) {
-            mbar_init(recFull + q * 8, 32);    // every prep lane arrives after its stores (release)
-            mbar_init(recEmpty + q * 8, 32);   // every chain lane arrives after its loads
+            // one arrival each, by lane 0 after __syncwarp() (a 32-lane arrive is 32 serialised shared-memory atomics)
+            mbar_init(recFull + q * 8, 1);     // prep warp: record stored
+            mbar_init(recEmpty + q * 8, 1);    // chain warp: record loaded
         }
-        for (int q = 0; q < 16; q++) mbar_init(outFull + q * 8, 32);   // every chain lane arrives after its result store
+        for (int q = 0; q < 16; q++) mbar_init(outFull + q * 8, 1);   // chain warp: result stored
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 // the per-step "neighbour values are in the ring" barriers start every tile in phase 0
                 for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                for (int q = 0; q < kPencilPrep; q++) st_release_cta(wPrepProg + q * 4, 0);
+                st_release_cta(wChainProg, 0);
                 st_release_cta(wWriterProg, 0);
             }
             // columns without a source tile hold a constant for the whole tile
@@ -286,24 +289,25 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 sts_f64(extRing + unsigned(e) * 8, (e % a.extW) < colSJ ? NEUTRAL : 0.0);
             __syncthreads();   // tile start: rings initialised, progress words reset
 
-            // ---- neighbour-value entries of this lane: (step offset, column) pairs over the present columns ----
+            // ---- every lane streams up to kPencilCPL columns of the ring (one source pencil of a neighbour tile each) ----
             const int4 tW = *reinterpret_cast<const int4*>(tp->nbrW);
             const int4 tJ = *reinterpret_cast<const int4*>(tp->nbrWj);
             const int nCols = (hasCJ ? wk : 0) + (hasCK ? wj : 0) + (hasSJ ? wk : 0) + (hasSK ? wj : 0);
-            const int W = a.window;
-            const int nE = W * nCols;
-            int eOff[kPencilMaxE];      // element offset of row 0 of the source pencil, -1: no entry
-            int eStride[kPencilMaxE];   // row stride of the source tile
-            int eInfo[kPencilMaxE];     // step offset | skew << 8 | column << 16 | chain << 24
+            const double* cSrc[kPencilCPL];   // element (row 0) of the source pencil; nullptr: no column
+            int cStride[kPencilCPL];          // row stride of the source tile
+            int cSkew[kPencilCPL];            // skew of the lane of this tile that consumes the column
+            unsigned cDst[kPencilCPL];        // ring address of the column in row 0
+            bool cChain[kPencilCPL];          // new values (polled) or old values (plain loads)
+            int cProg[kPencilCPL];            // steps of the column already in the ring
 #pragma unroll
-            for (int k = 0; k < kPencilMaxE; k++) {
-                const int e = k * 32 + lane;
-                eOff[k] = -1;
-                eStride[k] = 0;
-                eInfo[k] = 0;
-                if (nCols > 0 && e < nE) {
-                    const int stepOff = e / nCols;
-                    int q = e - stepOff * nCols;
+            for (int c = 0; c < kPencilCPL; c++) {
+                int q = c * 32 + lane;
+                cSrc[c] = nullptr;
+                cStride[c] = cSkew[c] = 0;
+                cDst[c] = 0;
+                cChain[c] = false;
+                cProg[c] = S;   // a lane without column never holds anyone back
+                if (q < nCols) {
                     // which group does column q of the compacted list belong to: 0 chain J, 1 chain K, 2 static J, 3 static K
                     int grp = -1, idx = 0;
                     if (hasCJ) { if (grp < 0 && q < wk) { grp = 0; idx = q; } q -= wk; }
@@ -329,96 +333,80 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     }
                     const int ejr = DIR > 0 ? ej : wj - 1 - ej, ekr = DIR > 0 ? ek : wk - 1 - ek;
                     const int col = (grp == 0 ? 0 : grp == 1 ? colCK : grp == 2 ? colSJ : colSK) + idx;
-                    eOff[k] = nBase + srcLane;
-                    eStride[k] = nW;
-                    eInfo[k] = stepOff | ((SKEW * (ejr + ekr)) << 8) | (col << 16) | (isChain ? (1 << 24) : 0);
+                    cSrc[c] = (isChain ? a.out : a.plane[8]) + nBase + srcLane;
+                    cStride[c] = nW;
+                    cSkew[c] = SKEW * (ejr + ekr);
+                    cDst[c] = extRing + unsigned(col) * 8;
+                    cChain[c] = isChain;
+                    cProg[c] = 0;
                 }
             }
-            const double* chainSrc = a.out;
-            const double* staticSrc = a.plane[8];
 
+            // Rounds: every lane loads the next kPencilLook steps of its columns (all loads in flight together), deposits
+            // the values that have arrived -- a producer publishes a pencil in order, so they form a prefix -- and the
+            // steps complete in EVERY column are handed over (one barrier per step).
             unsigned long long pRounds = 0, pCap = 0;
             if (nCols > 0) {
-                int prepProg = 0;
-                for (int s0 = 0; s0 < S; s0 += W) {
-                    // ring capacity: the window may only overwrite steps the prep warp has left behind
-                    unsigned spins = 0;
-                    if (s0 + W - kPencilE > prepProg) {
+                int published = 0, chainProg = 0;
+                unsigned spins = 0;
+                while (published < S) {
+                    pRounds++;
+                    if (a.debug & 2) __nanosleep(1000);
+                    // ring capacity: rows of steps the chain warp (the last reader) has finished may be overwritten
+                    const int limit = min(S, chainProg + kPencilE);
+                    double v[kPencilCPL][kPencilLook];
+#pragma unroll
+                    for (int c = 0; c < kPencilCPL; c++) {
+                        if (c * 32 >= nCols) break;   // (uniform) columns per lane actually in use
+#pragma unroll
+                        for (int d = 0; d < kPencilLook; d++) {
+                            const int st = cProg[c] + d, r = st - cSkew[c];
+                            v[c][d] = cChain[c] ? NEUTRAL : 0.0;   // rows outside the block: a constant
+                            if (cSrc[c] && st < limit && unsigned(r) < unsigned(nx)) {
+                                const double* p = cSrc[c] + size_t(DIR > 0 ? r : nx - 1 - r) * size_t(cStride[c]);
+                                v[c][d] = cChain[c] ? ld_l2(p) : ld_cg(p);
+                            }
+                        }
+                    }
+                    int myMin = S;
+#pragma unroll
+                    for (int c = 0; c < kPencilCPL; c++) {
+                        if (c * 32 >= nCols) break;
+                        if (cSrc[c]) {
+                            int cnt = 0;
+#pragma unroll
+                            for (int d = 0; d < kPencilLook; d++) {
+                                const int st = cProg[c] + d;
+                                if (cnt == d && st < limit && !(cChain[c] && is_sentinel(v[c][d]))) {
+                                    sts_f64(cDst[c] + unsigned(st & (kPencilE - 1)) * extRowB, v[c][d]);
+                                    cnt++;
+                                }
+                            }
+                            cProg[c] += cnt;
+                            myMin = min(myMin, cProg[c]);
+                        }
+                    }
+                    const int ready = __reduce_min_sync(0xffffffffu, myMin);
+                    __syncwarp();
+                    if (ready > published) {
+                        // arrive = release of the ring stores above; the chain / prep warps sleep on these barriers
+                        if (lane == 0)
+                            for (int q = published; q < ready; q++) mbar_arrive(extFull + unsigned(q & (kPencilE - 1)) * 8);
+                        published = ready;
+                        spins = 0;
+                    } else if (++spins > kMaxSpins) {
+                        *a.err = 1;
+                        break;
+                    }
+                    if (published + kPencilLook > chainProg + kPencilE) {
                         const long long c0 = a.prof ? clock64() : 0;
-                        while (s0 + W - kPencilE > prepProg) {
-                            __nanosleep(100);
-                            prepProg = ld_acquire_cta(wPrepProg);
-#pragma unroll
-                            for (int q = 1; q < kPencilPrep; q++) prepProg = min(prepProg, ld_acquire_cta(wPrepProg + q * 4));
-                            if (++spins > kMaxSpins) {
-                                *a.err = 1;
-                                break;
-                            }
-                        }
+                        chainProg = ld_acquire_cta(wChainProg);
                         if (a.prof) pCap += clock64() - c0;
-                    }
-                    // entries of this window: constants are deposited at once, the others are polled
-                    unsigned pend = 0;
-#pragma unroll
-                    for (int k = 0; k < kPencilMaxE; k++) {
-                        const int step = s0 + (eInfo[k] & 0xff);
-                        if (eOff[k] >= 0 && step < S) {
-                            const int r = step - ((eInfo[k] >> 8) & 0xff);
-                            if (r >= 0 && r < nx) {
-                                pend |= 1u << k;
-                            } else {
-                                sts_f64(extRing + unsigned(step & (kPencilE - 1)) * extRowB + unsigned((eInfo[k] >> 16) & 0xff) * 8,
-                                        (eInfo[k] >> 24) ? NEUTRAL : 0.0);
-                            }
-                        }
-                    }
-                    int published = 0;
-                    spins = 0;
-                    while (true) {
-                        // one polling round: every value still missing, all loads in flight together
-                        double v[kPencilMaxE];
-                        pRounds++;
-                        if (a.debug & 2) __nanosleep(1000);
-#pragma unroll
-                        for (int k = 0; k < kPencilMaxE; k++) {
-                            if (pend & (1u << k)) {
-                                const int r = s0 + (eInfo[k] & 0xff) - ((eInfo[k] >> 8) & 0xff);
-                                const int i = DIR > 0 ? r : nx - 1 - r;
-                                const size_t el = size_t(eOff[k]) + size_t(i) * size_t(eStride[k]);
-                                v[k] = (eInfo[k] >> 24) ? ld_l2(chainSrc + el) : ld_cg(staticSrc + el);
-                            }
-                        }
-                        int firstMissing = nE;
-#pragma unroll
-                        for (int k = 0; k < kPencilMaxE; k++) {
-                            if ((pend & (1u << k)) && !((eInfo[k] >> 24) && is_sentinel(v[k]))) {
-                                const int step = s0 + (eInfo[k] & 0xff);
-                                sts_f64(extRing + unsigned(step & (kPencilE - 1)) * extRowB + unsigned((eInfo[k] >> 16) & 0xff) * 8,
-                                        v[k]);
-                                pend &= ~(1u << k);
-                            }
-                            const unsigned m = __ballot_sync(0xffffffffu, (pend >> k) & 1u);
-                            if (m && firstMissing == nE) firstMissing = k * 32 + (__ffs(m) - 1);
-                        }
-                        // steps whose values are all in the ring
-                        const int ready = firstMissing == nE ? min(W, S - s0) : firstMissing / nCols;
-                        __syncwarp();
-                        if (ready > published) {
-                            // one barrier per step: the prep warp sleeps on it (arrive = release of the ring stores above)
-                            if (lane == 0)
-                                for (int q = published; q < ready; q++) mbar_arrive(extFull + unsigned((s0 + q) & (kPencilE - 1)) * 8);
-                            published = ready;
-                        }
-                        if (firstMissing == nE) break;
-                        if (++spins > kMaxSpins) {
-                            *a.err = 1;
-                            break;
-                        }
                     }
                 }
             }
             if (a.prof && lane == 0) {
-                unsigned long long* q = a.prof + size_t(ti) * 16;
+                unsigned long long* q = a.prof + size_t(ti) * kPencilProfWords;
                 q[8] = pRounds;
                 q[9] = pCap;
             }
@@ -432,7 +420,6 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             const int oJoff = sExtJ ? 0 : DIR * 8, oKoff = sExtK ? 0 : DIR * wj * 8;
             const unsigned wB = unsigned(w) * 8;
             const unsigned ringLane = dataRing + unsigned(lane) * 8;
-            const unsigned eJaddr = extRing + unsigned(kk) * 8, eKaddr = extRing + unsigned(colCK + jj) * 8;
             const unsigned sJaddr = extRing + unsigned(colSJ + kk) * 8, sKaddr = extRing + unsigned(colSK + jj) * 8;
             const unsigned recLane = recRing + unsigned(lane) * T::REC_LANE_BYTES;
             const unsigned dotLane = dotRing + unsigned(lane) * 8;
@@ -479,7 +466,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 // record slot taken by the chain warp
                 const unsigned eb = extFull + unsigned(s & (kPencilE - 1)) * 8, ep = unsigned(s >> 5) & 1;
                 const unsigned grp = group0 + unsigned(s >> 3), slot = unsigned(s & 7);
-                const bool needExt = anyExt && s < S;
+                const bool needExt = GS && (hasSJ || hasSK) && s < S;   // old values of the neighbour tiles
                 const bool extOk = !needExt || mbar_test_wait(eb, ep);
                 const bool slotOk = grp == 0 || mbar_test_wait(recEmpty + slot * 8, (grp - 1) & 1);
                 if (s >= waitStep) {                  // chunks holding processing rows <= s + LA
@@ -502,7 +489,6 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     if (a.prof) pExt += clock64() - c0;
                 }
                 const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
-                double eJ = lds_f64(eJaddr + er), eK = lds_f64(eKaddr + er);
                 double oI = 0.0, oJ = 0.0, oK = 0.0;
                 if (GS) {
                     const double esJ = lds_f64(sJaddr + er), esK = lds_f64(sKaddr + er);
@@ -557,17 +543,13 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     rec[5] = 0.0;
                 }
                 if (!act) {
-                    // idle lane: a record whose result is NEUTRAL whatever the neighbours hold
+                    // idle lane: a record whose result is NEUTRAL whatever (finite) values the neighbours hold
 #pragma unroll
-                    for (int q = 0; q < 2 * NV - 2; q++) rec[q] = 0.0;
+                    for (int q = 0; q < 2 * NV; q++) rec[q] = 0.0;
                     if (MODE == PM_FACTOR) rec[0] = 1.0;
                     if (MODE == PM_GS_FWD) rec[7] = 1.0;
                     if (MODE == PM_GS_REV) rec[4] = 1.0;
-                    eJ = NEUTRAL;
-                    eK = NEUTRAL;
                 }
-                rec[2 * NV - 2] = eK;
-                rec[2 * NV - 1] = eJ;
                 // wait until the chain warp has taken the previous occupant of the slot, write, hand over (release)
                 const unsigned ra = recLane + slot * T::REC_STEP_BYTES;
                 {
@@ -578,7 +560,8 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     }
 #pragma unroll
                     for (int q = 0; q < NV; q++) sts_v2(ra + q * 16, rec[2 * q], rec[2 * q + 1]);
-                    mbar_arrive(recFull + slot * 8);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(recFull + slot * 8);
                 }
                 if (doDot) sts_f64(dotLane + unsigned(s & (kPencilOutRows - 1)) * 256u, act ? c[4] : 0.0);
                 // Once the most skewed lane has read the last row of the oldest chunk (step relStep) no step of this warp
@@ -596,14 +579,12 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     const int nextFirst = relChunk * R - pad;
                     relStep = nextFirst < nx ? min(nx - 1, nextFirst + R - 1) + skewMax : kNever;
                 }
-                // tell the helper how far the neighbour ring has been consumed (by this warp)
-                if ((s & 7) >= 8 - kPencilPrep && anyExt && lane == 0) st_release_cta(wPrepProg + prepId * 4, s);
             }
             if (a.prof && lane == 0 && prepId == 0) {
-                unsigned long long* q = a.prof + size_t(ti) * 16;
+                unsigned long long* q = a.prof + size_t(ti) * kPencilProfWords;
                 q[4] = pData;
-                q[5] = pExt;
                 q[6] = pSlot;
+                q[11] = pExt;
             }
             __syncthreads();   // tile end
         } else if (role == 0) {
@@ -617,26 +598,50 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             __syncthreads();   // tile start
             const unsigned long long pStart = a.prof ? globaltimer_ns() : 0;
             const long long pClk0 = a.prof ? clock64() : 0;
-            unsigned long long pRec = 0, pOut = 0;
+            unsigned long long pRec = 0, pOut = 0, pExt = 0;
+            const unsigned eJaddr = extRing + unsigned(kk) * 8, eKaddr = extRing + unsigned(colCK + jj) * 8;
             double y1 = NEUTRAL, sJ = NEUTRAL, sK = NEUTRAL;
             int writerProg = 0;
             // Records are taken one step ahead: the wait and the loads of step s+1 are in flight during step s.  The
             // loop is unrolled over the eight slots of the record ring, so slot and barrier addresses are immediates.
-            auto fetch = [&](double2 (&v)[NV], int slot, unsigned parity) {
-                if (!mbar_test_wait(recFull + slot * 8, parity)) {
-                    const long long c0 = a.prof ? clock64() : 0;
-                    mbar_wait(recFull + slot * 8, parity, a.err);
-                    if (a.prof) pRec += clock64() - c0;
-                }
+            // (both barrier tests are issued first and the loads go out speculatively, so the test latencies overlap each
+            // other and the arithmetic of the current step; only when a test fails is the warp put to sleep and the
+            // loads repeated)
+            const bool chainExt = hasCJ || hasCK;
+            auto fetch = [&](double2 (&v)[NV], double2& e, int slot, unsigned parity, int s) {
+                const unsigned rb = recFull + slot * 8;
+                const unsigned eb = extFull + unsigned(s & (kPencilE - 1)) * 8, ep = unsigned(s >> 5) & 1;
+                const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
+                const bool needExt = chainExt && s < S;
+                const bool recOk = mbar_test_wait(rb, parity);
+                const bool extOk = !needExt || mbar_test_wait(eb, ep);
 #pragma unroll
                 for (int q = 0; q < NV; q++) v[q] = lds_v2(recLane + slot * T::REC_STEP_BYTES + q * 16);
+                e.x = lds_f64(eKaddr + er);
+                e.y = lds_f64(eJaddr + er);
+                return recOk && extOk;
             };
-            auto step = [&](const double2 (&v)[NV], int slot, unsigned outBase, int o16) {
+            auto refetch = [&](double2 (&v)[NV], double2& e, int slot, unsigned parity, int s) {   // slow path
+                const long long c0 = a.prof ? clock64() : 0;
+                mbar_wait(recFull + slot * 8, parity, a.err);
+                const long long c1 = a.prof ? clock64() : 0;
+                if (chainExt && s < S) mbar_wait(extFull + unsigned(s & (kPencilE - 1)) * 8, unsigned(s >> 5) & 1, a.err);
+                if (a.prof) {
+                    pRec += c1 - c0;
+                    pExt += clock64() - c1;
+                }
+                const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
+#pragma unroll
+                for (int q = 0; q < NV; q++) v[q] = lds_v2(recLane + slot * T::REC_STEP_BYTES + q * 16);
+                e.x = lds_f64(eKaddr + er);
+                e.y = lds_f64(eJaddr + er);
+            };
+            auto step = [&](const double2 (&v)[NV], const double2& e, int slot, unsigned outBase, int o16) {
                 if (SKEW == 1) {
                     sJ = __shfl_sync(0xffffffffu, y1, srcJ);
                     sK = __shfl_sync(0xffffffffu, y1, srcK);
                 }
-                const double vK = extK ? v[NV - 1].x : sK, vJ = extJ ? v[NV - 1].y : sJ;
+                const double vK = extK ? e.x : sK, vJ = extJ ? e.y : sJ;
                 double acc, y;
                 if (MODE == PM_FWD || MODE == PM_BWD) {
                     // record: {rD*in | in, t_K} {t_J, t_I}
@@ -676,15 +681,19 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 }
                 y1 = y;
                 sts_f64(outBase + slot * 256, y);
-                mbar_arrive(outFull + (o16 + slot) * 8);   // result written (release): the writer sleeps on this barrier
-                mbar_arrive(recEmpty + slot * 8);           // the loads of this record have long completed
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(outFull + (o16 + slot) * 8);   // result written (release): the writer sleeps on this barrier
+                    mbar_arrive(recEmpty + slot * 8);           // the loads of this record have long completed
+                }
             };
-            double2 vA[NV], vB[NV];
-            fetch(vA, 0, group0 & 1);
+            double2 vA[NV], vB[NV], eA, eB;
+            if (!fetch(vA, eA, 0, group0 & 1, 0)) refetch(vA, eA, 0, group0 & 1, 0);
             for (int s0 = 0; s0 < S8; s0 += kPencilD) {
                 const unsigned par = (group0 + unsigned(s0 >> 3)) & 1;
                 const unsigned outBase = outLane + unsigned(s0 & (kPencilOutRows - 1)) * 256u;
                 const int o16 = int((group0 + unsigned(s0 >> 3)) & 1) * 8;   // result barriers of this group
+                if (a.prof && lane == 0 && (s0 >> 3) < 48) a.prof[size_t(ti) * kPencilProfWords + 16 + (s0 >> 3)] = globaltimer_ns();
                 // the writer waits on 16 result barriers by phase parity: it must have finished the group before last
                 if (writerProg < s0 - 8) {
                     const long long c0 = a.prof ? clock64() : 0;
@@ -701,20 +710,26 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 }
 #pragma unroll
                 for (int k = 0; k < kPencilD; k += 2) {
-                    fetch(vB, k + 1, par);
-                    step(vA, k, outBase, o16);
-                    if (k + 2 < kPencilD) fetch(vA, k + 2, par);
-                    else if (s0 + kPencilD < S8) fetch(vA, 0, par ^ 1);
-                    step(vB, k + 1, outBase, o16);
+                    const bool okB = fetch(vB, eB, k + 1, par, s0 + k + 1);
+                    step(vA, eA, k, outBase, o16);
+                    if (!okB) refetch(vB, eB, k + 1, par, s0 + k + 1);
+                    const int kn = (k + 2) & (kPencilD - 1);
+                    const unsigned pn = k + 2 < kPencilD ? par : par ^ 1;
+                    const bool okA = fetch(vA, eA, kn, pn, s0 + k + 2);   // (past the last group: never consumed)
+                    step(vB, eB, k + 1, outBase, o16);
+                    if (!okA && s0 + k + 2 < S8) refetch(vA, eA, kn, pn, s0 + k + 2);
                 }
+                // tell the helper how far the neighbour ring has been consumed
+                if (anyExt && lane == 0) st_release_cta(wChainProg, s0 + kPencilD - 1);
             }
             if (a.prof && lane == 0) {
-                unsigned long long* q = a.prof + size_t(ti) * 16;
+                unsigned long long* q = a.prof + size_t(ti) * kPencilProfWords;
                 q[0] = pStart;
                 q[1] = globaltimer_ns();
                 q[2] = pRec;
                 q[3] = pOut;
                 q[10] = (unsigned long long)(clock64() - pClk0);
+                q[5] = pExt;
             }
             __syncthreads();   // tile end
         } else {
@@ -760,7 +775,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 elemRow += DIR * w;
                 if ((s & 7) == 7 && lane == 0) st_release_cta(wWriterProg, s + 1);
             }
-            if (a.prof && lane == 0) a.prof[size_t(ti) * 16 + 7] = pWait;
+            if (a.prof && lane == 0) a.prof[size_t(ti) * kPencilProfWords + 7] = pWait;
             __syncthreads();   // tile end
         }
     }

@@ -104,9 +104,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     Context& c = ctx();
     constexpr bool GS = PencilTraits<MODE>::GS;
     auto kernel = k_pencil<MODE, SKEW, NS>;
-    const int sideCols = std::max(1, cols) * (GS ? 2 : 1);
-    static const int maxWindow = getenv("B200LS_PENCIL_WINDOW") ? atoi(getenv("B200LS_PENCIL_WINDOW")) : 8;
-    a.window = std::max(1, std::min(maxWindow, (32 * kPencilMaxE) / sideCols));
+    if (cols * (GS ? 2 : 1) > 32 * kPencilCPL) throw CudaError("pencil sweep: too many neighbour columns for the helper warp");
     const size_t smem = size_t(pencilSmemBytes<MODE, NS>(a.extW, a.dotOut != nullptr));
     // per instantiation: the dynamic shared-memory limit only ever grows; occupancy per size
     static size_t smemLimit = 0;
@@ -136,8 +134,8 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     static const char* profFile = getenv("B200LS_PENCIL_PROF");
     static DevBuf<unsigned long long> profBuf;
     if (profFile) {
-        profBuf.alloc(size_t(a.nTiles) * 16);
-        B2_CUDA(cudaMemsetAsync(profBuf.p, 0, size_t(a.nTiles) * 128, c.stream));
+        profBuf.alloc(size_t(a.nTiles) * kPencilProfWords);
+        B2_CUDA(cudaMemsetAsync(profBuf.p, 0, size_t(a.nTiles) * kPencilProfWords * 8, c.stream));
         a.prof = profBuf.p;
     }
     void* args[] = {&a};
@@ -148,13 +146,13 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
                         " B shared memory, occupancy " + std::to_string(occ) + "/SM)");
     c.launches++;
     if (profFile) {
-        std::vector<unsigned long long> h(size_t(a.nTiles) * 16);
+        std::vector<unsigned long long> h(size_t(a.nTiles) * kPencilProfWords);
         B2_CUDA(cudaMemcpyAsync(h.data(), profBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
         B2_CUDA(cudaStreamSynchronize(c.stream));
         if (FILE* f = fopen(profFile, "a")) {
-            fprintf(f, "# mode %d skew %d stages %d tiles %d ctas %d window %d\n", MODE, SKEW, NS, a.nTiles, blocks, a.window);
+            fprintf(f, "# mode %d skew %d stages %d tiles %d ctas %d\n", MODE, SKEW, NS, a.nTiles, blocks);
             for (int t = 0; t < a.nTiles; t++) {
-                for (int q = 0; q < 16; q++) fprintf(f, "%llu ", h[size_t(t) * 16 + q]);
+                for (int q = 0; q < kPencilProfWords; q++) fprintf(f, "%llu ", h[size_t(t) * kPencilProfWords + q]);
                 fprintf(f, "\n");
             }
             fclose(f);
@@ -429,13 +427,31 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     Context& c = ctx();
-    if (M.p2pReady || !c.p2p.enabled || !D.anyProcIface) return;
+    // Every rank calls this once per (matrix, level) -- also ranks without a processor patch on the level -- and the
+    // decisions below are taken COLLECTIVELY: p2p.enabled is all-or-none by construction (setupP2P), the environment
+    // switch is process-wide, and anything rank-local goes through an all-reduce before any rank leaves.
+    if (M.p2pTried || !c.p2p.enabled) return;
+    M.p2pTried = true;
     static const bool off = getenv("B200LS_NO_P2P_HALO") != nullptr;
     if (off) return;
     auto isProc = [&](int i) { return D.ifacePartner[i] < 0; };   // cyclic halves never leave this GPU
+    auto anyRankSays = [&](bool mine) {   // global OR
+        DevBuf<double> flag;
+        flag.alloc(1);
+        const double v = mine ? 1.0 : 0.0;
+        B2_CUDA(cudaMemcpyAsync(flag.p, &v, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        if (c.nccl.AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, c.comm, c.stream) != 0)
+            throw CudaError("ncclAllReduce failed");
+        double sum = 0;
+        B2_CUDA(cudaMemcpyAsync(&sum, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+        return sum != 0.0;
+    };
+    bool duplicate = false;   // several patches to one neighbour (e.g. processor + processorCyclic): keep NCCL
     for (int i = 0; i < D.nIfaces; i++)
         for (int j = 0; j < i; j++)
-            if (isProc(i) && isProc(j) && D.ifaceNbr[i] == D.ifaceNbr[j]) return;   // several patches to one neighbour: keep NCCL
+            if (isProc(i) && isProc(j) && D.ifaceNbr[i] == D.ifaceNbr[j]) duplicate = true;
+    if (anyRankSays(duplicate)) return;
     std::vector<long long> mine(2 * D.nIfaces), theirs(2 * D.nIfaces, -1);
     M.p2pLocalRecv.assign(D.nIfaces, nullptr);
     M.p2pLocalFlag.assign(D.nIfaces, nullptr);
@@ -456,7 +472,7 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     // exchange the offsets pairwise (also tells the neighbour if we ran out of arena)
     DevBuf<long long> dMine, dTheirs;
     dMine.upload(mine, c.stream);
-    dTheirs.alloc(theirs.size());
+    dTheirs.alloc(std::max<size_t>(theirs.size(), 1));
     B2_CUDA(cudaStreamSynchronize(c.stream));
     c.nccl.GroupStart();
     for (int i = 0; i < D.nIfaces; i++) {
@@ -474,16 +490,7 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     }
     for (long long v : theirs) ok = ok && v >= 0;
     // every rank must take the same decision for a given interface pair; a global AND keeps it simple
-    DevBuf<double> flag;
-    flag.alloc(1);
-    const double mineOk = ok ? 0.0 : 1.0;
-    B2_CUDA(cudaMemcpyAsync(flag.p, &mineOk, sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    if (c.nccl.AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, c.comm, c.stream) != 0)
-        throw CudaError("ncclAllReduce failed");
-    double bad = 0;
-    B2_CUDA(cudaMemcpyAsync(&bad, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    B2_CUDA(cudaStreamSynchronize(c.stream));
-    if (bad != 0.0) return;
+    if (anyRankSays(!ok)) return;
     M.p2pRemoteRecv.resize(D.nIfaces);
     M.p2pRemoteFlag.resize(D.nIfaces);
     for (int i = 0; i < D.nIfaces; i++) {
@@ -501,8 +508,8 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
 static void setupIfaceViews(b200ls_matrix_s* m, int level) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
+    if (ctx().nRanks > 1) setupP2PHalos(m, level);   // collective: before any rank-local return
     if (D.nIfaces == 0) return;
-    if (ctx().nRanks > 1) setupP2PHalos(m, level);
     std::vector<IfaceView> v(D.nIfaces);
     for (int i = 0; i < D.nIfaces; i++) {
         M.sendBuf[i].alloc(D.ifaceSize[i]);
@@ -807,7 +814,11 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     const int n = D.nCells;
-    if (n == 0) return;
+    if (n == 0) {
+        // a rank without rows on this level still owns a term of the global sum
+        if (dotOut) B2_CUDA(cudaMemsetAsync(dotOut, 0, sizeof(double), S()));
+        return;
+    }
     if (precond == B200LS_NONE) {
         B2_CUDA(cudaMemcpyAsync(wA, rA, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
         return;

@@ -23,6 +23,7 @@ struct MatLevel {
     DevBuf<unsigned char> ifaceViews;   // IfaceView[nIfaces] on device
     // P2P halos: receive buffers/flags live in this rank's IPC arena, the neighbour's are mapped pointers
     bool p2pReady = false;
+    bool p2pTried = false;          // the (collective) P2P set-up of this level has run
     std::vector<double*> p2pRemoteRecv;                 // neighbour's receive buffer (2 parities)
     std::vector<unsigned long long*> p2pRemoteFlag;     // neighbour's epoch flag
     std::vector<double*> p2pLocalRecv;

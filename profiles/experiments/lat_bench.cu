@@ -15,6 +15,7 @@ __global__ void k(double* out, long long* cyc, int n, double seed) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(smem_u32(bar) + 8));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar) + 16));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar) + 24));
     }
     __syncthreads();
     if (threadIdx.x >= 32) return;
@@ -87,6 +88,46 @@ __global__ void k(double* out, long long* cyc, int n, double seed) {
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + 16) : "memory");
             }
         }
+        if (WHICH >= 16 && WHICH <= 19) {
+            // the chain warp's step as written in pencil.cuh: barrier tests (completed phases), record + neighbour loads
+            // one step ahead, shuffles, arithmetic, result store, warp sync, two single-lane arrives
+            unsigned ok1 = 1, ok2 = 1;
+            if (WHICH != 18) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok1) : "r"(smem_u32(bar)), "r"(1u) : "memory");
+                if (!ok1) x += 1.0;
+            }
+            double2 v0, v1;
+            const unsigned ra = smem_u32(sm) + lane * 48 + (i & 3) * 1536;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0.x), "=d"(v0.y) : "r"(ra));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v1.x), "=d"(v1.y) : "r"(ra + 16));
+            if (WHICH != 18) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok2) : "r"(smem_u32(bar)), "r"(1u) : "memory");
+                if (!ok2) x += 1.0;
+            }
+            double e0, e1;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(e0) : "r"(smem_u32(sm) + 7000 + (lane & 7) * 8));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(e1) : "r"(smem_u32(sm) + 7104 + (lane >> 3) * 8));
+            const double sJ = __shfl_sync(0xffffffffu, x, (lane + 31) & 31);
+            const double sK = __shfl_sync(0xffffffffu, x, (lane + 24) & 31);
+            const double vJ = (lane & 7) ? sJ : e0, vK = (lane >> 3) ? sK : e1;
+            double acc = v0.x;
+            acc -= v0.y * vK;
+            acc -= v1.x * vJ;
+            acc -= v1.y * x;
+            x = acc * 1e-30 + 1.0;
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(smem_u32(sm) + 6400 + lane * 8), "d"(x) : "memory");
+            if (WHICH != 19) {
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + 16) : "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + 24) : "memory");
+                }
+            }
+            if (WHICH == 17) {   // + another warp hammering shared memory is started by the host (block of 160 threads)
+            }
+        }
         if (WHICH == 10) {                                           // vote + dependent branch
             if (__any_sync(0xffffffffu, x == 12345.0)) x += 1.0;
             x = x - c2;
@@ -130,6 +171,9 @@ int main() {
     run<13>("chain step + 3 LDS.128 + STS", out, cyc);
     run<14>("chain step + 3 LDS.128 + STS + arrive x32", out, cyc);
     run<15>("chain step + 3 LDS.128 + STS + syncwarp + arrive x1", out, cyc);
+    run<16>("pencil chain step as written (2 tests, 2 LDS.128, 2 LDS.64, 2 arrives)", out, cyc);
+    run<18>("  ... without the two barrier tests", out, cyc);
+    run<19>("  ... without syncwarp + arrives", out, cyc);
     int clk = 0;
     cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("clock rate attribute %d kHz\n", clk);
