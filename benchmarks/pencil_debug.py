@@ -56,6 +56,23 @@ B = bad.reshape(nz, ny, nx)
 G = got.reshape(nz, ny, nx)
 for K in range(nK):
     print("K", K, " ".join(f"{int(B[K * WK:(K + 1) * WK, J * WJ:(J + 1) * WJ, :].sum()):6d}" for J in range(nJ)))
+# the first tile in forward (wavefront) order that has a bad cell, and its earliest bad cells
+best = None
+for K in range(nK):
+    for J in range(nJ):
+        blk = B[K * WK:(K + 1) * WK, J * WJ:(J + 1) * WJ, :]
+        if blk.any() and (best is None or J + K < best[0]):
+            best = (J + K, J, K)
+if best:
+    _, J, K = best
+    blk = B[K * WK:(K + 1) * WK, J * WJ:(J + 1) * WJ, :]
+    kk, jj, ii = np.nonzero(blk)
+    order = np.argsort(ii + jj + kk)
+    print("first bad tile in forward order: J", J, "K", K, "bad", int(blk.sum()))
+    W3 = want.reshape(nz, ny, nx)
+    for t in order[:10]:
+        k, j, i = kk[t] + K * WK, jj[t] + J * WJ, ii[t]
+        print(f"   step {ii[t] + jj[t] + kk[t]:3d} i {ii[t]} jj {jj[t]} kk {kk[t]}: got {G[k, j, i]!r} want {W3[k, j, i]!r}")
 # the last tile in forward order that has a bad cell = the first one in reverse order
 for K in reversed(range(nK)):
     for J in reversed(range(nJ)):

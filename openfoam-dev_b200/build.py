@@ -31,7 +31,8 @@ def build_lib(force=False, verbose=False):
                   list(CSRC.glob("*.hpp")) + [ROOT / "include" / "b200ls.h"])
     if not force and _newer(LIB, srcs):
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("B200LS_EXTRA_NVCC_FLAGS", "").split()   # debugging builds (e.g. -DB200LS_PENCIL_FASTFAIL)
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         str(CSRC / "lib.cu"), str(CSRC / "mesh.cpp"), "-o", str(LIB), "-ldl",
     ]
     r = subprocess.run(cmd, capture_output=True, text=True)

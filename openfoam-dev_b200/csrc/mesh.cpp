@@ -45,7 +45,7 @@ void makeTasks(const std::vector<int32_t>& offsets, std::vector<SweepTask>& task
 }  // namespace
 
 void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
-                std::vector<HostInterface> interfaces) {
+                std::vector<HostInterface> interfaces, bool allowPencil) {
     if (nCells < 0 || nFaces < 0) throw std::runtime_error("negative mesh size");
     L.nCells = nCells;
     L.nFaces = nFaces;
@@ -109,7 +109,7 @@ void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* low
         const char* on = getenv("B200LS_PENCIL");
         const char* mc = getenv("B200LS_PENCIL_MIN_CELLS");
         const int32_t minCells = mc ? int32_t(atoi(mc)) : 16384;
-        if (!(on && on[0] == '0') && nCells >= minCells) buildPencilPlan(L, L.pencil);
+        if (allowPencil && !(on && on[0] == '0') && nCells >= minCells) buildPencilPlan(L, L.pencil);
     }
     if (L.pencil.valid) {
         const PencilPlan& P = L.pencil;
@@ -622,11 +622,25 @@ static void appendCoarseLevel(HostMesh& mesh, std::vector<int32_t> map, int32_t 
     buildMaps(fine, coarse);
 }
 
+// A mesh that gets a GAMG hierarchy keeps every level, the finest included, in the wavefront-major layout (the pencil
+// layout only pays for the Krylov solvers' DIC/DILU sweeps; B200LS_PENCIL_GAMG=1 keeps it).
+static void finestLevelForGamg(HostMesh& mesh) {
+    LevelHost& L0 = mesh.levels[0];
+    const char* keep = getenv("B200LS_PENCIL_GAMG");
+    if (!L0.pencil.valid || (keep && keep[0] == '1')) return;
+    const std::vector<int32_t> lower = L0.lower, upper = L0.upper;
+    std::vector<HostInterface> ifaces = L0.interfaces;
+    LevelHost fresh;
+    buildLevel(fresh, L0.nCells, L0.nFaces, lower.data(), upper.data(), std::move(ifaces), false);
+    L0 = std::move(fresh);
+}
+
 int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerProcessor, int32_t mergeLevels,
                 bool& forward, const HostComm* comm) {
     if (mesh.nRanks > 1 && (!comm || !comm->sum)) throw std::runtime_error("multi-rank agglomeration needs a communicator");
     if (mergeLevels != 1) throw std::runtime_error("mergeLevels != 1 is not supported");
     mesh.levels.resize(1);
+    finestLevelForGamg(mesh);
     mesh.levels[0].hasCoarse = false;
     mesh.agglomerated = false;
 
@@ -662,6 +676,7 @@ int agglomerate(HostMesh& mesh, const double* faceWeights, int32_t minCellsPerPr
 int agglomerateFromMaps(HostMesh& mesh, int32_t nCoarseLevels, const int32_t* const* restrictAddr,
                         const int32_t* nCoarseCells, const HostComm* comm) {
     mesh.levels.resize(1);
+    finestLevelForGamg(mesh);
     mesh.levels[0].hasCoarse = false;
     mesh.agglomerated = false;
     for (int32_t k = 0; k < nCoarseLevels; k++) {

@@ -116,8 +116,10 @@ struct HostMesh {
 };
 
 // Throws std::runtime_error on invalid input (not upper-triangular ordered, out-of-range labels).
+// allowPencil = false keeps the wavefront-major layout even on a structured block (levels of a GAMG hierarchy: their
+// fused multi-sweep Gauss-Seidel kernel works on wavefront-major rows).
 void buildLevel(LevelHost& L, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper,
-                std::vector<HostInterface> interfaces);
+                std::vector<HostInterface> interfaces, bool allowPencil = true);
 
 // Detects an nx*ny*nz hex block numbered i-fastest with faces in upper-triangular order (blockMesh single block)
 // and chooses the pencil tiling; plan.valid stays false otherwise.  Called by buildLevel (B200LS_PENCIL=0 disables,

@@ -86,18 +86,26 @@ def test_wavefront_kernels_on_the_tile_major_layout(shape, sym, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(12, 10, 9), (40, 33, 17), (70, 70, 1)])
 @pytest.mark.parametrize("sym", [True, False])
-def test_pencil_solvers_match_oracle(shape, sym, monkeypatch):
+@pytest.mark.parametrize("gamg_keeps_pencil", [False, True])
+def test_pencil_solvers_match_oracle(shape, sym, gamg_keeps_pencil, monkeypatch):
+    """Krylov solve on the pencil layout; then the mesh is agglomerated -- which puts the finest level back into the
+    wavefront-major layout unless B200LS_PENCIL_GAMG=1 -- and GAMG / smoothSolver run on it."""
     monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
+    if gamg_keeps_pencil:
+        monkeypatch.setenv("B200LS_PENCIL_GAMG", "1")
     s = _system(shape, sym)
     mesh, mat = capi.from_system(s)
-    mesh.agglomerate(s.face_weights)
-    mat.set(s.diag, s.upper_coeffs, s.lower_coeffs)
     S = orc.System(s)
     kind = "DIC" if sym else "DILU"
     runs = [("PCG" if sym else "PBiCGStab", dict(preconditioner=kind), kind),
             ("GAMG", dict(smoother="GaussSeidel"), "GaussSeidel"),
             ("smoothSolver", dict(smoother="symGaussSeidel", nSweeps=2), "symGaussSeidel")]
     for solver, kw, okind in runs:
+        if solver == "GAMG":
+            assert mesh.get_i32(21, 0).size == 7
+            mesh.agglomerate(s.face_weights)
+            assert (mesh.get_i32(21, 0).size == 7) == gamg_keeps_pencil
+            mat.set(s.diag, s.upper_coeffs, s.lower_coeffs)
         ctl = capi.controls(solver, tolerance=1e-9, relTol=0.0, maxIter=60, recordHistory=1, **kw)
         psi, perf = mat.solve(ctl, s.source)
         okw = dict(tolerance=1e-9, maxIter=60)
