@@ -12,7 +12,14 @@ mode of SURVEY.md 8(d)) on the synthetic lid-driven-cavity p-equation of the nam
 metric  = cell-iterations/s = nCells_total * iterations / time.
 value   : matrix, psi and source resident in HBM when the timed region starts (b200ls_solve_dev).
 e2e     : the same solve through the host-pointer C-ABI calls a plugin makes (b200ls_matrix_set + b200ls_solve):
-          coefficient/psi/source H2D and psi D2H inside the timed region, from pinned host memory.
+          coefficient/psi/source H2D and psi D2H inside the timed region, from PAGEABLE host memory (what OpenFOAM's
+          scalarFields are).
+parity  : before anything is timed, a reference-generated golden (tests/golden, produced by the unmodified reference
+          through oracle/ref_harness) is solved on the same ranks: one GPU -> block_16x16x16_rand, N GPUs ->
+          decompN_sym (the reference's decomposed algorithm); the JSON line carries the comparison.
+extras  : sub-records for the other BASELINE configurations -- configs[2] (256^3 GAMG + GaussSeidel, one GPU) and
+          configs[3] (384^3 decomposed `simple` into N, PCG+DIC and GAMG; N = 1 is the undecomposed strong-scaling
+          denominator).  B200LS_BENCH_EXTRAS=0 skips them.
 """
 import argparse
 import json
@@ -177,6 +184,82 @@ def run_oracle_port_sample(sys_, iters):
     return sys_.n_cells * perf["nIterations"] / secs, secs, perf["nIterations"]
 
 
+def parity_check(capi, rank, world):
+    """Solve a reference-generated golden on these ranks before timing.  Returns the `parity` object of the JSON line
+    (rank 0's view; every rank takes part)."""
+    import torch
+    import torch.distributed as dist
+    from b200ls import cases, decompose
+    from _util import GOLDEN, controls_from_dict, load_fixture, solve_keys, system_from_entries
+
+    name = "block_16x16x16_rand" if world == 1 else f"decomp{world}_sym"
+    if not (GOLDEN / f"{name}.b2ls").exists():
+        return {"checked": False, "reason": f"no golden {name}"}
+    inp, ref = load_fixture(name)
+    if world == 1:
+        part = system_from_entries(inp)
+        lo, hi = 0, part.n_cells
+    else:
+        split = decompose.simple_split(world)
+        nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
+        glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random")
+        parts, _ = decompose.decompose_system(glob, decompose.box_cell_ranks(nx, ny, nz, split), world)
+        blk, offs = decompose.as_cyclic_blocks(parts)
+        if not (np.array_equal(blk.diag, inp["diag"]) and np.array_equal(blk.upper_coeffs, inp["upperCoeffs"])):
+            return {"checked": False, "reason": "golden does not match the generated decomposition"}
+        part = parts[rank]
+        lo, hi = int(offs[rank]), int(offs[rank + 1])
+    mesh, mat = capi.from_system(part)
+    if any("GAMG" in t for _, t in solve_keys(inp)):
+        mesh.agglomerate(part.face_weights)
+    mat.set(part.diag, part.upper_coeffs, part.lower_coeffs, [i.bou_coeffs for i in part.interfaces],
+            [i.int_coeffs for i in part.interfaces])
+    its_equal, worst_psi, worst_res, n = True, 0.0, 0.0, 0
+    for i, text in solve_keys(inp):
+        if "PBiCGStab" in text or "smoothSolver" in text or "none" in text or "diagonal" in text:
+            continue      # PCG+DIC and GAMG: the solvers this benchmark times
+        ctl = controls_from_dict(text, recordHistory=1)
+        psi, perf = mat.solve(ctl, part.source, inp.get("psi0"))
+        rperf = ref[f"solve.{i}.perf"]
+        n += 1
+        its_equal &= perf.nIterations == int(rperf[2])
+        worst_res = max(worst_res, abs(perf.finalResidual - rperf[1]) / abs(rperf[0]),
+                        abs(perf.initialResidual - rperf[0]) / abs(rperf[0]))
+        if perf.nIterations == int(rperf[2]):
+            rpsi = ref[f"solve.{i}.psi"][lo:hi]
+            worst_psi = max(worst_psi, float(np.max(np.abs(psi - rpsi)) / max(np.max(np.abs(rpsi)), 1e-300)))
+    if world > 1:
+        t = torch.tensor([worst_psi, worst_res, 0.0 if its_equal else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst_psi, worst_res, its_equal = float(t[0]), float(t[1]), float(t[2]) == 0.0
+    mat.close()
+    mesh.close()
+    return {"checked": True, "golden": f"tests/golden/{name}.b2ls (unmodified reference via oracle/ref_harness)",
+            "solver_runs": n, "iterations_equal": bool(its_equal), "max_rel_diff": worst_psi,
+            "max_residual_diff": worst_res, "ok": bool(its_equal and worst_psi <= 1e-9 and worst_res <= 1e-9)}
+
+
+def vcycle_bytes(sizes):
+    """Algorithmic bytes of one GAMG V-cycle with the default controls, symmetric matrix, from the
+    (nCells, nFaces) of every level, finest first."""
+    b_amul = lambda c, f: 24.0 * c + 16.0 * f      # noqa: E731
+    b_gs = lambda c, f: 60.0 * c + 12.0 * f        # noqa: E731
+    total = 0.0
+    n_coarse = len(sizes) - 1
+    for l in range(1, n_coarse + 1):               # coarse level l = reference matrixLevels_[l-1]
+        c, f = sizes[l]
+        cf = sizes[l - 1][0]
+        total += 2 * (12.0 * cf + 8.0 * c)         # restrict + prolong across (l-1, l)
+        if l < n_coarse:                            # the coarsest level is solved, not smoothed
+            total += min(2 + (l - 1), 4) * b_gs(c, f)
+            if l - 1 < n_coarse - 2:
+                total += b_amul(c, f) + 64.0 * c    # scale
+    c0, f0 = sizes[0]
+    total += (b_amul(c0, f0) + 64.0 * c0) + 24.0 * c0 + 2 * b_gs(c0, f0)   # finest: scale, psi += corr, 2 sweeps
+    total += b_amul(c0, f0) + 32.0 * c0                                     # closing residual
+    return total
+
+
 def bench_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the same global workload as our arm
     (the undecomposed (128*px)x(128*py)x(128*pz) cavity matrix; iterations per step bounded to ceil(50/N) so the run
@@ -243,6 +326,111 @@ def bench_reference(args):
     print(json.dumps(line))
 
 
+def bench_extras(capi, cases, decompose, rank, world, barrier):
+    """Sub-records for the other BASELINE configurations (every rank takes part; rank 0 reports).
+    configs[2]: 256^3 GAMG + GaussSeidel on one GPU (N = 1 only).
+    configs[3]: 384^3 decomposed `simple` into N subdomains: PCG+DIC (20 fixed iterations) and GAMG (3 fixed cycles);
+                N = 1 is the undecomposed matrix on one GPU -- the denominator of the strong-scaling efficiency, kept
+                in /tmp between the back-to-back runs of a scaling sweep."""
+    import torch
+    import torch.distributed as dist
+
+    peak, _ = load_peaks()
+    out = {}
+
+    def timed_solve(mat, ctl, source, reps):
+        d_src = torch.from_numpy(source).cuda()
+        d_psi = torch.zeros(source.size, dtype=torch.float64, device="cuda")
+        best, perf = None, None
+        for r in range(reps + 1):                     # first call: warm-up (factorisation, coarse matrices, plans)
+            d_psi.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            perf = mat.solve_dev(ctl, d_psi.data_ptr(), d_src.data_ptr())
+            barrier()
+            dt = time.perf_counter() - t0
+            if r > 0:
+                best = dt if best is None else min(best, dt)
+        t = torch.tensor([best], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), perf
+
+    def level_sizes(mesh):
+        return [tuple(int(v) for v in mesh.get_i32(12, k)) for k in range(mesh.n_levels())]
+
+    def gamg_record(sys_, n_total, n_cycles, label):
+        mesh, mat = capi.from_system(sys_)
+        t0 = time.perf_counter()
+        mesh.agglomerate(sys_.face_weights)
+        t_agg = time.perf_counter() - t0
+        mat.set(sys_.diag, sys_.upper_coeffs, None, [i.bou_coeffs for i in sys_.interfaces],
+                [i.int_coeffs for i in sys_.interfaces])
+        ctl = capi.controls("GAMG", smoother="GaussSeidel", tolerance=0.0, relTol=0.0, maxIter=n_cycles)
+        secs, perf = timed_solve(mat, ctl, sys_.source, 2)
+        sizes = level_sizes(mesh)
+        rec = {"workload": label, "n_cells": n_total, "cycles": int(perf.nIterations),
+               "ms_per_cycle": 1e3 * secs / max(1, perf.nIterations), "final_residual": perf.finalResidual,
+               "levels": len(sizes), "host_agglomeration_s": t_agg,
+               "kernel_launches_per_cycle": perf.kernelLaunches / max(1, perf.nIterations)}
+        if world == 1:
+            b = vcycle_bytes(sizes)
+            rec.update({"vcycle_algorithmic_bytes": b,
+                        "roofline_frac": b / (secs / max(1, perf.nIterations)) / 1e9 / peak})
+        mat.close()
+        mesh.close()
+        return rec
+
+    if world == 1:
+        s256 = cases.cavity_laplacian(256, 256, 256)
+        out["gamg_256"] = gamg_record(s256, s256.n_cells, 3,
+                                      "cavity 256^3 p-equation (BASELINE configs[2]), GAMG + GaussSeidel, 3 V-cycles")
+        del s256
+
+    # configs[3]: 384^3, strong scaling
+    n = 384
+    if world == 1:
+        part = cases.cavity_laplacian(n, n, n)
+        split = (1, 1, 1)
+    else:
+        split = decompose.simple_split(world)
+        part = decompose.cavity_subdomain(n, n, n, split, rank)
+    n_total = n ** 3
+    mesh, mat = capi.from_system(part)
+    mat.set(part.diag, part.upper_coeffs, None, [i.bou_coeffs for i in part.interfaces],
+            [i.int_coeffs for i in part.interfaces])
+    ctl = capi.controls("PCG", "DIC", tolerance=0.0, relTol=0.0, maxIter=20)
+    secs, perf = timed_solve(mat, ctl, part.source, 2)
+    mat.close()
+    mesh.close()
+    strong = {"workload": f"cavity 384^3 p-equation (BASELINE configs[3]) decomposed simple {split}, one subdomain per GPU",
+              "n_cells": n_total,
+              "pcg_dic": {"iterations": int(perf.nIterations), "ms_per_iteration": 1e3 * secs / max(1, perf.nIterations),
+                          "cell_iterations_per_s": n_total * perf.nIterations / secs}}
+    strong["gamg_gauss_seidel"] = gamg_record(part, n_total, 3, "384^3, GAMG + GaussSeidel, 3 V-cycles")
+    ref_file = Path(tempfile.gettempdir()) / "b200ls_bench_strong384_n1.json"
+    if rank == 0:
+        if world == 1:
+            try:
+                ref_file.write_text(json.dumps(strong))
+            except OSError:
+                pass
+        elif ref_file.exists():
+            try:
+                one = json.loads(ref_file.read_text())
+                strong["pcg_dic"]["efficiency_vs_1gpu"] = one["pcg_dic"]["ms_per_iteration"] / (
+                    world * strong["pcg_dic"]["ms_per_iteration"])
+                strong["gamg_gauss_seidel"]["efficiency_vs_1gpu"] = one["gamg_gauss_seidel"]["ms_per_cycle"] / (
+                    world * strong["gamg_gauss_seidel"]["ms_per_cycle"])
+                strong["one_gpu"] = {"pcg_ms_per_iteration": one["pcg_dic"]["ms_per_iteration"],
+                                     "gamg_ms_per_cycle": one["gamg_gauss_seidel"]["ms_per_cycle"],
+                                     "source": "the N = 1 run of this bench on the same box (kept in /tmp)"}
+            except Exception:
+                pass
+    out["strong_384"] = strong
+    return out
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -269,6 +457,8 @@ def bench_ours(args):
         uid = bytes(buf.cpu().numpy().tobytes())
     capi.init(local_rank, uid, rank, world)
 
+    parity = parity_check(capi, rank, world)
+
     # workload: this rank's subdomain
     if world == 1:
         sys_ = cases.cavity_laplacian(N_SIDE, N_SIDE, N_SIDE)
@@ -283,17 +473,14 @@ def bench_ours(args):
     n_faces = sys_.n_faces
 
     mesh, mat = capi.from_system(sys_)
+    pencil = mesh.get_i32(21, 0).size == 7      # structured block: tile-major layout + pencil sweeps
     ctl = capi.controls("PCG", "DIC", tolerance=0.0, relTol=0.0, maxIter=ITERS)
 
-    # pinned host copies (e2e) and device-resident inputs (value)
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t, t.numpy()
-
-    _, h_diag = pinned(sys_.diag)
-    _, h_upper = pinned(sys_.upper_coeffs)
-    _, h_source = pinned(sys_.source)
-    t_psi, h_psi = pinned(np.zeros(n_local))
+    # pageable host copies (e2e: what a plugin receives from OpenFOAM) and device-resident inputs (value)
+    h_diag = np.ascontiguousarray(sys_.diag)
+    h_upper = np.ascontiguousarray(sys_.upper_coeffs)
+    h_source = np.ascontiguousarray(sys_.source)
+    h_psi = np.zeros(n_local)
     bou = [i.bou_coeffs for i in sys_.interfaces]
     inn = [i.int_coeffs for i in sys_.interfaces]
     d_source = torch.from_numpy(sys_.source).cuda()
@@ -352,6 +539,12 @@ def bench_ours(args):
     t_pre_ms = mat.time_kernel(1, 20)      # one DIC precondition = k_sweep_fwd + k_sweep_bwd
     t_amul_ms = mat.time_kernel(0, 50)
 
+    mat.close()
+    mesh.close()
+    extras = None
+    if os.environ.get("B200LS_BENCH_EXTRAS", "1") != "0":
+        extras = bench_extras(capi, cases, decompose, rank, world, barrier)
+
     times = torch.tensor([wall, wall_e2e, dev_ms / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -366,10 +559,18 @@ def bench_ours(args):
         b_pre = 72.0 * n_local + 32.0 * n_faces
         b_amul = 24.0 * n_local + 16.0 * n_faces
         ach = b_pre / (t_pre_ms * 1e-3) / 1e9
-        # DRAM bytes of one fwd+bwd pair from the ncu --set full capture of this workload
-        # (profiles/r01_ncu_full_pcg128_top_kernels.txt: 151.1 MB + 178.2 MB); only valid for the 128^3 subdomain
-        traffic = 329.3e6 if n_local == N_SIDE ** 3 else None
-        roofline = {"bound": "hbm", "kernel": "DIC precondition = k_sweep_fwd + k_sweep_bwd (wavefront sweeps)",
+        # DRAM bytes of one fwd+bwd pair: read from the committed summary of the ncu --set full capture of this
+        # workload (profiles/dram_traffic.json, written by profiles/summarize.py); only valid for the 128^3 subdomain
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "dram_traffic.json").read_text())
+            if n_local == N_SIDE ** 3:
+                traffic = float(tr["dic_precondition_128"]["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
+        roofline = {"bound": "hbm",
+                    "kernel": ("DIC precondition = k_pencil<FWD> + k_pencil<BWD> (structured block: pencil tiles)"
+                               if pencil else "DIC precondition = k_sweep_fwd + k_sweep_bwd (wavefront sweeps)"),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "bytes_per_launch": b_pre, "ms_per_launch": t_pre_ms}
         spmv = {"kernel": "k_spmv (lduMatrix::Amul)", "achieved": b_amul / (t_amul_ms * 1e-3) / 1e9, "peak": peak,
@@ -407,6 +608,7 @@ def bench_ours(args):
                     "ms_per_step": 1e3 * wall_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "spmv": spmv, "cpu_baseline": cpu, "clocks": clocks,
+            "parity": parity, "extras": extras,
         }
         print(json.dumps(line))
     if world > 1:

@@ -217,6 +217,38 @@ def random_graph(n_cells, avg_degree=5, symmetric=True, seed=20261017, max_span=
                      source=rng.uniform(-1.0, 1.0, n_cells), face_weights=0.5 + rng.random(nf))
 
 
+def renumbered(sys_: LduSystem, seed=20261017, window=None):
+    """The same matrix under a random renumbering of the cells (within windows of `window` consecutive labels, or
+    globally): an unstructured LDU system -- faces re-oriented so that lower < upper and re-sorted into
+    upper-triangular order, coefficients following their faces (a flipped face swaps upper and lower coefficient).
+    Used for parity tests at sizes no shipped mesh reaches."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = sys_.n_cells
+    if window is None:
+        perm = rng.permutation(n)
+    else:
+        perm = np.arange(n)
+        for a in range(0, n, window):
+            b = min(n, a + window)
+            perm[a:b] = a + rng.permutation(b - a)
+    new_of = np.empty(n, dtype=np.int64)
+    new_of[perm] = np.arange(n)                     # old cell perm[i] gets label i
+    lo, up = new_of[sys_.lower], new_of[sys_.upper]
+    flip = lo > up
+    l2, u2 = np.where(flip, up, lo), np.where(flip, lo, up)
+    lower_c = sys_.upper_coeffs if sys_.lower_coeffs is None else sys_.lower_coeffs
+    cu = np.where(flip, lower_c, sys_.upper_coeffs)
+    cl = np.where(flip, sys_.upper_coeffs, lower_c)
+    order = np.lexsort((u2, l2))
+    out = LduSystem(
+        n_cells=n, lower=l2[order].astype(np.int32), upper=u2[order].astype(np.int32), diag=sys_.diag[perm].copy(),
+        upper_coeffs=cu[order].copy(), lower_coeffs=None if sys_.lower_coeffs is None else cl[order].copy(),
+        source=None if sys_.source is None else sys_.source[perm].copy(),
+        face_weights=None if sys_.face_weights is None else sys_.face_weights[order].copy(),
+    )
+    return out
+
+
 def to_entries(sys_: LduSystem):
     """B2LS entries understood by oracle/ref_harness.C and the C oracle."""
     e = {

@@ -198,7 +198,9 @@ def main():
     # decomposed runs, executed by the SERIAL reference as block-diagonal systems with cyclic pairs in place of the
     # processor patches; nCellsInCoarsestLevel = 10*nRanks reproduces the decomposed stop criterion
     for kind, n_ranks, solves, sm in (("sym", 2, SYM_SOLVES, sym_sm), ("asym", 2, ASYM_SOLVES, asym_sm),
-                                      ("sym", 4, SYM_SOLVES, sym_sm), ("asym", 4, ASYM_SOLVES, asym_sm)):
+                                      ("sym", 4, SYM_SOLVES, sym_sm), ("asym", 4, ASYM_SOLVES, asym_sm),
+                                      # eight ranks (2 2 2): the Krylov / GAMG runs bench.py --gpus 8 checks before timing
+                                      ("sym", 8, SYM_SOLVES[:2] + SYM_SOLVES[5:6], sym_sm[:1])):
         blk, offs = decomposed_case(kind, n_ranks)
         fixture(f"decomp{n_ranks}_{kind}", blk, with_coarsest(solves, 10 * n_ranks), sm,
                 agglom_dict=f"solver GAMG; nCellsInCoarsestLevel {10 * n_ranks};",
