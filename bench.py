@@ -366,7 +366,10 @@ def bench_extras(capi, cases, decompose, rank, world, barrier):
         t_agg = time.perf_counter() - t0
         mat.set(sys_.diag, sys_.upper_coeffs, None, [i.bou_coeffs for i in sys_.interfaces],
                 [i.int_coeffs for i in sys_.interfaces])
-        ctl = capi.controls("GAMG", smoother="GaussSeidel", tolerance=0.0, relTol=0.0, maxIter=n_cycles)
+        # the tutorials' p controls (tolerance 1e-6, relTol 0.01: inherited by the coarsest-level solver,
+        # GAMGSolverSolve.C:538-545); minIter = maxIter pins the number of V-cycles
+        ctl = capi.controls("GAMG", smoother="GaussSeidel", tolerance=1e-6, relTol=0.01, minIter=n_cycles,
+                            maxIter=n_cycles)
         secs, perf = timed_solve(mat, ctl, sys_.source, 2)
         sizes = level_sizes(mesh)
         # the solve loop on the device (CUDA events inside the library); the per-solve set-up (coarse matrices,

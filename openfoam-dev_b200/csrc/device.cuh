@@ -7,6 +7,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <array>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -132,6 +133,21 @@ struct PencilTileDev {
 };
 
 // Addressing of one level in HBM (built once per mesh)
+// Coarsest GAMG level with coupled patches (several ranks and/or cyclic halves): the blocks of all ranks concatenated
+// in rank order, so that one single-thread kernel per rank can replay the reference's distributed PCG/PBiCGStab without
+// a launch or a collective per operation (solver.cu: ensureCoarsestGather / solveCoarsest).
+struct CoarsestGather {
+    bool tried = false, ok = false;
+    int nCells = 0, nFaces = 0, nCouple = 0;        // totals over ranks
+    int maxCells = 0, maxFaces = 0, maxCouple = 0;  // per-rank maxima: padded block sizes of the all-gathers
+    int blockLen = 0;                               // maxCells + 2*maxFaces + maxCouple doubles per rank
+    int myCouple = 0;
+    std::vector<int> ifaceCoupleOff;                // start of every local interface inside this rank's coupling block
+    DevBuf<int> lower, upper;                       // global cell numbers (block offset added), face blocks in rank order
+    DevBuf<int> cRow, cCol;                         // couplings in (rank, patch, face) order: Apsi[cRow] -= coef*psi[cCol]
+    DevBuf<int> cellOff, faceOff, coupleOff;        // [nRanks+1]
+};
+
 struct DevLevel {
     int nCells = 0, nFaces = 0;
     DevBuf<int> perm, ipos;
@@ -169,6 +185,9 @@ struct DevLevel {
     std::vector<DevBuf<int>> aiPtr, aiSrc;
     // coarsest-level direct data (reference order) for the single-thread coarsest solve
     DevBuf<int> refLower, refUpper, Uidx, Lidx;
+    std::vector<int> hostRefLower, hostRefUpper;
+    std::vector<std::vector<int>> ifaceCellsRef;    // per interface: faceCells in reference cell numbering (host)
+    CoarsestGather gather;
 };
 
 struct DeviceMesh {

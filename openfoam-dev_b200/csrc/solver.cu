@@ -67,6 +67,51 @@ static inline int gridRows(int n) { return std::max(1, (n + 255) / 256); }
         ctx().launches++;                                 \
     } while (0)
 
+// Opt-in phase timer for the V-cycle (B200LS_VPROF=<file prefix>): events on the solver stream at phase boundaries,
+// summed per label when the solve ends.  Off: one branch per mark.
+struct PhaseProf {
+    bool on = false;
+    std::string prefix;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    PhaseProf() {
+        const char* e = getenv("B200LS_VPROF");
+        on = e && *e;
+        if (on) prefix = e;
+    }
+};
+static PhaseProf g_vprof;
+static inline void vmark(const char* phase, int level) {
+    if (!g_vprof.on) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, S());
+    char label[64];
+    snprintf(label, sizeof(label), "L%02d %s", level, phase);
+    g_vprof.marks.emplace_back(label, ev);
+}
+static void vprofDump(int nCycles) {
+    if (!g_vprof.on || g_vprof.marks.size() < 2) return;
+    cudaStreamSynchronize(S());
+    std::map<std::string, std::pair<double, int>> sum;
+    double total = 0;
+    for (size_t i = 0; i + 1 < g_vprof.marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_vprof.marks[i].second, g_vprof.marks[i + 1].second);
+        auto& e = sum[g_vprof.marks[i + 1].first];   // a mark closes the phase it names
+        e.first += ms;
+        e.second++;
+        total += ms;
+    }
+    FILE* f = fopen((g_vprof.prefix + ".rank" + std::to_string(ctx().rank)).c_str(), "a");
+    if (f) {
+        fprintf(f, "# V-cycle phases, %d cycles, %.3f ms in marked phases\n", nCycles, total);
+        for (auto& kv : sum) fprintf(f, "%-28s %9.4f ms  x%d\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        fclose(f);
+    }
+    for (auto& mk : g_vprof.marks) cudaEventDestroy(mk.second);
+    g_vprof.marks.clear();
+}
+
 static void checkLaunch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
@@ -330,6 +375,11 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         D.ifaceCellsPos[i].upload(pos, s);
         B2_CUDA(cudaStreamSynchronize(s));
     }
+    D.ifaceCellsRef.clear();
+    if (coarsest)
+        for (int i = 0; i < D.nIfaces; i++)
+            D.ifaceCellsRef.emplace_back(H.interfaces[i].faceCells.begin(), H.interfaces[i].faceCells.end());
+    D.gather = CoarsestGather();
     D.nBRows = int(H.bRowPos.size());
     D.bRowPos.upload(H.bRowPos, s);
     D.bRowPtr.upload(H.bRowPtr, s);
@@ -363,6 +413,8 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         D.refUpper.upload(H.upper, s);
         D.Uidx.upload(H.Uidx, s);
         D.Lidx.upload(H.Lidx, s);
+        D.hostRefLower.assign(H.lower.begin(), H.lower.end());
+        D.hostRefUpper.assign(H.upper.begin(), H.upper.end());
     }
     B2_CUDA(cudaStreamSynchronize(s));
 }
@@ -1153,6 +1205,7 @@ static void record(b200ls_perf* perf, const b200ls_controls& c, double r) {
 // preconditioner dispatch of the Krylov solvers: DIC/DILU/diagonal/none per level, or GAMG V-cycles (finest level)
 static void gamgPrecondition(b200ls_matrix_s* m, const b200ls_controls& c, double* wA, const double* rA);
 static void buildCoarseMatrices(b200ls_matrix_s* m);
+static void gatherCoarsestCoefs(b200ls_matrix_s* m);
 
 static void preparePrecond(b200ls_matrix_s* m, const b200ls_controls& c, int lv) {
     if (c.precond == B200LS_GAMG_PRECOND) {
@@ -1414,6 +1467,7 @@ static void buildCoarseMatrices(b200ls_matrix_s* m) {
         MC.corr.alloc(C.nCells);
         MC.src.alloc(C.nCells);
     }
+    gatherCoarsestCoefs(m);
     m->coarseValid = true;
 }
 
@@ -1429,7 +1483,31 @@ struct CoarsestArgs {
     double* work;           // 10*nCells + 2*nFaces doubles
     double tolerance, relTol;
     int maxIter;
+    // gathered mode: the level of every rank, concatenated in rank order (CoarsestGather).  lower/upper then hold global
+    // cell numbers for nFaces = all faces, nCells = all cells; coefficients and sources come as padded per-rank blocks.
+    int gathered, nRanks, myRank, nCouple;
+    int maxCells, maxFaces, blockLen;
+    const int *cellOff, *faceOff, *coupleOff, *cRow, *cCol;
+    const double *gCoef, *gSrc;
+    const double* cc;       // coupling coefficients (filled by the kernel from gCoef)
 };
+
+// sum over the cells in the order of the distributed reference: every rank's partial sum, then the ranks in order
+template <class F>
+__device__ static double c_sum(const CoarsestArgs& a, F term) {
+    if (!a.gathered) {
+        double s = 0.0;
+        for (int c = 0; c < a.nCells; c++) s += term(c);
+        return s;
+    }
+    double total = 0.0;
+    for (int r = 0; r < a.nRanks; r++) {
+        double s = 0.0;
+        for (int c = a.cellOff[r]; c < a.cellOff[r + 1]; c++) s += term(c);
+        total = r == 0 ? s : total + s;
+    }
+    return total;
+}
 
 __device__ static void c_amul(const CoarsestArgs& a, const double* up, const double* lo, const double* dg,
                               double* out, const double* x) {
@@ -1438,6 +1516,9 @@ __device__ static void c_amul(const CoarsestArgs& a, const double* up, const dou
         out[a.upper[f]] += lo[f] * x[a.lower[f]];
         out[a.lower[f]] += up[f] * x[a.upper[f]];
     }
+    // coupled patches after the faces, patch by patch (lduMatrixUpdateMatrixInterfaces.C, processorFvPatchField /
+    // cyclicFvPatchField::updateInterfaceMatrix: result[faceCells] -= coeffs*psiNeighbour)
+    for (int q = 0; q < a.nCouple; q++) out[a.cRow[q]] -= a.cc[q] * x[a.cCol[q]];
 }
 
 __device__ static void c_precondition(const CoarsestArgs& a, const double* up, const double* lo, const double* rD,
@@ -1462,16 +1543,37 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
     extern __shared__ double csm[];
     CoarsestArgs a = a_;
     const int n = a.nCells, nF = a.nFaces;
+    const int nQ = a.nCouple;
     if (useSmem) {
-        int* sl = reinterpret_cast<int*>(csm + 2 * nF + 12 * n);
+        int* sl = reinterpret_cast<int*>(csm + 2 * nF + 12 * n + nQ);
         int* su = sl + nF;
+        int* sr = su + nF;
+        int* sc = sr + nQ;
+        int* so = sc + nQ;
         for (int f = threadIdx.x; f < nF; f += blockDim.x) {
             sl[f] = a.lower[f];
             su[f] = a.upper[f];
         }
+        for (int q = threadIdx.x; q < nQ; q += blockDim.x) {
+            sr[q] = a.cRow[q];
+            sc[q] = a.cCol[q];
+        }
+        if (a.gathered)
+            for (int r = threadIdx.x; r <= a.nRanks; r += blockDim.x) {
+                so[r] = a.cellOff[r];
+                so[a.nRanks + 1 + r] = a.faceOff[r];
+                so[2 * (a.nRanks + 1) + r] = a.coupleOff[r];
+            }
         __syncthreads();
         a.lower = sl;
         a.upper = su;
+        a.cRow = sr;
+        a.cCol = sc;
+        if (a.gathered) {
+            a.cellOff = so;
+            a.faceOff = so + a.nRanks + 1;
+            a.coupleOff = so + 2 * (a.nRanks + 1);
+        }
     }
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double* w = useSmem ? csm : a.work;
@@ -1489,18 +1591,39 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
     double* v5 = w;            w += n;
     double* v6 = w;            w += n;
     double* v7 = w;            w += n;
-    for (int f = 0; f < nF; f++) {
-        up[f] = a.Uval[a.Uidx[f]];
-        lo[f] = a.Lval[a.Lidx[f]];
-    }
-    for (int c = 0; c < n; c++) {
-        dg[c] = a.diag[a.ipos[c]];
-        b[c] = a.source[a.ipos[c]];
-        x[c] = 0.0;
+    double* cc = w;            w += nQ;
+    a.cc = cc;
+    if (a.gathered) {
+        // per-rank block of gCoef: [diag (maxCells) | upper (maxFaces) | lower (maxFaces) | coupling (maxCouple)]
+        for (int r = 0; r < a.nRanks; r++) {
+            const double* blk = a.gCoef + size_t(r) * a.blockLen;
+            const double* sb = a.gSrc + size_t(r) * a.maxCells;
+            const int c0 = a.cellOff[r], f0 = a.faceOff[r], q0 = a.coupleOff[r];
+            for (int c = c0; c < a.cellOff[r + 1]; c++) {
+                dg[c] = blk[c - c0];
+                b[c] = sb[c - c0];
+                x[c] = 0.0;
+            }
+            for (int f = f0; f < a.faceOff[r + 1]; f++) {
+                up[f] = blk[a.maxCells + f - f0];
+                lo[f] = blk[a.maxCells + a.maxFaces + f - f0];
+            }
+            for (int q = q0; q < a.coupleOff[r + 1]; q++) cc[q] = blk[a.maxCells + 2 * a.maxFaces + q - q0];
+        }
+    } else {
+        for (int f = 0; f < nF; f++) {
+            up[f] = a.Uval[a.Uidx[f]];
+            lo[f] = a.Lval[a.Lidx[f]];
+        }
+        for (int c = 0; c < n; c++) {
+            dg[c] = a.diag[a.ipos[c]];
+            b[c] = a.source[a.ipos[c]];
+            x[c] = 0.0;
+        }
     }
     const double vSmall = 2.2250738585072014e-308;
 
-    if (nF == 0) {
+    if (nF == 0 && !a.gathered) {
         for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = b[c] / dg[c];   // diagonalSolver.C:66
         return;
     }
@@ -1516,17 +1639,15 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
         tmp[a.upper[f]] += lo[f];
         tmp[a.lower[f]] += up[f];
     }
-    double sumX = 0.0;
-    for (int c = 0; c < n; c++) sumX += x[c];
+    for (int q = 0; q < nQ; q++) tmp[a.cRow[q]] -= cc[q];   // lduMatrix::sumA, coupled patches (lduMatrixATmul.C:187-198)
+    const double sumX = c_sum(a, [&](int c) { return x[c]; });
     const double xbar = sumX / n;
-    double nfac = 0.0;
-    for (int c = 0; c < n; c++) {
+    double nfac = c_sum(a, [&](int c) {
         const double t = tmp[c] * xbar;
-        nfac += fabs(Ax[c] - t) + fabs(b[c] - t);
-    }
+        return fabs(Ax[c] - t) + fabs(b[c] - t);
+    });
     nfac += 1e-20;
-    double sm = 0.0;
-    for (int c = 0; c < n; c++) sm += fabs(r[c]);
+    double sm = c_sum(a, [&](int c) { return fabs(r[c]); });
     const double ini = sm / nfac;
     double fin = ini;
 
@@ -1544,8 +1665,7 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
             do {
                 wArAold = wArA;
                 c_precondition(a, up, lo, rD, wA, r);
-                wArA = 0.0;
-                for (int c = 0; c < n; c++) wArA += wA[c] * r[c];
+                wArA = c_sum(a, [&](int c) { return wA[c] * r[c]; });
                 if (it == 0) {
                     for (int c = 0; c < n; c++) p[c] = wA[c];
                 } else {
@@ -1553,16 +1673,14 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
                     for (int c = 0; c < n; c++) p[c] = wA[c] + beta * p[c];
                 }
                 c_amul(a, up, lo, dg, wA, p);
-                double wApA = 0.0;
-                for (int c = 0; c < n; c++) wApA += wA[c] * p[c];
+                const double wApA = c_sum(a, [&](int c) { return wA[c] * p[c]; });
                 if (fabs(wApA) / nfac < vSmall) break;
                 const double alpha = wArA / wApA;
                 for (int c = 0; c < n; c++) {
                     x[c] += alpha * p[c];
                     r[c] -= alpha * wA[c];
                 }
-                sm = 0.0;
-                for (int c = 0; c < n; c++) sm += fabs(r[c]);
+                sm = c_sum(a, [&](int c) { return fabs(r[c]); });
                 fin = sm / nfac;
             } while (++it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
         } else {
@@ -1578,8 +1696,7 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
             int it = 0;
             do {
                 const double rhoOld = rho;
-                rho = 0.0;
-                for (int c = 0; c < n; c++) rho += r0[c] * r[c];
+                rho = c_sum(a, [&](int c) { return r0[c] * r[c]; });
                 if (fabs(rho) < vSmall) break;
                 if (it == 0) {
                     for (int c = 0; c < n; c++) p[c] = r[c];
@@ -1590,12 +1707,10 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
                 }
                 c_precondition(a, up, lo, rD, y, p);
                 c_amul(a, up, lo, dg, AyA, y);
-                double r0AyA = 0.0;
-                for (int c = 0; c < n; c++) r0AyA += r0[c] * AyA[c];
+                const double r0AyA = c_sum(a, [&](int c) { return r0[c] * AyA[c]; });
                 alpha = rho / r0AyA;
                 for (int c = 0; c < n; c++) s[c] = r[c] - alpha * AyA[c];
-                sm = 0.0;
-                for (int c = 0; c < n; c++) sm += fabs(s[c]);
+                sm = c_sum(a, [&](int c) { return fabs(s[c]); });
                 fin = sm / nfac;
                 if (++it >= 0 && c_converged(fin, ini, a.tolerance, a.relTol)) {
                     for (int c = 0; c < n; c++) x[c] += alpha * y[c];
@@ -1603,22 +1718,200 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
                 }
                 c_precondition(a, up, lo, rD, z, s);
                 c_amul(a, up, lo, dg, t, z);
-                double tt = 0.0;
-                for (int c = 0; c < n; c++) tt += t[c] * t[c];
-                double ts = 0.0;
-                for (int c = 0; c < n; c++) ts += t[c] * s[c];
+                const double tt = c_sum(a, [&](int c) { return t[c] * t[c]; });
+                const double ts = c_sum(a, [&](int c) { return t[c] * s[c]; });
                 omega = ts / tt;
                 for (int c = 0; c < n; c++) {
                     x[c] += alpha * y[c] + omega * z[c];
                     r[c] = s[c] - omega * t[c];
                 }
-                sm = 0.0;
-                for (int c = 0; c < n; c++) sm += fabs(r[c]);
+                sm = c_sum(a, [&](int c) { return fabs(r[c]); });
                 fin = sm / nfac;
             } while (it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
         }
     }
-    for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = x[c];
+    if (a.gathered) {
+        const int c0 = a.cellOff[a.myRank];
+        for (int c = c0; c < a.cellOff[a.myRank + 1]; c++) a.psi[a.ipos[c - c0]] = x[c];
+    } else {
+        for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = x[c];
+    }
+}
+
+// ---- gathered coarsest level ------------------------------------------------------------------------------
+// With coupled patches on the coarsest level (processor patches of a decomposed case, cyclic halves) the reference
+// runs its regular distributed PCG+DIC / PBiCGStab+DILU there (GAMGSolver.C:286-319).  Launch by launch that is a few
+// thousand tiny kernels and all-reduces per V-cycle.  Instead every rank receives the coarsest blocks of all ranks
+// (topology once per mesh, coefficients once per matrix, the source once per cycle: one all-gather) and replays the
+// distributed iteration in k_coarsest_solve: block-local DIC/DILU (faces never cross ranks), couplings as explicit
+// off-diagonal entries, sums rank by rank.  All ranks compute the same numbers; each keeps its own slice.
+
+static void allGatherInts(const std::vector<int>& mine, std::vector<int>& all) {
+    Context& c = ctx();
+    if (c.nRanks == 1) {
+        all = mine;
+        return;
+    }
+    DevBuf<int> snd, rcv;
+    snd.upload(mine, c.stream);
+    rcv.alloc(mine.size() * c.nRanks);
+    int r = c.nccl.AllGather(snd.p, rcv.p, mine.size(), ncclInt32, c.comm, c.stream);
+    if (r != 0) throw CudaError(std::string("ncclAllGather: ") + c.nccl.GetErrorString((ncclResult_t)r));
+    all.resize(mine.size() * c.nRanks);
+    B2_CUDA(cudaMemcpyAsync(all.data(), rcv.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static constexpr int kMaxGatheredCells = 4096;
+
+// Collective: every rank calls it at the same point (first GAMG solve on a mesh) and all ranks reach the same
+// decision, because it is taken from the all-gathered data only.
+static void ensureCoarsestGather(b200ls_matrix_s* m, int k) {
+    DevLevel& D = DL(m, k);
+    CoarsestGather& G = D.gather;
+    Context& c = ctx();
+    if (G.tried) return;
+    G.tried = true;
+    static const bool off = getenv("B200LS_NO_COARSEST_GATHER") != nullptr;
+    if (off || int(D.ifaceCellsRef.size()) != D.nIfaces) return;
+    const int R = c.nRanks;
+    G.ifaceCoupleOff.assign(D.nIfaces + 1, 0);
+    for (int i = 0; i < D.nIfaces; i++) G.ifaceCoupleOff[i + 1] = G.ifaceCoupleOff[i] + D.ifaceSize[i];
+    G.myCouple = G.ifaceCoupleOff[D.nIfaces];
+    int unsupported = 0;   // several processor patches to one neighbour: the pairing by rank is ambiguous
+    for (int i = 0; i < D.nIfaces; i++)
+        for (int j = 0; j < i; j++)
+            if (D.ifacePartner[i] < 0 && D.ifacePartner[j] < 0 && D.ifaceNbr[i] == D.ifaceNbr[j]) unsupported = 1;
+    std::vector<int> sizes;
+    allGatherInts({D.nCells, D.nFaces, G.myCouple, unsupported}, sizes);
+    std::vector<int> cellOff(R + 1, 0), faceOff(R + 1, 0), coupleOff(R + 1, 0);
+    G.maxCells = G.maxFaces = G.maxCouple = 0;
+    for (int r = 0; r < R; r++) {
+        cellOff[r + 1] = cellOff[r] + sizes[4 * r];
+        faceOff[r + 1] = faceOff[r] + sizes[4 * r + 1];
+        coupleOff[r + 1] = coupleOff[r] + sizes[4 * r + 2];
+        G.maxCells = std::max(G.maxCells, sizes[4 * r]);
+        G.maxFaces = std::max(G.maxFaces, sizes[4 * r + 1]);
+        G.maxCouple = std::max(G.maxCouple, sizes[4 * r + 2]);
+        if (sizes[4 * r + 3]) unsupported = 1;
+    }
+    if (unsupported || cellOff[R] > kMaxGatheredCells) return;
+    G.nCells = cellOff[R];
+    G.nFaces = faceOff[R];
+    G.nCouple = coupleOff[R];
+    G.blockLen = G.maxCells + 2 * G.maxFaces + G.maxCouple;
+
+    // topology block of this rank: [lower | upper] (maxFaces each), then per coupling entry
+    // [cell | peer rank | peer patch (cyclic partner on the same rank, -1: the peer's patch towards me) | patch | face]
+    const int mf = G.maxFaces, mq = G.maxCouple;
+    std::vector<int> topo(size_t(2) * mf + size_t(5) * mq, -1), all;
+    for (int f = 0; f < D.nFaces; f++) {
+        topo[f] = D.hostRefLower[f];
+        topo[mf + f] = D.hostRefUpper[f];
+    }
+    for (int i = 0; i < D.nIfaces; i++)
+        for (int e = 0; e < D.ifaceSize[i]; e++) {
+            int* t = topo.data() + 2 * mf;
+            const int q = G.ifaceCoupleOff[i] + e;
+            t[q] = D.ifaceCellsRef[i][e];
+            t[mq + q] = D.ifacePartner[i] >= 0 ? c.rank : D.ifaceNbr[i];
+            t[2 * mq + q] = D.ifacePartner[i];
+            t[3 * mq + q] = i;
+            t[4 * mq + q] = e;
+        }
+    allGatherInts(topo, all);
+    const size_t tb = topo.size();
+    std::vector<int> lower(G.nFaces), upper(G.nFaces), cRow(G.nCouple), cCol(G.nCouple, -1);
+    // (rank, patch, face) -> global cell, and for processor patches (rank, neighbour rank) -> patch
+    std::map<std::array<int, 3>, int> cellOf;
+    std::map<std::array<int, 2>, int> patchTo;
+    for (int r = 0; r < R; r++) {
+        const int* t = all.data() + tb * r;
+        for (int f = 0; f < sizes[4 * r + 1]; f++) {
+            lower[faceOff[r] + f] = t[f] + cellOff[r];
+            upper[faceOff[r] + f] = t[mf + f] + cellOff[r];
+        }
+        t += 2 * mf;
+        for (int q = 0; q < sizes[4 * r + 2]; q++) {
+            cellOf[{r, t[3 * mq + q], t[4 * mq + q]}] = t[q] + cellOff[r];
+            if (t[2 * mq + q] < 0) patchTo[{r, t[mq + q]}] = t[3 * mq + q];
+        }
+    }
+    for (int r = 0; r < R; r++) {
+        const int* t = all.data() + tb * r + 2 * mf;
+        for (int q = 0; q < sizes[4 * r + 2]; q++) {
+            const int peer = t[mq + q];
+            int peerPatch = t[2 * mq + q];
+            if (peerPatch < 0) {
+                auto it = patchTo.find({peer, r});
+                if (it == patchTo.end()) return;
+                peerPatch = it->second;
+            }
+            auto it = cellOf.find({peer, peerPatch, t[4 * mq + q]});
+            if (it == cellOf.end()) return;
+            cRow[coupleOff[r] + q] = t[q] + cellOff[r];
+            cCol[coupleOff[r] + q] = it->second;
+        }
+    }
+    G.lower.upload(lower, c.stream);
+    G.upper.upload(upper, c.stream);
+    G.cRow.upload(cRow, c.stream);
+    G.cCol.upload(cCol, c.stream);
+    G.cellOff.upload(cellOff, c.stream);
+    G.faceOff.upload(faceOff, c.stream);
+    G.coupleOff.upload(coupleOff, c.stream);
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    G.ok = true;
+}
+
+static void allGatherDoubles(const double* mine, double* all, size_t count) {
+    Context& c = ctx();
+    int r = c.nccl.AllGather(mine, all, count, ncclDouble, c.comm, c.stream);
+    if (r != 0) throw CudaError(std::string("ncclAllGather: ") + c.nccl.GetErrorString((ncclResult_t)r));
+}
+
+// coefficients of the coarsest level of every rank, after the coarse matrices were (re)built
+static void gatherCoarsestCoefs(b200ls_matrix_s* m) {
+    const int k = int(m->levels.size()) - 1;
+    DevLevel& D = DL(m, k);
+    MatLevel& M = m->levels[k];
+    Context& c = ctx();
+    if (!(c.nRanks > 1 || D.nIfaces > 0)) return;
+    ensureCoarsestGather(m, k);
+    const CoarsestGather& G = D.gather;
+    if (!G.ok) return;
+    m->gSendCoef.alloc(G.blockLen);
+    m->gSendSrc.alloc(G.maxCells);
+    if (G.blockLen) B2_CUDA(cudaMemsetAsync(m->gSendCoef.p, 0, sizeof(double) * G.blockLen, S()));
+    if (G.maxCells) B2_CUDA(cudaMemsetAsync(m->gSendSrc.p, 0, sizeof(double) * G.maxCells, S()));
+    double* blk = m->gSendCoef.p;
+    if (D.nCells) LAUNCH(k_gather, gridStride(D.nCells), 256, blk, M.diag.p, D.ipos.p, D.nCells);
+    if (D.nFaces) {
+        LAUNCH(k_gather, gridStride(D.nFaces), 256, blk + G.maxCells, M.Uval(), D.Uidx.p, D.nFaces);
+        LAUNCH(k_gather, gridStride(D.nFaces), 256, blk + G.maxCells + G.maxFaces, M.Lval(D.nFaces), D.Lidx.p,
+               D.nFaces);
+    }
+    for (int i = 0; i < D.nIfaces; i++)
+        if (D.ifaceSize[i])
+            B2_CUDA(cudaMemcpyAsync(blk + G.maxCells + 2 * G.maxFaces + G.ifaceCoupleOff[i], M.bou[i].p,
+                                    sizeof(double) * D.ifaceSize[i], cudaMemcpyDeviceToDevice, S()));
+    if (c.nRanks > 1) {
+        m->gCoef.alloc(size_t(G.blockLen) * c.nRanks);
+        m->gSrc.alloc(size_t(G.maxCells) * c.nRanks);
+        allGatherDoubles(m->gSendCoef.p, m->gCoef.p, G.blockLen);
+    }
+}
+
+static void launchCoarsest(const CoarsestArgs& a, size_t smemBytes) {
+    constexpr size_t kMax = 200 * 1024;
+    const int useSmem = smemBytes <= kMax ? 1 : 0;
+    static bool attr = false;
+    if (!attr) {
+        B2_CUDA(cudaFuncSetAttribute(k_coarsest_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMax)));
+        attr = true;
+    }
+    k_coarsest_solve<<<1, 32, useSmem ? smemBytes : 0, S()>>>(a, useSmem);
+    ctx().launches++;
 }
 
 static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
@@ -1628,6 +1921,49 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
     if (ctx().nRanks == 1 && D.nIfaces > 0 && D.nFaces == 0) {
         // lduMatrix::diagonal() -> diagonalSolver, which ignores the interfaces (GAMGSolver.C:271-284, diagonalSolver.C:66)
         LAUNCH(k_div, gridStride(D.nCells), 256, M.corr.p, M.src.p, M.diag.p, D.nCells);
+        return;
+    }
+    if ((ctx().nRanks > 1 || D.nIfaces > 0) && D.gather.ok) {
+        const CoarsestGather& G = D.gather;
+        Context& cx = ctx();
+        const double *gCoef = m->gSendCoef.p, *gSrc = m->gSendSrc.p;
+        if (D.nCells) LAUNCH(k_gather, gridStride(D.nCells), 256, m->gSendSrc.p, M.src.p, D.ipos.p, D.nCells);
+        if (cx.nRanks > 1) {
+            allGatherDoubles(m->gSendSrc.p, m->gSrc.p, G.maxCells);
+            gCoef = m->gCoef.p;
+            gSrc = m->gSrc.p;
+        }
+        const size_t nD = size_t(2) * G.nFaces + size_t(12) * G.nCells + G.nCouple;
+        m->coarsestWork.alloc(nD + 16);
+        CoarsestArgs a;
+        memset(&a, 0, sizeof(a));
+        a.nCells = G.nCells;
+        a.nFaces = G.nFaces;
+        a.symmetric = m->symmetric ? 1 : 0;
+        a.lower = G.lower.p;
+        a.upper = G.upper.p;
+        a.ipos = D.ipos.p;
+        a.psi = M.corr.p;
+        a.work = m->coarsestWork.p;
+        a.tolerance = c.tolerance;
+        a.relTol = c.relTol;
+        a.maxIter = 1000;   // lduMatrix::solver::defaultMaxIter_
+        a.gathered = 1;
+        a.nRanks = cx.nRanks;
+        a.myRank = cx.rank;
+        a.nCouple = G.nCouple;
+        a.maxCells = G.maxCells;
+        a.maxFaces = G.maxFaces;
+        a.blockLen = G.blockLen;
+        a.cellOff = G.cellOff.p;
+        a.faceOff = G.faceOff.p;
+        a.coupleOff = G.coupleOff.p;
+        a.cRow = G.cRow.p;
+        a.cCol = G.cCol.p;
+        a.gCoef = gCoef;
+        a.gSrc = gSrc;
+        launchCoarsest(a, nD * sizeof(double) +
+                              (size_t(2) * G.nFaces + size_t(2) * G.nCouple + size_t(3) * (cx.nRanks + 1)) * sizeof(int));
         return;
     }
     if (ctx().nRanks > 1 || D.nIfaces > 0) {
@@ -1673,17 +2009,13 @@ static void solveCoarsest(b200ls_matrix_s* m, const b200ls_controls& c) {
     a.tolerance = c.tolerance;
     a.relTol = c.relTol;
     a.maxIter = 1000;   // lduMatrix::solver::defaultMaxIter_
-    {
-        const size_t bytes = (size_t(2) * D.nFaces + size_t(12) * D.nCells) * sizeof(double) + size_t(2) * D.nFaces * sizeof(int);
-        const int useSmem = bytes <= 160 * 1024 ? 1 : 0;
-        static bool attr = false;
-        if (!attr) {
-            B2_CUDA(cudaFuncSetAttribute(k_coarsest_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr = true;
-        }
-        k_coarsest_solve<<<1, 32, useSmem ? bytes : 0, S()>>>(a, useSmem);
-        ctx().launches++;
-    }
+    a.gathered = 0;
+    a.nRanks = 1;
+    a.myRank = 0;
+    a.nCouple = 0;
+    a.cRow = a.cCol = nullptr;
+    launchCoarsest(a, (size_t(2) * D.nFaces + size_t(12) * D.nCells) * sizeof(double) +
+                          size_t(2) * D.nFaces * sizeof(int));
 }
 
 // GAMGSolver::scale (GAMGSolverScale.C:31-76)
@@ -1718,7 +2050,9 @@ static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, d
     const int coarsest = nL - 2;   // reference coarsestLevel index into matrixLevels_
     const int n0 = DL(m, 0).nCells;
 
+    vmark("start", 0);
     restrictTo(m, 0, m->levels[1].src.p, finestResidual);
+    vmark("restrict", 0);
     for (int l = 0; l < coarsest; l++) {
         MatLevel& ML = m->levels[l + 1];
         if (c.nPreSweeps) {
@@ -1729,17 +2063,21 @@ static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, d
             double* spare = ML.tmpC.p;
             opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
                      std::min(c.nPreSweeps + c.preSweepsLevelMultiplier * l, c.maxPreSweeps));
+            vmark("pre-smooth", l + 1);
             if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
             double* ACf = ML.tmpB.p;
             if (scaleCorrection && l < coarsest - 1) gamgScale(m, l + 1, ML.corr.p, ACf, ML.src.p);
             opAmul(m, l + 1, ACf, ML.corr.p);
             // coarseSources[l] -= ACf
             LAUNCH(k_sub_inplace, gridStride(D.nCells), 256, ML.src.p, ACf, D.nCells);
+            vmark("scale+residual", l + 1);
         }
         restrictTo(m, l + 1, m->levels[l + 2].src.p, ML.src.p);
+        vmark("restrict", l + 1);
     }
 
     solveCoarsest(m, c);
+    vmark("coarsest solve", nL - 1);
 
     for (int l = coarsest - 1; l >= 0; l--) {
         DevLevel& D = DL(m, l + 1);
@@ -1755,18 +2093,22 @@ static void vcycle(b200ls_matrix_s* m, const b200ls_controls& c, double*& psi, d
         prolongTo(m, l + 1, ML.corr.p, m->levels[l + 2].corr.p);
         if (scaleCorrection && l < coarsest - 1) gamgScale(m, l + 1, ML.corr.p, ML.tmpB.p, ML.src.p);
         if (pre) LAUNCH(k_add_inplace, gridStride(D.nCells), 256, ML.corr.p, pre, D.nCells);
+        vmark("prolong+scale", l + 1);
         double* corr = ML.corr.p;
         double* spare = ML.tmpC.p;
         // Gauss-Seidel sweeps swap corr/spare; the other smoothers leave corr in place
         opSmooth(m, l + 1, c.precond, corr, spare, ML.src.p,
                  std::min(c.nPostSweeps + c.postSweepsLevelMultiplier * l, c.maxPostSweeps));
+        vmark("post-smooth", l + 1);
         if (corr != ML.corr.p) std::swap(ML.corr.p, ML.tmpC.p);
     }
 
     prolongTo(m, 0, finestCorrection, m->levels[1].corr.p);
     if (scaleCorrection) gamgScale(m, 0, finestCorrection, Apsi, finestResidual);
     LAUNCH(k_add_inplace, gridStride(n0), 256, psi, finestCorrection, n0);
+    vmark("prolong+scale", 0);
     opSmooth(m, 0, c.precond, psi, psiSpare, source, c.nFinestSweeps);
+    vmark("finest smooth", 0);
 }
 
 // GAMGPreconditioner::precondition (GAMGPreconditioner.C:81-148): nVcycles V-cycles on A wA = rA from wA = 0
@@ -1896,6 +2238,7 @@ void solveDev(b200ls_matrix_s* m, const b200ls_controls& c, double* psiCell, con
                 throw CudaError("unknown solver");
         }
         toCells(m, 0, psiCell, vPsi.buf.p);
+        vprofDump(perf->nIterations);
         B2_CUDA(cudaEventRecord(ev2, S()));
         B2_CUDA(cudaStreamSynchronize(S()));
         checkLaunch("solve");

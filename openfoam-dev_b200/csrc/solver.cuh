@@ -56,6 +56,8 @@ struct b200ls_matrix_s {
     b200ls::DevBuf<double> stageA, stageB;       // cell-order staging (H2D / D2H)
     b200ls::DevBuf<double> scalars;              // device scalars of the Krylov loops
     b200ls::DevBuf<double> coarsestWork;         // scratch of the single-thread coarsest solve
+    // gathered coarsest level (CoarsestGather): this rank's padded coefficient / source block and all ranks' blocks
+    b200ls::DevBuf<double> gSendCoef, gCoef, gSendSrc, gSrc;
     double* vec(const std::string& name);
 };
 
