@@ -187,6 +187,8 @@ struct DevLevel {
     DevBuf<int> refLower, refUpper, Uidx, Lidx;
     std::vector<int> hostRefLower, hostRefUpper;
     std::vector<std::vector<int>> ifaceCellsRef;    // per interface: faceCells in reference cell numbering (host)
+    std::vector<std::vector<int>> hostIfaceCellsPos;   // per interface: positions of the patch cells (host copy)
+    DevBuf<int> bRowOf;                             // position -> boundary row or -1 (coupled fused Gauss-Seidel)
     CoarsestGather gather;
 };
 

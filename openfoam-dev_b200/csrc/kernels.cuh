@@ -66,6 +66,11 @@ __global__ void k_gather(double* __restrict__ out, const double* __restrict__ in
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[idx[i]];
 }
 
+__global__ void k_scatter_index(int* __restrict__ out, const int* __restrict__ idx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[idx[i]] = i;
+}
+
 __global__ void k_fill(double* __restrict__ out, double v, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = v;
 }
@@ -688,6 +693,13 @@ __device__ __noinline__ double gather_tail(double acc, int j0, int j1, const int
 }
 
 static constexpr int kMaxFusedSweeps = 8;
+static constexpr int kCoupledSlotSweeps = 3;   // coupled fused Gauss-Seidel: up to 1 + 3 sweeps per launch
+struct CoupledView {
+    const double* coeffs;   // interfaceBouCoeffs of the patch
+    double* mine;           // [kCoupledSlotSweeps][size] slots of this call's parity in my arena (neighbour writes)
+    double* theirs;         // the neighbour's slots for its side of the patch (I write)
+    int size, pad;
+};
 struct MultiSweepArgs {
     const int4* tasks;      // (start, count, sweep, -)
     int nTasks;
@@ -702,7 +714,18 @@ struct MultiSweepArgs {
     const double* b;
     double* X[kMaxFusedSweeps + 1];
     int* err;
+    // COUPLED (processor patches, P2P): rows on a patch take the neighbour rank's values of the previous sweep from
+    // slots in this rank's arena (the neighbour stores them there the moment it has finished the row) and publish
+    // their own the same way.  Sweep 0 uses b0 = source with the regular halo exchange already applied.
+    int nSweeps;
+    const double* b0;
+    const int* bRowOf;      // position -> boundary row or -1
+    const int* bRowPtr;
+    const int* bEntIface;
+    const int* bEntFace;
+    const CoupledView* views;
 };
+template <bool COUPLED>
 __global__ void __launch_bounds__(256, 2) k_gs_multi(MultiSweepArgs a) {
     const int wpb = blockDim.x >> 5;
     const int nW = gridDim.x * wpb;
@@ -719,7 +742,28 @@ __global__ void __launch_bounds__(256, 2) k_gs_multi(MultiSweepArgs a) {
             const int j0 = a.Lptr[p], j1 = a.Lptr[p + 1];
             const int k0 = a.Uptr[p], k1 = a.Uptr[p + 1];
             const double dg = a.diag[p];
-            double acc = a.b[p];
+            const int br = COUPLED ? a.bRowOf[p] : -1;
+            double acc = (COUPLED && s == 0) ? a.b0[p] : a.b[p];
+            if (COUPLED && s > 0 && br >= 0) {
+                // bPrime = source - sum (-bouCoeffs)*psiNeighbour (GaussSeidelSmoother.C:110-145), neighbour values
+                // of the previous sweep; patch by patch, face by face like k_iface_apply
+                for (int e = a.bRowPtr[br]; e < a.bRowPtr[br + 1]; e++) {
+                    const CoupledView v = a.views[a.bEntIface[e]];
+                    const int f = a.bEntFace[e];
+                    double* slot = v.mine + size_t(s - 1) * v.size + f;
+                    double w = ld_sys(slot);
+                    unsigned spins = 0;
+                    while (is_sentinel(w)) {
+                        if (++spins > kMaxSpins) {
+                            *a.err = 2;
+                            break;
+                        }
+                        w = ld_sys(slot);
+                    }
+                    acc -= (-1.0 * v.coeffs[f]) * w;
+                    *slot = sentinel();   // re-armed for the call after next (same parity)
+                }
+            }
             if (s == 0) {
                 double up[4];
 #pragma unroll
@@ -781,7 +825,14 @@ __global__ void __launch_bounds__(256, 2) k_gs_multi(MultiSweepArgs a) {
                     if (k < nu) acc -= vu[k] * wu[k];
                 if (k0 + nu < k1) acc = gather_tail(acc, k0 + nu, k1, a.Ucol, a.Uval, xo, a.err);
             }
-            st_l2(xn + p, acc / dg);
+            const double xNew = acc / dg;
+            st_l2(xn + p, xNew);
+            if (COUPLED && br >= 0 && s + 1 < a.nSweeps) {
+                for (int e = a.bRowPtr[br]; e < a.bRowPtr[br + 1]; e++) {
+                    const CoupledView v = a.views[a.bEntIface[e]];
+                    st_sys(v.theirs + size_t(s) * v.size + a.bEntFace[e], xNew);
+                }
+            }
         }
         __syncwarp();
         task = next;

@@ -364,6 +364,8 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
     D.anyProcIface = false;
     D.ifaceCellsPos.clear();
     D.ifaceCellsPos.resize(D.nIfaces);
+    D.hostIfaceCellsPos.clear();
+    D.bRowOf.release();
     for (int i = 0; i < D.nIfaces; i++) {
         const auto& fc = H.interfaces[i].faceCells;
         D.ifaceSize.push_back(int(fc.size()));
@@ -374,6 +376,7 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         for (size_t k = 0; k < fc.size(); k++) pos[k] = H.ipos[fc[k]];
         D.ifaceCellsPos[i].upload(pos, s);
         B2_CUDA(cudaStreamSynchronize(s));
+        D.hostIfaceCellsPos.emplace_back(pos.begin(), pos.end());
     }
     D.ifaceCellsRef.clear();
     if (coarsest)
@@ -463,6 +466,8 @@ static void syncMatrixWithMesh(b200ls_matrix_s* m) {
     }
 }
 
+static void setupCoupledGS(b200ls_matrix_s* m, int level);
+static void fillSentinel(double* p, int n);
 // bump allocation inside this rank's IPC arena; returns nullptr when the arena is exhausted
 static char* arenaAlloc(size_t bytes) {
     P2PState& P = ctx().p2p;
@@ -471,6 +476,22 @@ static char* arenaAlloc(size_t bytes) {
     char* p = P.arena + P.bump;
     P.bump += aligned;
     return p;
+}
+
+static void allGatherInts(const std::vector<int>& mine, std::vector<int>& all) {
+    Context& c = ctx();
+    if (c.nRanks == 1) {
+        all = mine;
+        return;
+    }
+    DevBuf<int> snd, rcv;
+    snd.upload(mine, c.stream);
+    rcv.alloc(mine.size() * c.nRanks);
+    int r = c.nccl.AllGather(snd.p, rcv.p, mine.size(), ncclInt32, c.comm, c.stream);
+    if (r != 0) throw CudaError(std::string("ncclAllGather: ") + c.nccl.GetErrorString((ncclResult_t)r));
+    all.resize(mine.size() * c.nRanks);
+    B2_CUDA(cudaMemcpyAsync(all.data(), rcv.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // P2P halos: place the receive buffers (two parities) and epoch flags of this level in the arena and swap their
@@ -555,6 +576,128 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
     B2_CUDA(cudaMemsetAsync(M.p2pTickets.p, 0, sizeof(unsigned int) * D.nIfaces, c.stream));
     M.haloEpoch = 0;
     M.p2pReady = true;
+    setupCoupledGS(m, level);
+}
+
+// Fused Gauss-Seidel sweeps across processor patches (k_gs_multi<true>): sweep s of a patch row needs the neighbour
+// rank's value after sweep s-1.  Ordering every (row, sweep) of every rank by tau = wavefront + lag*sweep with ONE lag
+// for all ranks, lag > (neighbour's wavefront - my wavefront) for every coupled pair, makes every dependency --
+// local or across ranks -- point to a smaller tau, so the pipelined kernels of all ranks cannot deadlock and the chain
+// is nLevels + lag*(nSweeps-1) hops instead of nSweeps*nLevels plus a halo exchange per sweep.
+// Collective (called by every rank at the end of setupP2PHalos).
+static void setupCoupledGS(b200ls_matrix_s* m, int level) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    Context& c = ctx();
+    M.gsCoupled = false;
+    static const bool off = getenv("B200LS_NO_COUPLED_FUSED_GS") != nullptr;
+    if (off) return;
+    bool okLocal = D.fwdPos.n == 0 && !D.hasPencil && int(D.hostIfaceCellsPos.size()) == D.nIfaces;
+    for (int i = 0; i < D.nIfaces; i++) okLocal = okLocal && D.ifacePartner[i] < 0;
+    // wavefront of every patch cell
+    std::vector<std::vector<int>> myLevel(D.nIfaces), nbLevel(D.nIfaces);
+    if (okLocal && D.nIfaces) {
+        std::vector<int> lvl(D.nCells, 0);
+        for (size_t t = 0; t < D.hostFwdTasks.size(); t++)
+            for (int r = 0; r < D.hostFwdTasks[t].y; r++) lvl[D.hostFwdTasks[t].x + r] = D.hostFwdTaskLevel[t];
+        for (int i = 0; i < D.nIfaces; i++) {
+            myLevel[i].resize(D.ifaceSize[i]);
+            for (int f = 0; f < D.ifaceSize[i]; f++) myLevel[i][f] = lvl[D.hostIfaceCellsPos[i][f]];
+        }
+    }
+    for (int i = 0; i < D.nIfaces; i++) {
+        myLevel[i].resize(D.ifaceSize[i], 0);
+        nbLevel[i].assign(D.ifaceSize[i], 0);
+    }
+    // slots in my arena: [2 parities][kCoupledSlotSweeps][size], all-sentinel
+    M.gsSlotLocal.assign(D.nIfaces, nullptr);
+    M.gsSlotRemote.assign(D.nIfaces, nullptr);
+    std::vector<long long> mine(std::max(D.nIfaces, 1), -1), theirs(std::max(D.nIfaces, 1), -1);
+    for (int i = 0; i < D.nIfaces && okLocal; i++) {
+        const size_t cnt = size_t(2) * kCoupledSlotSweeps * std::max(D.ifaceSize[i], 1);
+        char* q = arenaAlloc(cnt * sizeof(double));
+        if (!q) {
+            okLocal = false;
+            break;
+        }
+        M.gsSlotLocal[i] = reinterpret_cast<double*>(q);
+        fillSentinel(M.gsSlotLocal[i], int(cnt));
+        mine[i] = q - c.p2p.arena;
+    }
+    if (!okLocal) std::fill(mine.begin(), mine.end(), -1);
+    // pairwise: slot offsets and wavefronts of the patch cells
+    DevBuf<long long> dMine, dTheirs;
+    dMine.upload(mine, c.stream);
+    dTheirs.alloc(mine.size());
+    std::vector<DevBuf<int>> dLm(D.nIfaces), dLn(D.nIfaces);
+    for (int i = 0; i < D.nIfaces; i++) {
+        dLm[i].upload(myLevel[i], c.stream);
+        dLn[i].alloc(std::max(D.ifaceSize[i], 1));
+    }
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    c.nccl.GroupStart();
+    for (int i = 0; i < D.nIfaces; i++) {
+        if (D.ifacePartner[i] >= 0) continue;
+        c.nccl.Send(dMine.p + i, 1, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
+        c.nccl.Recv(dTheirs.p + i, 1, ncclInt64, D.ifaceNbr[i], c.comm, c.stream);
+        if (D.ifaceSize[i]) {
+            c.nccl.Send(dLm[i].p, D.ifaceSize[i], ncclInt32, D.ifaceNbr[i], c.comm, c.stream);
+            c.nccl.Recv(dLn[i].p, D.ifaceSize[i], ncclInt32, D.ifaceNbr[i], c.comm, c.stream);
+        }
+    }
+    if (c.nccl.GroupEnd() != 0) throw CudaError("nccl exchange of the coupled Gauss-Seidel set-up failed");
+    if (D.nIfaces)
+        B2_CUDA(cudaMemcpyAsync(theirs.data(), dTheirs.p, sizeof(long long) * D.nIfaces, cudaMemcpyDeviceToHost, c.stream));
+    for (int i = 0; i < D.nIfaces; i++)
+        if (D.ifaceSize[i])
+            B2_CUDA(cudaMemcpyAsync(nbLevel[i].data(), dLn[i].p, sizeof(int) * D.ifaceSize[i], cudaMemcpyDeviceToHost,
+                                    c.stream));
+    B2_CUDA(cudaStreamSynchronize(c.stream));
+    int lag = D.maxFwdSpan + 1;
+    for (int i = 0; i < D.nIfaces; i++) {
+        if (D.ifacePartner[i] < 0 && theirs[i] < 0) okLocal = false;
+        for (int f = 0; f < D.ifaceSize[i]; f++) lag = std::max(lag, nbLevel[i][f] - myLevel[i][f] + 1);
+    }
+    std::vector<int> all;
+    // rows per wavefront: wide wavefronts are bandwidth-bound, and with sweep s+1 trailing by `lag` wavefronts the
+    // iterate has left L2 before it is read again -- measured at 384^3 on 2 GPUs: 29.5k rows per wavefront 15 % slower
+    // fused than sweep by sweep, 12k rows 15 % faster, 3k rows 45 % faster.  Below the limit the level is latency-bound.
+    static const int maxRows = getenv("B200LS_COUPLED_FUSED_MAX_ROWS") ? atoi(getenv("B200LS_COUPLED_FUSED_MAX_ROWS")) : 16000;
+    allGatherInts({lag, D.nFwdLevels, okLocal ? 1 : 0, D.nCells / std::max(1, D.nFwdLevels)}, all);
+    int maxLevels = 0, rowsPerLevel = 0;
+    bool ok = true;
+    for (int r = 0; r < c.nRanks; r++) {
+        lag = std::max(lag, all[4 * r]);
+        maxLevels = std::max(maxLevels, all[4 * r + 1]);
+        ok = ok && all[4 * r + 2] != 0;
+        rowsPerLevel = std::max(rowsPerLevel, all[4 * r + 3]);
+    }
+    if (!ok || lag >= maxLevels || rowsPerLevel > maxRows) return;
+    M.gsLag = lag;
+    M.gsEpoch = 0;
+    if (D.nIfaces == 0) return;   // nothing coupled here: this rank keeps its local fused sweeps
+    for (int par = 0; par < 2; par++) {
+        std::vector<CoupledView> v(D.nIfaces);
+        for (int i = 0; i < D.nIfaces; i++) {
+            const size_t parOff = size_t(par) * kCoupledSlotSweeps * std::max(D.ifaceSize[i], 1);
+            M.gsSlotRemote[i] = reinterpret_cast<double*>(c.p2p.view.peer[D.ifaceNbr[i]] + theirs[i]);
+            v[i].coeffs = M.bou[i].p;   // allocated before setupIfaceViews; the size never changes for a mesh level
+            v[i].mine = M.gsSlotLocal[i] + parOff;
+            v[i].theirs = M.gsSlotRemote[i] + parOff;
+            v[i].size = D.ifaceSize[i];
+            v[i].pad = 0;
+        }
+        M.gsViews[par].alloc(v.size() * sizeof(CoupledView));
+        B2_CUDA(cudaMemcpyAsync(M.gsViews[par].p, v.data(), v.size() * sizeof(CoupledView), cudaMemcpyHostToDevice,
+                                c.stream));
+        B2_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (D.bRowOf.n != size_t(D.nCells)) {
+        D.bRowOf.alloc(D.nCells);
+        B2_CUDA(cudaMemsetAsync(D.bRowOf.p, 0xFF, sizeof(int) * D.nCells, c.stream));
+        if (D.nBRows) LAUNCH(k_scatter_index, gridRows(D.nBRows), 256, D.bRowOf.p, D.bRowPos.p, D.nBRows);
+    }
+    M.gsCoupled = true;
 }
 
 static void setupIfaceViews(b200ls_matrix_s* m, int level) {
@@ -958,13 +1101,19 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
     const int lag = D.maxFwdSpan + 1;
     const bool pencil = usePencil(D);
     if (pencil) ensurePencilPlanes(m, level);
-    if (!pencil && smoother == B200LS_GAUSS_SEIDEL && D.nIfaces == 0 && nSweeps >= 2 && nSweeps <= kMaxFusedSweeps &&
-        !noFusedGS && 2 * lag <= D.nFwdLevels) {
+    const bool coupledFused = !pencil && smoother == B200LS_GAUSS_SEIDEL && D.nIfaces > 0 && M.gsCoupled &&
+                              nSweeps >= 2 && nSweeps <= 1 + kCoupledSlotSweeps && !noFusedGS;
+    const bool localFused = !pencil && smoother == B200LS_GAUSS_SEIDEL && D.nIfaces == 0 && nSweeps >= 2 &&
+                            nSweeps <= kMaxFusedSweeps && !noFusedGS && 2 * lag <= D.nFwdLevels;
+    if (coupledFused || localFused) {
         // all sweeps in one pipelined launch (k_gs_multi): chain of nLevels + lag*(nSweeps-1) hops instead of
-        // nSweeps*nLevels.  Needs no communication between sweeps, so only levels without processor interfaces.
-        auto it = D.multiSweepTasks.find(nSweeps);
+        // nSweeps*nLevels.  Levels without processor patches need no communication between sweeps; with patches the
+        // neighbours' intermediate values travel through P2P slots inside the kernel (setupCoupledGS).
+        const int useLag = coupledFused ? M.gsLag : lag;
+        const int key = coupledFused ? 1000 + nSweeps : nSweeps;
+        auto it = D.multiSweepTasks.find(key);
         if (it == D.multiSweepTasks.end()) {
-            // bucket the (task, sweep) pairs by tau = level + 2*sweep
+            // bucket the (task, sweep) pairs by tau = level + lag*sweep
             const int nT = int(D.hostFwdTasks.size());
             std::vector<int> levelStart(D.nFwdLevels + 1, nT);
             for (int t = nT - 1; t >= 0; t--) levelStart[D.hostFwdTaskLevel[t]] = t;
@@ -972,21 +1121,21 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
                 if (levelStart[l] == nT) levelStart[l] = levelStart[l + 1];
             std::vector<int4> fused;
             fused.reserve(size_t(nT) * nSweeps);
-            const int maxTau = D.nFwdLevels - 1 + lag * (nSweeps - 1);
+            const int maxTau = D.nFwdLevels - 1 + useLag * (nSweeps - 1);
             for (int tau = 0; tau <= maxTau; tau++) {
                 for (int sw = 0; sw < nSweeps; sw++) {
-                    const int l = tau - lag * sw;
+                    const int l = tau - useLag * sw;
                     if (l < 0 || l >= D.nFwdLevels) continue;
                     for (int t = levelStart[l]; t < levelStart[l + 1]; t++)
                         fused.push_back(make_int4(D.hostFwdTasks[t].x, D.hostFwdTasks[t].y, sw, 0));
                 }
             }
-            DevBuf<int4>& buf = D.multiSweepTasks[nSweeps];
+            DevBuf<int4>& buf = D.multiSweepTasks[key];
             buf.alloc(fused.size());
             if (!fused.empty())
                 B2_CUDA(cudaMemcpyAsync(buf.p, fused.data(), fused.size() * sizeof(int4), cudaMemcpyHostToDevice, S()));
             B2_CUDA(cudaStreamSynchronize(S()));
-            it = D.multiSweepTasks.find(nSweeps);
+            it = D.multiSweepTasks.find(key);
         }
         if (M.gsBufs.n < size_t(nSweeps - 1) * n) M.gsBufs.alloc(size_t(nSweeps - 1) * n);
         fillSentinel(M.gsBufs.p, (nSweeps - 1) * n);
@@ -1007,14 +1156,30 @@ void opSmooth(b200ls_matrix_s* m, int level, int smoother, double*& psi, double*
         for (int sw = 1; sw < nSweeps; sw++) a.X[sw] = M.gsBufs.p + size_t(sw - 1) * n;
         a.X[nSweeps] = spare;
         a.err = ctx().errFlag.p;
+        a.nSweeps = nSweeps;
+        if (coupledFused) {
+            // sweep 0: bPrime = source + bouCoeffs*psi_nbr through the regular halo exchange (which also orders this
+            // call after the neighbours' previous one: the slot parity protocol relies on it)
+            B2_CUDA(cudaMemcpyAsync(M.tmpB.p, source, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+            haloExchange(m, level, psi);
+            ifaceApply(m, level, M.tmpB.p, -1.0);
+            a.b0 = M.tmpB.p;
+            a.bRowOf = D.bRowOf.p;
+            a.bRowPtr = D.bRowPtr.p;
+            a.bEntIface = D.bEntIface.p;
+            a.bEntFace = D.bEntFace.p;
+            a.views = reinterpret_cast<const CoupledView*>(M.gsViews[(M.gsEpoch++) & 1].p);
+        }
         {
             Context& c = ctx();
-            static int occ = 0;
-            if (!occ) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_multi, 256, 0));
-            const int perSM = std::min(occ, c.sweepBlocksPerSM > 0 ? c.sweepBlocksPerSM : 4);
+            static int occ[2] = {0, 0};
+            const void* fn = coupledFused ? (const void*)k_gs_multi<true> : (const void*)k_gs_multi<false>;
+            int& oc = occ[coupledFused ? 1 : 0];
+            if (!oc) B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, fn, 256, 0));
+            const int perSM = std::min(oc, c.sweepBlocksPerSM > 0 ? c.sweepBlocksPerSM : 4);
             const int blocks = std::max(1, std::min(perSM * c.numSMs, (a.nTasks + 7) / 8));
             void* args[] = {&a};
-            B2_CUDA(cudaLaunchCooperativeKernel((const void*)k_gs_multi, dim3(blocks), dim3(256), args, 0, c.stream));
+            B2_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, c.stream));
             c.launches++;
         }
         std::swap(psi, spare);
@@ -1492,79 +1657,81 @@ struct CoarsestArgs {
     const double* cc;       // coupling coefficients (filled by the kernel from gCoef)
 };
 
-// sum over the cells in the order of the distributed reference: every rank's partial sum, then the ranks in order
+// The kernel runs on one warp.  Lane r replays rank r of the distributed reference on block r of the gathered level
+// (cells, faces and coupled-patch entries of that rank); a level that is not gathered is a single block on lane 0.
+// Everything inside a block is sequential in the reference's order; blocks only meet in the sums (rank partials added
+// in rank order, like a linear reduce) and in the coupled-patch update of Amul.
+struct CoarsestBlock {
+    int c0, c1, f0, f1, q0, q1;
+};
+
 template <class F>
-__device__ static double c_sum(const CoarsestArgs& a, F term) {
-    if (!a.gathered) {
-        double s = 0.0;
-        for (int c = 0; c < a.nCells; c++) s += term(c);
-        return s;
-    }
-    double total = 0.0;
-    for (int r = 0; r < a.nRanks; r++) {
-        double s = 0.0;
-        for (int c = a.cellOff[r]; c < a.cellOff[r + 1]; c++) s += term(c);
-        total = r == 0 ? s : total + s;
-    }
+__device__ static double c_sum(const CoarsestArgs& a, const CoarsestBlock& B, F term) {
+    double s = 0.0;
+    for (int c = B.c0; c < B.c1; c++) s += term(c);
+    const int nB = a.gathered ? a.nRanks : 1;
+    double total = __shfl_sync(0xffffffffu, s, 0);
+    for (int r = 1; r < nB; r++) total += __shfl_sync(0xffffffffu, s, r);
     return total;
 }
 
-__device__ static void c_amul(const CoarsestArgs& a, const double* up, const double* lo, const double* dg,
-                              double* out, const double* x) {
-    for (int c = 0; c < a.nCells; c++) out[c] = dg[c] * x[c];
-    for (int f = 0; f < a.nFaces; f++) {
+__device__ static void c_amul(const CoarsestArgs& a, const CoarsestBlock& B, const double* up, const double* lo,
+                              const double* dg, double* out, const double* x) {
+    for (int c = B.c0; c < B.c1; c++) out[c] = dg[c] * x[c];
+    for (int f = B.f0; f < B.f1; f++) {
         out[a.upper[f]] += lo[f] * x[a.lower[f]];
         out[a.lower[f]] += up[f] * x[a.upper[f]];
     }
     // coupled patches after the faces, patch by patch (lduMatrixUpdateMatrixInterfaces.C, processorFvPatchField /
-    // cyclicFvPatchField::updateInterfaceMatrix: result[faceCells] -= coeffs*psiNeighbour)
-    for (int q = 0; q < a.nCouple; q++) out[a.cRow[q]] -= a.cc[q] * x[a.cCol[q]];
+    // cyclicFvPatchField::updateInterfaceMatrix: result[faceCells] -= coeffs*psiNeighbour); x of the other blocks
+    // was written by their lanes
+    __syncwarp();
+    for (int q = B.q0; q < B.q1; q++) out[a.cRow[q]] -= a.cc[q] * x[a.cCol[q]];
+    __syncwarp();   // x may be overwritten by its owners from here on
 }
 
-__device__ static void c_precondition(const CoarsestArgs& a, const double* up, const double* lo, const double* rD,
-                                      double* w, const double* r) {
-    for (int c = 0; c < a.nCells; c++) w[c] = rD[c] * r[c];
-    // faces sorted by upper cell == losort order: walk cells' neighbour-side faces through a stable scan
-    // (DILU uses losort order, DIC plain face order: both give ascending faces per row)
-    for (int f = 0; f < a.nFaces; f++) {
-        // plain face order is valid for both because every row only depends on finished rows (owner-sorted)
-        w[a.upper[f]] -= rD[a.upper[f]] * lo[f] * w[a.lower[f]];
-    }
-    for (int f = a.nFaces - 1; f >= 0; f--) w[a.lower[f]] -= rD[a.lower[f]] * up[f] * w[a.upper[f]];
+__device__ static void c_precondition(const CoarsestArgs& a, const CoarsestBlock& B, const double* up,
+                                      const double* lo, const double* rD, double* w, const double* r) {
+    for (int c = B.c0; c < B.c1; c++) w[c] = rD[c] * r[c];
+    // DILU walks the lower triangle in losort order, DIC in face order: both visit the faces of a row in ascending
+    // order and every row only depends on finished rows (owner-sorted), so plain face order reproduces both
+    for (int f = B.f0; f < B.f1; f++) w[a.upper[f]] -= rD[a.upper[f]] * lo[f] * w[a.lower[f]];
+    for (int f = B.f1 - 1; f >= B.f0; f--) w[a.lower[f]] -= rD[a.lower[f]] * up[f] * w[a.upper[f]];
 }
 
 __device__ static bool c_converged(double fin, double ini, double tol, double relTol) {
     return fin < tol || (relTol > 1e-20 && fin < relTol * ini);
 }
 
-__global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
-    // The arithmetic is one thread's sequential replay of the reference; when the level fits, its vectors,
-    // coefficients and addressing are staged in shared memory first (the loops are chains of dependent loads).
+__global__ void __launch_bounds__(32) k_coarsest_solve(CoarsestArgs a_, int useSmem) {
+    // When the level fits, its vectors, coefficients and addressing are staged in shared memory first (the loops are
+    // chains of dependent loads).
     extern __shared__ double csm[];
     CoarsestArgs a = a_;
     const int n = a.nCells, nF = a.nFaces;
     const int nQ = a.nCouple;
+    const int lane = threadIdx.x;
     if (useSmem) {
         int* sl = reinterpret_cast<int*>(csm + 2 * nF + 12 * n + nQ);
         int* su = sl + nF;
         int* sr = su + nF;
         int* sc = sr + nQ;
         int* so = sc + nQ;
-        for (int f = threadIdx.x; f < nF; f += blockDim.x) {
+        for (int f = lane; f < nF; f += 32) {
             sl[f] = a.lower[f];
             su[f] = a.upper[f];
         }
-        for (int q = threadIdx.x; q < nQ; q += blockDim.x) {
+        for (int q = lane; q < nQ; q += 32) {
             sr[q] = a.cRow[q];
             sc[q] = a.cCol[q];
         }
         if (a.gathered)
-            for (int r = threadIdx.x; r <= a.nRanks; r += blockDim.x) {
+            for (int r = lane; r <= a.nRanks; r += 32) {
                 so[r] = a.cellOff[r];
                 so[a.nRanks + 1 + r] = a.faceOff[r];
                 so[2 * (a.nRanks + 1) + r] = a.coupleOff[r];
             }
-        __syncthreads();
+        __syncwarp();
         a.lower = sl;
         a.upper = su;
         a.cRow = sr;
@@ -1575,7 +1742,14 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
             a.coupleOff = so + 2 * (a.nRanks + 1);
         }
     }
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    CoarsestBlock B = {0, 0, 0, 0, 0, 0};
+    if (a.gathered) {
+        if (lane < a.nRanks)
+            B = {a.cellOff[lane], a.cellOff[lane + 1], a.faceOff[lane], a.faceOff[lane + 1], a.coupleOff[lane],
+                 a.coupleOff[lane + 1]};
+    } else if (lane == 0) {
+        B = {0, n, 0, nF, 0, 0};
+    }
     double* w = useSmem ? csm : a.work;
     double* up = w;            w += nF;
     double* lo = w;            w += nF;
@@ -1595,36 +1769,34 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
     a.cc = cc;
     if (a.gathered) {
         // per-rank block of gCoef: [diag (maxCells) | upper (maxFaces) | lower (maxFaces) | coupling (maxCouple)]
-        for (int r = 0; r < a.nRanks; r++) {
-            const double* blk = a.gCoef + size_t(r) * a.blockLen;
-            const double* sb = a.gSrc + size_t(r) * a.maxCells;
-            const int c0 = a.cellOff[r], f0 = a.faceOff[r], q0 = a.coupleOff[r];
-            for (int c = c0; c < a.cellOff[r + 1]; c++) {
-                dg[c] = blk[c - c0];
-                b[c] = sb[c - c0];
-                x[c] = 0.0;
-            }
-            for (int f = f0; f < a.faceOff[r + 1]; f++) {
-                up[f] = blk[a.maxCells + f - f0];
-                lo[f] = blk[a.maxCells + a.maxFaces + f - f0];
-            }
-            for (int q = q0; q < a.coupleOff[r + 1]; q++) cc[q] = blk[a.maxCells + 2 * a.maxFaces + q - q0];
+        const double* blk = a.gCoef + size_t(lane) * a.blockLen;
+        const double* sb = a.gSrc + size_t(lane) * a.maxCells;
+        for (int c = B.c0; c < B.c1; c++) {
+            dg[c] = blk[c - B.c0];
+            b[c] = sb[c - B.c0];
+            x[c] = 0.0;
         }
+        for (int f = B.f0; f < B.f1; f++) {
+            up[f] = blk[a.maxCells + f - B.f0];
+            lo[f] = blk[a.maxCells + a.maxFaces + f - B.f0];
+        }
+        for (int q = B.q0; q < B.q1; q++) cc[q] = blk[a.maxCells + 2 * a.maxFaces + q - B.q0];
     } else {
-        for (int f = 0; f < nF; f++) {
+        for (int f = B.f0; f < B.f1; f++) {
             up[f] = a.Uval[a.Uidx[f]];
             lo[f] = a.Lval[a.Lidx[f]];
         }
-        for (int c = 0; c < n; c++) {
+        for (int c = B.c0; c < B.c1; c++) {
             dg[c] = a.diag[a.ipos[c]];
             b[c] = a.source[a.ipos[c]];
             x[c] = 0.0;
         }
     }
+    __syncwarp();
     const double vSmall = 2.2250738585072014e-308;
 
     if (nF == 0 && !a.gathered) {
-        for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = b[c] / dg[c];   // diagonalSolver.C:66
+        for (int c = B.c0; c < B.c1; c++) a.psi[a.ipos[c]] = b[c] / dg[c];   // diagonalSolver.C:66
         return;
     }
 
@@ -1632,30 +1804,30 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
     double* Ax = v0;
     double* r = v1;
     double* tmp = v2;
-    c_amul(a, up, lo, dg, Ax, x);
-    for (int c = 0; c < n; c++) r[c] = b[c] - Ax[c];
-    for (int c = 0; c < n; c++) tmp[c] = dg[c];
-    for (int f = 0; f < nF; f++) {
+    c_amul(a, B, up, lo, dg, Ax, x);
+    for (int c = B.c0; c < B.c1; c++) r[c] = b[c] - Ax[c];
+    for (int c = B.c0; c < B.c1; c++) tmp[c] = dg[c];
+    for (int f = B.f0; f < B.f1; f++) {
         tmp[a.upper[f]] += lo[f];
         tmp[a.lower[f]] += up[f];
     }
-    for (int q = 0; q < nQ; q++) tmp[a.cRow[q]] -= cc[q];   // lduMatrix::sumA, coupled patches (lduMatrixATmul.C:187-198)
-    const double sumX = c_sum(a, [&](int c) { return x[c]; });
+    for (int q = B.q0; q < B.q1; q++) tmp[a.cRow[q]] -= cc[q];   // lduMatrix::sumA, coupled patches (lduMatrixATmul.C:187-198)
+    const double sumX = c_sum(a, B, [&](int c) { return x[c]; });
     const double xbar = sumX / n;
-    double nfac = c_sum(a, [&](int c) {
+    double nfac = c_sum(a, B, [&](int c) {
         const double t = tmp[c] * xbar;
         return fabs(Ax[c] - t) + fabs(b[c] - t);
     });
     nfac += 1e-20;
-    double sm = c_sum(a, [&](int c) { return fabs(r[c]); });
+    double sm = c_sum(a, B, [&](int c) { return fabs(r[c]); });
     const double ini = sm / nfac;
     double fin = ini;
 
     if (!c_converged(fin, ini, a.tolerance, a.relTol)) {
         // reciprocal preconditioned diagonal
-        for (int c = 0; c < n; c++) rD[c] = dg[c];
-        for (int f = 0; f < nF; f++) rD[a.upper[f]] -= up[f] * lo[f] / rD[a.lower[f]];
-        for (int c = 0; c < n; c++) rD[c] = 1.0 / rD[c];
+        for (int c = B.c0; c < B.c1; c++) rD[c] = dg[c];
+        for (int f = B.f0; f < B.f1; f++) rD[a.upper[f]] -= up[f] * lo[f] / rD[a.lower[f]];
+        for (int c = B.c0; c < B.c1; c++) rD[c] = 1.0 / rD[c];
 
         if (a.symmetric) {
             double* p = v3;
@@ -1664,23 +1836,23 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
             int it = 0;
             do {
                 wArAold = wArA;
-                c_precondition(a, up, lo, rD, wA, r);
-                wArA = c_sum(a, [&](int c) { return wA[c] * r[c]; });
+                c_precondition(a, B, up, lo, rD, wA, r);
+                wArA = c_sum(a, B, [&](int c) { return wA[c] * r[c]; });
                 if (it == 0) {
-                    for (int c = 0; c < n; c++) p[c] = wA[c];
+                    for (int c = B.c0; c < B.c1; c++) p[c] = wA[c];
                 } else {
                     const double beta = wArA / wArAold;
-                    for (int c = 0; c < n; c++) p[c] = wA[c] + beta * p[c];
+                    for (int c = B.c0; c < B.c1; c++) p[c] = wA[c] + beta * p[c];
                 }
-                c_amul(a, up, lo, dg, wA, p);
-                const double wApA = c_sum(a, [&](int c) { return wA[c] * p[c]; });
+                c_amul(a, B, up, lo, dg, wA, p);
+                const double wApA = c_sum(a, B, [&](int c) { return wA[c] * p[c]; });
                 if (fabs(wApA) / nfac < vSmall) break;
                 const double alpha = wArA / wApA;
-                for (int c = 0; c < n; c++) {
+                for (int c = B.c0; c < B.c1; c++) {
                     x[c] += alpha * p[c];
                     r[c] -= alpha * wA[c];
                 }
-                sm = c_sum(a, [&](int c) { return fabs(r[c]); });
+                sm = c_sum(a, B, [&](int c) { return fabs(r[c]); });
                 fin = sm / nfac;
             } while (++it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
         } else {
@@ -1691,50 +1863,50 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
             double* z = v5;
             double* t = v6;
             double* r0 = v7;
-            for (int c = 0; c < n; c++) r0[c] = r[c];
+            for (int c = B.c0; c < B.c1; c++) r0[c] = r[c];
             double rho = 0, alpha = 0, omega = 0;
             int it = 0;
             do {
                 const double rhoOld = rho;
-                rho = c_sum(a, [&](int c) { return r0[c] * r[c]; });
+                rho = c_sum(a, B, [&](int c) { return r0[c] * r[c]; });
                 if (fabs(rho) < vSmall) break;
                 if (it == 0) {
-                    for (int c = 0; c < n; c++) p[c] = r[c];
+                    for (int c = B.c0; c < B.c1; c++) p[c] = r[c];
                 } else {
                     if (fabs(omega) < vSmall) break;
                     const double beta = (rho / rhoOld) * (alpha / omega);
-                    for (int c = 0; c < n; c++) p[c] = r[c] + beta * (p[c] - omega * AyA[c]);
+                    for (int c = B.c0; c < B.c1; c++) p[c] = r[c] + beta * (p[c] - omega * AyA[c]);
                 }
-                c_precondition(a, up, lo, rD, y, p);
-                c_amul(a, up, lo, dg, AyA, y);
-                const double r0AyA = c_sum(a, [&](int c) { return r0[c] * AyA[c]; });
+                c_precondition(a, B, up, lo, rD, y, p);
+                c_amul(a, B, up, lo, dg, AyA, y);
+                const double r0AyA = c_sum(a, B, [&](int c) { return r0[c] * AyA[c]; });
                 alpha = rho / r0AyA;
-                for (int c = 0; c < n; c++) s[c] = r[c] - alpha * AyA[c];
-                sm = c_sum(a, [&](int c) { return fabs(s[c]); });
+                for (int c = B.c0; c < B.c1; c++) s[c] = r[c] - alpha * AyA[c];
+                sm = c_sum(a, B, [&](int c) { return fabs(s[c]); });
                 fin = sm / nfac;
                 if (++it >= 0 && c_converged(fin, ini, a.tolerance, a.relTol)) {
-                    for (int c = 0; c < n; c++) x[c] += alpha * y[c];
+                    for (int c = B.c0; c < B.c1; c++) x[c] += alpha * y[c];
                     break;
                 }
-                c_precondition(a, up, lo, rD, z, s);
-                c_amul(a, up, lo, dg, t, z);
-                const double tt = c_sum(a, [&](int c) { return t[c] * t[c]; });
-                const double ts = c_sum(a, [&](int c) { return t[c] * s[c]; });
+                c_precondition(a, B, up, lo, rD, z, s);
+                c_amul(a, B, up, lo, dg, t, z);
+                const double tt = c_sum(a, B, [&](int c) { return t[c] * t[c]; });
+                const double ts = c_sum(a, B, [&](int c) { return t[c] * s[c]; });
                 omega = ts / tt;
-                for (int c = 0; c < n; c++) {
+                for (int c = B.c0; c < B.c1; c++) {
                     x[c] += alpha * y[c] + omega * z[c];
                     r[c] = s[c] - omega * t[c];
                 }
-                sm = c_sum(a, [&](int c) { return fabs(r[c]); });
+                sm = c_sum(a, B, [&](int c) { return fabs(r[c]); });
                 fin = sm / nfac;
             } while (it < a.maxIter && !c_converged(fin, ini, a.tolerance, a.relTol));
         }
     }
     if (a.gathered) {
-        const int c0 = a.cellOff[a.myRank];
-        for (int c = c0; c < a.cellOff[a.myRank + 1]; c++) a.psi[a.ipos[c - c0]] = x[c];
+        if (lane == a.myRank)
+            for (int c = B.c0; c < B.c1; c++) a.psi[a.ipos[c - B.c0]] = x[c];
     } else {
-        for (int c = 0; c < n; c++) a.psi[a.ipos[c]] = x[c];
+        for (int c = B.c0; c < B.c1; c++) a.psi[a.ipos[c]] = x[c];
     }
 }
 
@@ -1745,22 +1917,6 @@ __global__ void k_coarsest_solve(CoarsestArgs a_, int useSmem) {
 // (topology once per mesh, coefficients once per matrix, the source once per cycle: one all-gather) and replays the
 // distributed iteration in k_coarsest_solve: block-local DIC/DILU (faces never cross ranks), couplings as explicit
 // off-diagonal entries, sums rank by rank.  All ranks compute the same numbers; each keeps its own slice.
-
-static void allGatherInts(const std::vector<int>& mine, std::vector<int>& all) {
-    Context& c = ctx();
-    if (c.nRanks == 1) {
-        all = mine;
-        return;
-    }
-    DevBuf<int> snd, rcv;
-    snd.upload(mine, c.stream);
-    rcv.alloc(mine.size() * c.nRanks);
-    int r = c.nccl.AllGather(snd.p, rcv.p, mine.size(), ncclInt32, c.comm, c.stream);
-    if (r != 0) throw CudaError(std::string("ncclAllGather: ") + c.nccl.GetErrorString((ncclResult_t)r));
-    all.resize(mine.size() * c.nRanks);
-    B2_CUDA(cudaMemcpyAsync(all.data(), rcv.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    B2_CUDA(cudaStreamSynchronize(c.stream));
-}
 
 static constexpr int kMaxGatheredCells = 4096;
 

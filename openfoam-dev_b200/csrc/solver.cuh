@@ -30,6 +30,12 @@ struct MatLevel {
     std::vector<unsigned long long*> p2pLocalFlag;
     DevBuf<unsigned int> p2pTickets;                    // one last-block ticket per interface
     unsigned long long haloEpoch = 0;
+    // fused Gauss-Seidel sweeps across processor patches (setupCoupledGS)
+    bool gsCoupled = false;
+    int gsLag = 0;
+    unsigned long long gsEpoch = 0;
+    std::vector<double*> gsSlotLocal, gsSlotRemote;
+    DevBuf<unsigned char> gsViews[2];                   // CoupledView[nIfaces] per call parity
     // level work vectors (GAMG): correction, source, scratch
     DevBuf<double> corr, src, tmpA, tmpB, tmpC;
     DevBuf<double> gsBufs;          // intermediate iterates of the fused multi-sweep Gauss-Seidel kernel
