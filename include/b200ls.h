@@ -144,6 +144,19 @@ void b200ls_matrix_free(b200ls_matrix_t m);
 int b200ls_matrix_set(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
                       const double* const* ifaceBouCoeffs, const double* const* ifaceIntCoeffs);
 
+/* The same with DEVICE pointers (diag/upper/lower and every bou[i]/inn[i] live on this GPU, reference cell / face
+ * order; the pointer arrays themselves are host memory): the coefficients of a GPU-side assembly never visit the host.
+ * Replaces the host copies of fvMatrix::solveSegregated's arguments (fvMatrixSolve.C:150-190). */
+int b200ls_matrix_set_dev(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
+                          const double* const* ifaceBouCoeffs, const double* const* ifaceIntCoeffs);
+/* b200ls_matrix_set that first compares a 64-bit fingerprint of all arrays with the one of the coefficients the
+ * matrix already holds: when equal nothing is copied and the factorisation / coarse-level matrices stay valid
+ * (*changed = 0).  PISO solves the same pressure matrix once per corrector with a new source only
+ * (pEqn.H of icoFoam: the matrix is rebuilt from the same rAU). */
+int b200ls_matrix_set_if_changed(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
+                                 const double* const* ifaceBouCoeffs, const double* const* ifaceIntCoeffs,
+                                 int32_t* changed);
+
 int b200ls_amul(b200ls_matrix_t m, const double* psi, double* Apsi);
 int b200ls_residual(b200ls_matrix_t m, const double* psi, const double* source, double* rA);
 int b200ls_sum_a(b200ls_matrix_t m, double* sumA);

@@ -29,6 +29,7 @@ EXPORTS = [
     "b200ls_init", "b200ls_set_host_comm", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
     "b200ls_mesh_create", "b200ls_mesh_free", "b200ls_mesh_get_i32", "b200ls_mesh_get_iface_i32", "b200ls_mesh_n_levels",
     "b200ls_agglomerate", "b200ls_agglomerate_from_maps", "b200ls_matrix_create", "b200ls_matrix_free", "b200ls_matrix_set",
+    "b200ls_matrix_set_dev", "b200ls_matrix_set_if_changed",
     "b200ls_amul", "b200ls_residual", "b200ls_sum_a", "b200ls_precondition", "b200ls_reciprocal_d",
     "b200ls_smooth", "b200ls_controls_default", "b200ls_solve", "b200ls_solve_dev", "b200ls_time_kernel",
 ]
@@ -88,6 +89,8 @@ def lib():
     L.b200ls_matrix_create.argtypes = [p]
     L.b200ls_matrix_free.argtypes = [p]
     L.b200ls_matrix_set.argtypes = [p, p, p, p, p, p]
+    L.b200ls_matrix_set_dev.argtypes = [p, p, p, p, p, p]
+    L.b200ls_matrix_set_if_changed.argtypes = [p, p, p, p, p, p, p]
     L.b200ls_amul.argtypes = [p, p, p]
     L.b200ls_residual.argtypes = [p, p, p, p]
     L.b200ls_sum_a.argtypes = [p, p]
@@ -276,6 +279,30 @@ class Matrix:
         ip = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in inn])
         _check(lib().b200ls_matrix_set(self.h, _ptr(d), _ptr(u), _ptr(lo), C.cast(bp, C.c_void_p),
                                        C.cast(ip, C.c_void_p)))
+
+    def set_if_changed(self, diag, upper, lower=None, bou_coeffs=(), int_coeffs=()):
+        """b200ls_matrix_set_if_changed: returns True when the coefficients were uploaded, False when the matrix
+        already held exactly these."""
+        d, u = _f64(diag), _f64(upper)
+        lo = _f64(lower) if lower is not None else None
+        bou = [_f64(b) for b in bou_coeffs]
+        inn = [_f64(b) for b in int_coeffs]
+        n_if = len(bou)
+        bp = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in bou])
+        ip = (C.c_void_p * max(n_if, 1))(*[a.ctypes.data for a in inn])
+        changed = C.c_int32(-1)
+        _check(lib().b200ls_matrix_set_if_changed(self.h, _ptr(d), _ptr(u), _ptr(lo), C.cast(bp, C.c_void_p),
+                                                  C.cast(ip, C.c_void_p), C.byref(changed)))
+        return bool(changed.value)
+
+    def set_dev(self, diag_ptr, upper_ptr, lower_ptr=None, bou_ptrs=(), int_ptrs=()):
+        """b200ls_matrix_set_dev: raw device addresses (e.g. torch tensors' data_ptr()) in reference order."""
+        n_if = len(bou_ptrs)
+        bp = (C.c_void_p * max(n_if, 1))(*bou_ptrs)
+        ip = (C.c_void_p * max(n_if, 1))(*int_ptrs)
+        _check(lib().b200ls_matrix_set_dev(self.h, C.c_void_p(diag_ptr), C.c_void_p(upper_ptr),
+                                           C.c_void_p(lower_ptr) if lower_ptr else None,
+                                           C.cast(bp, C.c_void_p), C.cast(ip, C.c_void_p)))
 
     def amul(self, psi):
         x = _f64(psi)

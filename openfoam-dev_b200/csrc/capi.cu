@@ -256,6 +256,7 @@ void b200ls_finalize(void) {
     cudaStreamSynchronize(c.stream);
     for (void* q : c.p2p.opened) cudaIpcCloseMemHandle(q);
     c.p2p.opened.clear();
+    c.p2p.freeBlocks.clear();
     c.p2p.enabled = false;
     if (c.comm) {
         c.nccl.CommDestroy(c.comm);
@@ -430,6 +431,57 @@ int b200ls_matrix_set(b200ls_matrix_t m, const double* diag, const double* upper
     return guarded([&] {
         if (!m) throw CudaError("null matrix");
         matrixSet(m, diag, upper, lower, bou, inn);
+    });
+}
+
+int b200ls_matrix_set_dev(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
+                          const double* const* bou, const double* const* inn) {
+    return guarded([&] {
+        if (!m) throw CudaError("null matrix");
+        matrixSet(m, diag, upper, lower, bou, inn, true);
+    });
+}
+
+// 64-bit fingerprint of host arrays: four independent multiply-rotate lanes over 32-byte blocks (memory-bound)
+static inline unsigned long long fpMix(unsigned long long h, unsigned long long v) {
+    h ^= v * 0x9E3779B97F4A7C15ull;
+    h = (h << 27) | (h >> 37);
+    return h * 0x94D049BB133111EBull + 0x2545F4914F6CDD1Dull;
+}
+static unsigned long long fingerprintOf(const double* data, size_t n, unsigned long long seed) {
+    unsigned long long h0 = seed, h1 = seed ^ 0xA5A5A5A5A5A5A5A5ull, h2 = ~seed, h3 = seed + 0x632BE59BD9B4E019ull;
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(data);
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        h0 = fpMix(h0, w[i]);
+        h1 = fpMix(h1, w[i + 1]);
+        h2 = fpMix(h2, w[i + 2]);
+        h3 = fpMix(h3, w[i + 3]);
+    }
+    for (; i < n; i++) h0 = fpMix(h0, w[i]);
+    return fpMix(fpMix(fpMix(fpMix(n, h0), h1), h2), h3);
+}
+
+int b200ls_matrix_set_if_changed(b200ls_matrix_t m, const double* diag, const double* upper, const double* lower,
+                                 const double* const* bou, const double* const* inn, int32_t* changed) {
+    return guarded([&] {
+        if (!m) throw CudaError("null matrix");
+        const LevelHost& L = m->mesh->host.levels[0];
+        unsigned long long h = fingerprintOf(diag, L.nCells, 1);
+        h = fpMix(h, fingerprintOf(upper, L.nFaces, 2));
+        h = fpMix(h, lower ? fingerprintOf(lower, L.nFaces, 3) : 0x5bd1e995ull);
+        for (size_t i = 0; i < L.interfaces.size(); i++) {
+            const size_t n = L.interfaces[i].faceCells.size();
+            h = fpMix(h, fingerprintOf(bou[i], n, 4 + 2 * i));
+            h = fpMix(h, fingerprintOf(inn[i], n, 5 + 2 * i));
+        }
+        const bool same = m->valuesSet && m->hasFingerprint && m->fingerprint == h &&
+                          m->meshGeneration == m->mesh->generation && m->symmetric == (lower == nullptr);
+        if (changed) *changed = same ? 0 : 1;
+        if (same) return;
+        matrixSet(m, diag, upper, lower, bou, inn, false);
+        m->fingerprint = h;
+        m->hasFingerprint = true;
     });
 }
 

@@ -100,6 +100,7 @@ struct P2PState {
     P2PView view{};
     unsigned long long reduceEpoch = 0;
     std::vector<void*> opened;                            // cudaIpcOpenMemHandle results
+    std::multimap<size_t, char*> freeBlocks;              // arena blocks handed back by destroyed matrices, by size
 };
 
 struct Context {

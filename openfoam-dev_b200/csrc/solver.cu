@@ -468,14 +468,34 @@ static void syncMatrixWithMesh(b200ls_matrix_s* m) {
 
 static void setupCoupledGS(b200ls_matrix_s* m, int level);
 static void fillSentinel(double* p, int n);
-// bump allocation inside this rank's IPC arena; returns nullptr when the arena is exhausted
-static char* arenaAlloc(size_t bytes) {
+// Allocation inside this rank's IPC arena for one matrix level: a block of the same size handed back by a destroyed
+// matrix if there is one (zeroed again: epoch flags restart at 0), else bump allocation; nullptr when the arena is
+// exhausted.  Matrices are created and destroyed in the same order on every rank, so the choice is the same everywhere;
+// the neighbours learn the new offsets in the exchange that follows, which is stream-ordered after the memset.
+static char* arenaAlloc(MatLevel& M, size_t bytes) {
     P2PState& P = ctx().p2p;
     const size_t aligned = (bytes + 255) & ~size_t(255);
-    if (!P.enabled || P.bump + aligned > P.arenaBytes) return nullptr;
-    char* p = P.arena + P.bump;
-    P.bump += aligned;
+    if (!P.enabled) return nullptr;
+    char* p = nullptr;
+    auto it = P.freeBlocks.find(aligned);
+    if (it != P.freeBlocks.end()) {
+        p = it->second;
+        P.freeBlocks.erase(it);
+        B2_CUDA(cudaMemsetAsync(p, 0, aligned, S()));
+    } else {
+        if (P.bump + aligned > P.arenaBytes) return nullptr;
+        p = P.arena + P.bump;
+        P.bump += aligned;
+    }
+    M.arenaBlocks.emplace_back(p, aligned);
     return p;
+}
+void arenaRelease(std::vector<std::pair<char*, size_t>>& blocks) {
+    if (blocks.empty()) return;
+    P2PState& P = ctx().p2p;
+    if (P.enabled)
+        for (auto& b : blocks) P.freeBlocks.emplace(b.second, b.first);
+    blocks.clear();
 }
 
 static void allGatherInts(const std::vector<int>& mine, std::vector<int>& all) {
@@ -534,8 +554,8 @@ static void setupP2PHalos(b200ls_matrix_s* m, int level) {
             mine[2 * i] = mine[2 * i + 1] = theirs[2 * i] = theirs[2 * i + 1] = 0;
             continue;
         }
-        char* r = arenaAlloc(size_t(2) * std::max(D.ifaceSize[i], 1) * sizeof(double));
-        char* f = arenaAlloc(sizeof(unsigned long long));
+        char* r = arenaAlloc(M, size_t(2) * std::max(D.ifaceSize[i], 1) * sizeof(double));
+        char* f = arenaAlloc(M, sizeof(unsigned long long));
         if (!r || !f) ok = false;
         M.p2pLocalRecv[i] = reinterpret_cast<double*>(r);
         M.p2pLocalFlag[i] = reinterpret_cast<unsigned long long*>(f);
@@ -615,7 +635,7 @@ static void setupCoupledGS(b200ls_matrix_s* m, int level) {
     std::vector<long long> mine(std::max(D.nIfaces, 1), -1), theirs(std::max(D.nIfaces, 1), -1);
     for (int i = 0; i < D.nIfaces && okLocal; i++) {
         const size_t cnt = size_t(2) * kCoupledSlotSweeps * std::max(D.ifaceSize[i], 1);
-        char* q = arenaAlloc(cnt * sizeof(double));
+        char* q = arenaAlloc(M, cnt * sizeof(double));
         if (!q) {
             okLocal = false;
             break;
@@ -729,29 +749,43 @@ static void setupIfaceViews(b200ls_matrix_s* m, int level) {
 }
 
 void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, const double* lower,
-               const double* const* bou, const double* const* inn) {
+               const double* const* bou, const double* const* inn, bool devicePointers) {
     syncMatrixWithMesh(m);
     DevLevel& D = DL(m, 0);
     MatLevel& M = m->levels[0];
     const int nC = D.nCells, nF = D.nFaces;
     m->symmetric = (lower == nullptr);
-    m->stageA.alloc(std::max(nC, nF));
+    m->hasFingerprint = false;
     M.diag.alloc(nC);
     M.vals.alloc(size_t(2) * nF);
     cudaStream_t s = S();
+    // reference order -> native layout; host arrays pass through a staging buffer, device arrays are gathered in place
+    const double *dDiag = diag, *dUpper = upper, *dLower = lower;
+    if (!devicePointers) {
+        m->stageA.alloc(std::max(nC, nF));
+        if (lower) m->stageB.alloc(std::max(nC, nF));
+    }
     if (nC) {
-        B2_CUDA(cudaMemcpyAsync(m->stageA.p, diag, sizeof(double) * nC, cudaMemcpyHostToDevice, s));
-        LAUNCH(k_gather, gridStride(nC), 256, M.diag.p, m->stageA.p, D.perm.p, nC);
+        if (!devicePointers) {
+            B2_CUDA(cudaMemcpyAsync(m->stageA.p, diag, sizeof(double) * nC, cudaMemcpyHostToDevice, s));
+            dDiag = m->stageA.p;
+        }
+        LAUNCH(k_gather, gridStride(nC), 256, M.diag.p, dDiag, D.perm.p, nC);
     }
     if (nF) {
-        B2_CUDA(cudaMemcpyAsync(m->stageA.p, upper, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
-        LAUNCH(k_gather, gridStride(nF), 256, M.Uval(), m->stageA.p, D.Uface.p, nF);
+        if (!devicePointers) {
+            B2_CUDA(cudaMemcpyAsync(m->stageA.p, upper, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+            dUpper = m->stageA.p;
+        }
+        LAUNCH(k_gather, gridStride(nF), 256, M.Uval(), dUpper, D.Uface.p, nF);
         if (lower) {
-            m->stageB.alloc(std::max(nC, nF));
-            B2_CUDA(cudaMemcpyAsync(m->stageB.p, lower, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
-            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), m->stageB.p, D.Lface.p, nF);
+            if (!devicePointers) {
+                B2_CUDA(cudaMemcpyAsync(m->stageB.p, lower, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+                dLower = m->stageB.p;
+            }
+            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), dLower, D.Lface.p, nF);
         } else {
-            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), m->stageA.p, D.Lface.p, nF);
+            LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), dUpper, D.Lface.p, nF);
         }
     }
     M.bou.resize(D.nIfaces);
@@ -762,8 +796,9 @@ void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, cons
         M.bou[i].alloc(D.ifaceSize[i]);
         M.inn[i].alloc(D.ifaceSize[i]);
         if (D.ifaceSize[i]) {
-            B2_CUDA(cudaMemcpyAsync(M.bou[i].p, bou[i], sizeof(double) * D.ifaceSize[i], cudaMemcpyHostToDevice, s));
-            B2_CUDA(cudaMemcpyAsync(M.inn[i].p, inn[i], sizeof(double) * D.ifaceSize[i], cudaMemcpyHostToDevice, s));
+            const cudaMemcpyKind kind = devicePointers ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            B2_CUDA(cudaMemcpyAsync(M.bou[i].p, bou[i], sizeof(double) * D.ifaceSize[i], kind, s));
+            B2_CUDA(cudaMemcpyAsync(M.inn[i].p, inn[i], sizeof(double) * D.ifaceSize[i], kind, s));
         }
     }
     setupIfaceViews(m, 0);

@@ -7,7 +7,14 @@
 namespace b200ls {
 
 // Coefficients of one level in the native layout
+void arenaRelease(std::vector<std::pair<char*, size_t>>& blocks);
+
 struct MatLevel {
+    MatLevel() = default;
+    MatLevel(MatLevel&&) = default;
+    MatLevel& operator=(MatLevel&&) = default;
+    ~MatLevel() { arenaRelease(arenaBlocks); }
+    std::vector<std::pair<char*, size_t>> arenaBlocks;   // P2P arena blocks of this level (returned on destruction)
     DevBuf<double> diag;
     DevBuf<double> vals;            // [Uval (nFaces) | Lval (nFaces)]
     DevBuf<double> rD;              // DIC/DILU reciprocal diagonal
@@ -57,6 +64,8 @@ struct b200ls_matrix_s {
     bool symmetric = true;
     bool valuesSet = false;
     bool coarseValid = false;       // coarse-level matrices match the current coefficients
+    bool hasFingerprint = false;    // b200ls_matrix_set_if_changed: fingerprint of the coefficients held
+    unsigned long long fingerprint = 0;
     std::vector<b200ls::MatLevel> levels;
     std::map<std::string, b200ls::Vec> vecs;     // named finest-level work vectors (position order)
     b200ls::DevBuf<double> stageA, stageB;       // cell-order staging (H2D / D2H)
@@ -71,7 +80,7 @@ namespace b200ls {
 
 void ensureDeviceMesh(b200ls_mesh_s* mesh);
 void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, const double* lower,
-               const double* const* bou, const double* const* inn);
+               const double* const* bou, const double* const* inn, bool devicePointers = false);
 void opAmul(b200ls_matrix_s* m, int level, double* out, const double* x);
 void opResidual(b200ls_matrix_s* m, int level, double* out, const double* x, const double* b);
 void opSumA(b200ls_matrix_s* m, int level, double* out);

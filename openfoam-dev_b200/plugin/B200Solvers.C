@@ -315,18 +315,23 @@ static void uploadCoeffs
         }
     }
 
+    // PISO solves the same pressure matrix once per corrector: unchanged
+    // coefficients are not uploaded again and the factorisation / GAMG
+    // coarse-level matrices on the device stay valid
+    int32_t changed = 1;
     check
     (
-        b200ls_matrix_set
+        b200ls_matrix_set_if_changed
         (
             e.matrix,
             matrix.diag().begin(),
             matrix.upper().begin(),
             matrix.asymmetric() ? matrix.lower().begin() : nullptr,
             bou.data(),
-            inn.data()
+            inn.data(),
+            &changed
         ),
-        "b200ls_matrix_set"
+        "b200ls_matrix_set_if_changed"
     );
 }
 
