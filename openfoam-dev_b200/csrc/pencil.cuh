@@ -9,15 +9,19 @@
 // so the dependency chain of a step is one multiply and one subtract (the own-row term is the last one in the
 // reference's accumulation order), and only tile-to-tile hand-overs go through L2: nJ + nK hops (48 at 128^3).
 //
-// A CTA is a warp pair:
-//   * the CHAIN warp does the arithmetic, in exactly the order of kernels.cuh / the reference, and publishes every
-//     result with one 8-byte L2 store (sentinel protocol, as the wavefront kernels);
+// A CTA is a pipeline of five warps around one tile:
 //   * the HELPER warp (a) streams the per-row operands, which are contiguous per (tile, i-range) in the tile-major
-//     layout, into a shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx, one elected
+//     layout, into a shared-memory raw ring with bulk async copies (cp.async.bulk + mbarrier complete_tx, one elected
 //     lane), and (b) fetches the values the face lanes need from the neighbouring tiles a window of steps ahead:
-//     polls them in L2 until none is the sentinel, deposits them in a small shared-memory ring indexed by step and
-//     publishes its progress (release/acquire on a shared-memory word).  The chain warp never touches global memory
-//     except for its stores.
+//     polls them in L2 until none is the sentinel and deposits them in a small ring, one mbarrier per step;
+//   * two PREP warps turn raw operands + neighbour values into per-step records (2-4 16-byte vectors per lane:
+//     pre-multiplied coefficients, right-hand side), so that
+//   * the CHAIN warp does nothing but: load record, two shuffles, the reference's multiply-subtract sequence in
+//     exactly the order of kernels.cuh / the reference, store the result to the result ring;
+//   * the WRITER warp drains the result ring: face lanes publish at once with one 8-byte L2 store (sentinel protocol,
+//     as the wavefront kernels), complete rows are stored coalesced, the other buffer is re-armed, the fused dot
+//     product accumulated.
+// Hand-overs inside the CTA are mbarrier full/empty pairs (one elected lane arrives after __syncwarp()).
 // Backward sweeps run the same code on reflected coordinates.
 //
 // Reference order per row (bit-exact, -fmad=false):
