@@ -767,20 +767,20 @@ void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, cons
     }
     if (nC) {
         if (!devicePointers) {
-            B2_CUDA(cudaMemcpyAsync(m->stageA.p, diag, sizeof(double) * nC, cudaMemcpyHostToDevice, s));
+            h2dBytes(m->stageA.p, diag, sizeof(double) * nC);
             dDiag = m->stageA.p;
         }
         LAUNCH(k_gather, gridStride(nC), 256, M.diag.p, dDiag, D.perm.p, nC);
     }
     if (nF) {
         if (!devicePointers) {
-            B2_CUDA(cudaMemcpyAsync(m->stageA.p, upper, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+            h2dBytes(m->stageA.p, upper, sizeof(double) * nF);
             dUpper = m->stageA.p;
         }
         LAUNCH(k_gather, gridStride(nF), 256, M.Uval(), dUpper, D.Uface.p, nF);
         if (lower) {
             if (!devicePointers) {
-                B2_CUDA(cudaMemcpyAsync(m->stageB.p, lower, sizeof(double) * nF, cudaMemcpyHostToDevice, s));
+                h2dBytes(m->stageB.p, lower, sizeof(double) * nF);
                 dLower = m->stageB.p;
             }
             LAUNCH(k_gather, gridStride(nF), 256, M.Lval(nF), dLower, D.Lface.p, nF);

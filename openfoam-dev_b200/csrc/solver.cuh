@@ -79,6 +79,9 @@ struct b200ls_matrix_s {
 namespace b200ls {
 
 void ensureDeviceMesh(b200ls_mesh_s* mesh);
+// copies between (pageable) host memory and the device, ordered on the solver stream (capi.cu: CopyPool)
+void h2dBytes(void* dev, const void* host, size_t bytes);
+void d2hBytes(void* host, const void* dev, size_t bytes);
 void matrixSet(b200ls_matrix_s* m, const double* diag, const double* upper, const double* lower,
                const double* const* bou, const double* const* inn, bool devicePointers = false);
 void opAmul(b200ls_matrix_s* m, int level, double* out, const double* x);
