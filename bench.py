@@ -397,6 +397,25 @@ def bench_extras(capi, cases, decompose, rank, world, barrier):
                                       "cavity 256^3 p-equation (BASELINE configs[2]), GAMG + GaussSeidel, 3 V-cycles")
         del s256
 
+    if world == 1:
+        # configs[4] stand-in: asymmetric 2-D convection-diffusion of pitzDaily-refined size, PBiCGStab+DILU
+        n2 = 3538
+        s2 = cases.convection_diffusion(n2, n2, 1, dt_coeff=50.0)
+        mesh, mat = capi.from_system(s2)
+        mat.set(s2.diag, s2.upper_coeffs, s2.lower_coeffs)
+        ctl = capi.controls("PBiCGStab", "DILU", tolerance=0.0, relTol=0.0, maxIter=10)
+        secs, perf = timed_solve(mat, ctl, s2.source, 2)
+        out["pbicgstab_dilu_12m"] = {
+            "workload": f"asymmetric convection-diffusion {n2}x{n2} ({s2.n_cells} cells; BASELINE configs[4] stand-in: "
+                        "the pitzDaily multi-block mesh itself is not generated), PBiCGStab+DILU, 10 iterations",
+            "n_cells": s2.n_cells, "iterations": int(perf.nIterations),
+            "ms_per_iteration": perf.solveMs / max(1, perf.nIterations),
+            "cell_iterations_per_s": s2.n_cells * perf.nIterations / (perf.solveMs * 1e-3),
+            "wall_ms_per_solve": 1e3 * secs, "pencil_layout": bool(mesh.get_i32(21, 0).size == 7)}
+        mat.close()
+        mesh.close()
+        del s2
+
     # configs[3]: 384^3, strong scaling
     n = 384
     if world == 1:
