@@ -79,10 +79,13 @@ def main():
     dist.broadcast(buf, 0)
     capi.init(local, bytes(buf.cpu().numpy().tobytes()), rank, world)
 
-    split = decompose.simple_split(world)
-    nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
     ok = True
     for kind in ("sym", "asym", "cyc"):
+        split = decompose.simple_split(world)
+        if kind == "cyc" and split[2] > 1:
+            # the periodic direction must stay inside a rank (processorCyclic patches are out of scope)
+            split = (split[0] * split[2], split[1], 1)
+        nx, ny, nz = 10 * split[0], 8 * split[1], 6 * split[2]
         # "cyc": periodic in z on top of the decomposition -- every rank has processor patches AND a cyclic pair
         glob = cases.cavity_laplacian(nx, ny, nz, coeffs="random") if kind == "sym" else \
             cases.convection_diffusion(nx, ny, nz, dt_coeff=50.0) if kind == "asym" else \
