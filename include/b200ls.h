@@ -50,6 +50,8 @@ void b200ls_finalize(void);
 const char* b200ls_last_error(void);
 /* 1 if a CUDA device is usable by this process, else 0 (no error is recorded). */
 int b200ls_device_available(void);
+/* number of CUDA devices visible to this process (0 without a driver): hosts map node-local ranks to devices with it */
+int b200ls_device_count(void);
 
 /* Optional host-side communicator for the once-per-mesh agglomeration of a DECOMPOSED mesh: the neighbour
  * exchange of restrictMap over each processor patch (GAMGAgglomerateLduAddressing.C:268-283) and the global sums of

@@ -26,7 +26,7 @@ PRECONDS = {"none": NONE, "diagonal": DIAGONAL, "DIC": DIC, "DILU": DILU, "Gauss
             "DILUGaussSeidel": DILU_GAUSS_SEIDEL, "GAMG": GAMG_PRECOND}
 
 EXPORTS = [
-    "b200ls_init", "b200ls_set_host_comm", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available",
+    "b200ls_init", "b200ls_set_host_comm", "b200ls_nccl_unique_id", "b200ls_finalize", "b200ls_last_error", "b200ls_device_available", "b200ls_device_count",
     "b200ls_mesh_create", "b200ls_mesh_free", "b200ls_mesh_get_i32", "b200ls_mesh_get_iface_i32", "b200ls_mesh_n_levels",
     "b200ls_agglomerate", "b200ls_agglomerate_from_maps", "b200ls_matrix_create", "b200ls_matrix_free", "b200ls_matrix_set",
     "b200ls_matrix_set_dev", "b200ls_matrix_set_if_changed",

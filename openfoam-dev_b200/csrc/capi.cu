@@ -394,6 +394,15 @@ int b200ls_device_available(void) {
     return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
 }
 
+int b200ls_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int b200ls_nccl_unique_id(void* out128) {
     return guarded([&] {
         loadNccl(ctx().nccl);

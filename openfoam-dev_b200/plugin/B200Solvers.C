@@ -30,6 +30,7 @@
 #include "processorLduInterface.H"
 #include "cyclicLduInterface.H"
 #include "cyclicLduInterfaceField.H"
+#include "processorLduInterfaceField.H"
 #include "GAMGAgglomeration.H"
 #include "addToRunTimeSelectionTable.H"
 #include "Pstream.H"
@@ -62,7 +63,17 @@ struct cacheEntry
     label nCells;
     label nFaces;
     uint64_t fingerprint;
-    bool agglomerated;
+    //- The reference's agglomeration object handed to the library
+    //  (nullptr: none yet).  A rebuilt GAMGAgglomeration (e.g.
+    //  cacheAgglomeration false) is a new object and is handed over again
+    const void* agglomeration;
+    //- Serial of the preconditioner/smoother/solver object whose
+    //  coefficients the device matrix holds
+    uint64_t owner;
+    //- Last use (for eviction)
+    uint64_t stamp;
+    //- Live preconditioner/smoother objects holding a reference
+    int pins;
 
     cacheEntry()
     :
@@ -71,28 +82,65 @@ struct cacheEntry
         nCells(-1),
         nFaces(-1),
         fingerprint(0),
-        agglomerated(false)
+        agglomeration(nullptr),
+        owner(0),
+        stamp(0),
+        pins(0)
     {}
 };
 
 static std::map<const lduAddressing*, cacheEntry> cache_;
 static bool initialised_ = false;
+static uint64_t clock_ = 0;
+static uint64_t nextOwner_ = 0;
+
+//- At most this many addressings keep device meshes alive (dynamic or
+//  topology-changing meshes create new lduAddressing objects)
+static const size_t maxCacheEntries_ = 16;
+
+static void freeEntry(cacheEntry& e)
+{
+    if (e.matrix) b200ls_matrix_free(e.matrix);
+    if (e.mesh) b200ls_mesh_free(e.mesh);
+    e = cacheEntry();
+}
 
 
-//- Cheap fingerprint of the addressing (sizes + a strided sample of lower/upper): a mesh that changed topology
-//  under an unchanged lduAddressing object must not reuse the cached device layout
+//- Fingerprint of the addressing (sizes + every lower/upper label; a few
+//  ms per million faces, small against a solve): a mesh that changed
+//  topology under an unchanged lduAddressing address must not reuse the
+//  cached device layout
+static inline uint64_t fpMix(uint64_t h, const uint64_t v)
+{
+    h ^= v*0x9E3779B97F4A7C15ull;
+    h = (h << 27) | (h >> 37);
+    return h*0x94D049BB133111EBull + 0x2545F4914F6CDD1Dull;
+}
+
+static uint64_t fingerprint(const labelUList& l, uint64_t seed)
+{
+    // four independent lanes over pairs of labels (memory-bound)
+    uint64_t h0 = seed, h1 = ~seed, h2 = seed ^ 0xA5A5A5A5A5A5A5A5ull, h3 = seed + 0x632BE59BD9B4E019ull;
+    const label n = l.size();
+    label i = 0;
+    for (; i + 8 <= n; i += 8)
+    {
+        h0 = fpMix(h0, (uint64_t(uint32_t(l[i])) << 32) | uint32_t(l[i+1]));
+        h1 = fpMix(h1, (uint64_t(uint32_t(l[i+2])) << 32) | uint32_t(l[i+3]));
+        h2 = fpMix(h2, (uint64_t(uint32_t(l[i+4])) << 32) | uint32_t(l[i+5]));
+        h3 = fpMix(h3, (uint64_t(uint32_t(l[i+6])) << 32) | uint32_t(l[i+7]));
+    }
+    for (; i < n; i++) h0 = fpMix(h0, uint32_t(l[i]));
+    return fpMix(fpMix(fpMix(fpMix(uint64_t(n), h0), h1), h2), h3);
+}
+
 static uint64_t fingerprint(const lduAddressing& addr)
 {
-    const labelUList& l = addr.lowerAddr();
-    const labelUList& u = addr.upperAddr();
-    uint64_t h = 1469598103934665603ull ^ uint64_t(addr.size());
-    const label stride = max(label(1), l.size()/4096);
-    for (label f = 0; f < l.size(); f += stride)
-    {
-        h = (h ^ uint64_t(uint32_t(l[f]))) * 1099511628211ull;
-        h = (h ^ uint64_t(uint32_t(u[f]))) * 1099511628211ull;
-    }
-    return h ^ uint64_t(l.size());
+    return fpMix
+    (
+        fingerprint(addr.lowerAddr(), 1) ^ uint64_t(addr.size()),
+        fingerprint(addr.upperAddr(), 2)
+    );
 }
 
 
@@ -107,9 +155,13 @@ static void check(const int rc, const char* what)
 }
 
 
-//- One process per GPU: device = local rank modulo visible devices unless
-//  B200LS_DEVICE is set.  In parallel the NCCL id is created on the master
-//  and scattered through Pstream.
+//- One process per GPU: device = B200LS_DEVICE if set, else the node-local
+//  rank the MPI launcher exports (OpenMPI, Slurm, PMI/MPICH/Hydra, MVAPICH,
+//  Intel MPI) modulo the number of visible devices.  Two ranks of one host
+//  on the same device are an error (the persistent sweep kernels and the
+//  peer-memory reductions of several processes would time-slice on one GPU).
+//  In parallel the NCCL id is created on the master and scattered through
+//  Pstream.
 static void init()
 {
     if (initialised_) return;
@@ -119,13 +171,44 @@ static void init()
     {
         device = atoi(s);
     }
-    else if (const char* s = getenv("OMPI_COMM_WORLD_LOCAL_RANK"))
+    else
     {
-        device = atoi(s);
+        static const char* const vars[] =
+        {
+            "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", "PMI_LOCAL_RANK",
+            "MPI_LOCALRANKID", "MV2_COMM_WORLD_LOCAL_RANK"
+        };
+        for (const char* v : vars)
+        {
+            if (const char* s = getenv(v))
+            {
+                device = atoi(s);
+                break;
+            }
+        }
+        const int nDev = b200ls_device_count();
+        if (nDev > 0) device %= nDev;
     }
-    else if (const char* s = getenv("MPI_LOCALRANKID"))
+
+    if (Pstream::parRun())
     {
-        device = atoi(s);
+        // (host, device) of every rank: no two ranks may share a GPU
+        List<string> where(Pstream::nProcs());
+        where[Pstream::myProcNo()] = hostName() + ":" + Foam::name(device);
+        Pstream::gatherList(where);
+        Pstream::scatterList(where);
+        forAll(where, proci)
+        {
+            if (proci != Pstream::myProcNo() && where[proci] == where[Pstream::myProcNo()])
+            {
+                FatalErrorInFunction
+                    << "ranks " << proci << " and " << Pstream::myProcNo()
+                    << " both map to GPU " << where[proci]
+                    << ": libB200LinearSolvers runs one rank per GPU (set"
+                    << " B200LS_DEVICE per rank, or start at most as many"
+                    << " ranks per host as it has GPUs)" << exit(FatalError);
+            }
+        }
     }
 
     if (Pstream::parRun())
@@ -183,19 +266,45 @@ static cacheEntry& entryFor
     init();
 
     const lduAddressing& addr = matrix.lduAddr();
+    if (cache_.find(&addr) == cache_.end() && cache_.size() >= maxCacheEntries_)
+    {
+        // evict the entry that has not been used for the longest time
+        auto oldest = cache_.end();
+        for (auto it = cache_.begin(); it != cache_.end(); ++it)
+        {
+            if
+            (
+                it->second.pins == 0
+             && (oldest == cache_.end() || it->second.stamp < oldest->second.stamp)
+            )
+            {
+                oldest = it;
+            }
+        }
+        if (oldest != cache_.end())
+        {
+            freeEntry(oldest->second);
+            cache_.erase(oldest);
+        }
+    }
     cacheEntry& e = cache_[&addr];
+    e.stamp = ++clock_;
 
     const label nCells = addr.size();
     const label nFaces = addr.lowerAddr().size();
 
+    // (hashing every label on every call would cost as much as a small
+    //  solve: sizes are compared always, the labels when the entry is created
+    //  and whenever the sizes of a cached entry still match)
     const uint64_t fp = fingerprint(addr);
 
     if (e.mesh && (e.nCells != nCells || e.nFaces != nFaces || e.fingerprint != fp))
     {
         // mesh changed under the same address: rebuild
-        b200ls_matrix_free(e.matrix);
-        b200ls_mesh_free(e.mesh);
-        e = cacheEntry();
+        const int pins = e.pins;
+        freeEntry(e);
+        e.stamp = clock_;
+        e.pins = pins;
     }
 
     if (!e.mesh)
@@ -227,6 +336,22 @@ static cacheEntry& entryFor
 
                 if (isA<processorLduInterface>(li))
                 {
+                    if
+                    (
+                        isA<processorLduInterfaceField>(interfaces[patchi])
+                     && refCast<const processorLduInterfaceField>
+                        (
+                            interfaces[patchi]
+                        ).transforms()
+                    )
+                    {
+                        FatalErrorInFunction
+                            << "processor patch " << patchi
+                            << " transforms the field (processorCyclic half"
+                            << " of a rotational cyclic on a vector/tensor"
+                            << " component): not supported by"
+                            << " libB200LinearSolvers" << exit(FatalError);
+                    }
                     nbr.push_back
                     (
                         refCast<const processorLduInterface>(li)
@@ -302,9 +427,12 @@ static void uploadCoeffs
     const lduMatrix& matrix,
     const Field<Field<scalar>>& bouCoeffs,
     const Field<Field<scalar>>& intCoeffs,
-    const lduInterfaceFieldPtrsList& interfaces
+    const lduInterfaceFieldPtrsList& interfaces,
+    const uint64_t owner = 0
 )
 {
+    e.owner = owner;
+
     std::vector<const double*> bou, inn;
     forAll(interfaces, patchi)
     {
@@ -367,16 +495,36 @@ protected:
     //  GAMGAgglomeration.C:349-400) to the library, once per mesh
     void ensureAgglomeration(B200::cacheEntry& e, const dictionary& dict) const
     {
-        if (e.agglomerated) return;
+        if (dict.found("processorAgglomerator"))
+        {
+            FatalErrorInFunction
+                << "processorAgglomerator "
+                << word(dict.lookup("processorAgglomerator"))
+                << ": processor agglomeration is not supported by"
+                << " libB200LinearSolvers" << exit(FatalError);
+        }
 
+        // the reference's (cached) agglomeration; a rebuilt one is a new
+        // object and is handed to the library again
         const GAMGAgglomeration& agg = GAMGAgglomeration::New(matrix_, dict);
+        if (e.agglomeration == &agg) return;
 
         std::vector<const int32_t*> maps;
         std::vector<int32_t> nCoarse;
+        label nFine = matrix_.lduAddr().size();
         for (label lev = 0; lev < agg.size(); lev++)
         {
+            // restrictAddressing(lev): one coarse label per cell of level lev
+            if (agg.restrictAddressing(lev).size() != nFine)
+            {
+                FatalErrorInFunction
+                    << "restrictAddressing of level " << lev << " has "
+                    << agg.restrictAddressing(lev).size() << " entries for "
+                    << nFine << " cells" << exit(FatalError);
+            }
             maps.push_back(agg.restrictAddressing(lev).begin());
             nCoarse.push_back(agg.nCells(lev));
+            nFine = agg.nCells(lev);
         }
         if
         (
@@ -393,7 +541,7 @@ protected:
                 << "b200ls_agglomerate_from_maps failed: "
                 << b200ls_last_error() << exit(FatalError);
         }
-        e.agglomerated = true;
+        e.agglomeration = &agg;
     }
 
     //- GAMGSolver::readControls (GAMGSolver.C:348-371)
@@ -437,7 +585,10 @@ protected:
         {
             const Foam::entry& pe =
                 controlDict_.lookupEntry("preconditioner", false, false);
-            const dictionary& pd = pe.isDict() ? pe.dict() : controlDict_;
+            // a word entry carries no controls: the reference constructs the
+            // preconditioner from dictionary::null then
+            // (lduMatrixPreconditioner.C:40-59), i.e. every default
+            const dictionary& pd = pe.isDict() ? pe.dict() : dictionary::null;
 
             ensureAgglomeration(entry(), pd);
             readGAMGControls(c, pd);
@@ -669,24 +820,40 @@ class B200Preconditioner
     public lduMatrix::preconditioner
 {
     B200::cacheEntry& e_;
+    const uint64_t owner_;
+
+    //- The device matrix of an addressing is shared: if another object has
+    //  put its coefficients there since, bring ours back
+    void upload() const
+    {
+        B200::uploadCoeffs
+        (
+            e_,
+            solver_.matrix(),
+            solver_.interfaceBouCoeffs(),
+            solver_.interfaceIntCoeffs(),
+            solver_.interfaces(),
+            owner_
+        );
+    }
 
 public:
 
     B200Preconditioner(const lduMatrix::solver& sol, const dictionary&)
     :
         lduMatrix::preconditioner(sol),
-        e_(B200::entryFor(sol.matrix(), sol.interfaces()))
+        e_(B200::entryFor(sol.matrix(), sol.interfaces())),
+        owner_(++B200::nextOwner_)
     {
         // coefficients are read once per construction, like
         // DICPreconditioner's calcReciprocalD (DICPreconditioner.C:42-52)
-        B200::uploadCoeffs
-        (
-            e_,
-            sol.matrix(),
-            sol.interfaceBouCoeffs(),
-            sol.interfaceIntCoeffs(),
-            sol.interfaces()
-        );
+        e_.pins++;
+        upload();
+    }
+
+    virtual ~B200Preconditioner()
+    {
+        e_.pins--;
     }
 
     virtual void precondition
@@ -696,6 +863,7 @@ public:
         const direction cmpt = 0
     ) const
     {
+        if (e_.owner != owner_) upload();
         B200::check
         (
             b200ls_precondition(e_.matrix, Kind, rA.begin(), wA.begin()),
@@ -729,6 +897,20 @@ class B200Smoother
     public lduMatrix::smoother
 {
     B200::cacheEntry& e_;
+    const uint64_t owner_;
+
+    void upload() const
+    {
+        B200::uploadCoeffs
+        (
+            e_,
+            matrix_,
+            interfaceBouCoeffs_,
+            interfaceIntCoeffs_,
+            interfaces_,
+            owner_
+        );
+    }
 
 public:
 
@@ -749,12 +931,16 @@ public:
             interfaceIntCoeffs,
             interfaces
         ),
-        e_(B200::entryFor(matrix, interfaces))
+        e_(B200::entryFor(matrix, interfaces)),
+        owner_(++B200::nextOwner_)
     {
-        B200::uploadCoeffs
-        (
-            e_, matrix, interfaceBouCoeffs, interfaceIntCoeffs, interfaces
-        );
+        e_.pins++;
+        upload();
+    }
+
+    virtual ~B200Smoother()
+    {
+        e_.pins--;
     }
 
     virtual void smooth
@@ -765,6 +951,7 @@ public:
         const label nSweeps
     ) const
     {
+        if (e_.owner != owner_) upload();
         B200::check
         (
             b200ls_smooth(e_.matrix, Kind, psi.begin(), source.begin(), nSweeps),
