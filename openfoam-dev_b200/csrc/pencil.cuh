@@ -789,6 +789,74 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Amul on a pencil level: a 7-point stencil on the tile-major layout
+// ------------------------------------------------------------------------------------------------------------
+
+// wA = A x (lduMatrixATmul.C:34-92) for a structured block in tile-major positions, optionally fused with wA.x
+// (PCG.C:159-161).  Neighbour positions follow from the tile geometry (same tile: +-1 along j, +-wj along k, +-w along
+// i; across a tile face: the facing pencil of the neighbour tile), so no row pointers or column indices are read: per
+// row the diagonal, x, the result and six coefficients -- the upper-side planes cU (I+, J+, K+) of the row and, for the
+// lower side, either the planes cL (K-, J-, I-) or (SYM) the neighbours' own cU entries of the shared faces, which the
+// neighbouring threads load anyway.  Absent faces carry +0 coefficients and point at the row itself.  Accumulation
+// order = k_spmv: diagonal, K-, J-, I-, I+, J+, K+.  One work item = 256 consecutive rows of one tile; grid-stride
+// over the items so that the block partials of the fused dot product fit the reduction scratch.
+template <bool SYM, bool DOT>
+__global__ void __launch_bounds__(256)
+k_pencil_spmv(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ diag,
+              const double* __restrict__ cL, const double* __restrict__ cU, size_t np,
+              const PencilTileDev* __restrict__ tiles, int nTiles, int nx, int chunksPerTile,
+              double* __restrict__ dotOut, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    double v[1] = {0.0};
+    const int nItems = nTiles * chunksPerTile;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int ti = item / chunksPerTile;
+        const int local = (item - ti * chunksPerTile) * 256 + threadIdx.x;
+        const PencilTileDev* tp = tiles + ti;
+        const int4 t0 = *reinterpret_cast<const int4*>(&tp->base);   // base, w, wj, wk
+        const int w = t0.y, wj = t0.z, wk = t0.w;
+        if (local >= nx * w) continue;
+        const int4 nB = *reinterpret_cast<const int4*>(tp->nbrBase);
+        const int4 nW = *reinterpret_cast<const int4*>(tp->nbrW);
+        const int4 nJ = *reinterpret_cast<const int4*>(tp->nbrWj);
+        const int i = local / w, ln = local - i * w;
+        const int kk = ln / wj, jj = ln - kk * wj;
+        const int p = t0.x + local;
+        // neighbour positions (p itself where there is no cell: the coefficient is +0 there)
+        const int qIm = i > 0 ? p - w : p;
+        const int qIp = i < nx - 1 ? p + w : p;
+        const int qJm = jj > 0 ? p - 1 : (nB.x >= 0 ? nB.x + i * nW.x + (nJ.x - 1) + nJ.x * kk : p);
+        const int qJp = jj < wj - 1 ? p + 1 : (nB.z >= 0 ? nB.z + i * nW.z + nJ.z * kk : p);
+        const int qKm = kk > 0 ? p - wj : (nB.y >= 0 ? nB.y + i * nW.y + jj + nJ.y * (nW.y / nJ.y - 1) : p);
+        const int qKp = kk < wk - 1 ? p + wj : (nB.w >= 0 ? nB.w + i * nW.w + jj : p);
+        const double xp = x[p];
+        double lK, lJ, lI;
+        if (SYM) {
+            // the lower coefficient of a face equals its upper coefficient, stored with the owner (the lower-side
+            // neighbour): slot K+ of q_K-, J+ of q_J-, I+ of q_I-
+            lK = qKm != p ? cU[2 * np + qKm] : 0.0;
+            lJ = qJm != p ? cU[np + qJm] : 0.0;
+            lI = qIm != p ? cU[qIm] : 0.0;
+        } else {
+            lK = cL[p];
+            lJ = cL[np + p];
+            lI = cL[2 * np + p];
+        }
+        double acc = diag[p] * xp;
+        acc += lK * x[qKm];
+        acc += lJ * x[qJm];
+        acc += lI * x[qIm];
+        acc += cU[p] * x[qIp];
+        acc += cU[np + p] * x[qJp];
+        acc += cU[2 * np + p] * x[qKp];
+        out[p] = acc;
+        if (DOT) v[0] += acc * xp;
+    }
+    if (DOT) {
+        if (grid_reduce<1>(v, partials, ticket)) dotOut[0] = v[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // coefficient planes of a pencil level
 // ------------------------------------------------------------------------------------------------------------
 

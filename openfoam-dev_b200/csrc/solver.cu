@@ -868,11 +868,43 @@ static void ifaceApply(b200ls_matrix_s* m, int level, double* result, double sig
 // SpMV family
 // ------------------------------------------------------------------------------------------------------------
 
+static bool usePencil(const DevLevel& D);
+static void ensurePencilPlanes(b200ls_matrix_s* m, int level);
+static size_t planeStride(const DevLevel& D);
+
+// Amul on a pencil level (tile-major structured block): the 7-point stencil kernel on the coefficient planes, optionally
+// fused with the dot product wA.x (dotOut != nullptr)
+static void pencilSpmv(b200ls_matrix_s* m, int level, double* out, const double* x, double* dotOut) {
+    DevLevel& D = DL(m, level);
+    MatLevel& M = m->levels[level];
+    Context& c = ctx();
+    ensurePencilPlanes(m, level);
+    const size_t np = planeStride(D);
+    const int chunks = std::max(1, (D.pNx * 32 + 255) / 256);
+    const int grid = std::max(1, std::min(D.nPencilTiles * chunks, kMaxPartials / 2));
+#define B2_PSPMV(SYM, DOT)                                                                                            \
+    LAUNCH((k_pencil_spmv<SYM, DOT>), grid, 256, out, x, M.diag.p, M.pcL.p, M.pcU.p, np, D.pTiles.p, D.nPencilTiles, \
+           D.pNx, chunks, dotOut, c.partials.p, c.ticket.p)
+    if (m->symmetric) {
+        if (dotOut) B2_PSPMV(true, true);
+        else B2_PSPMV(true, false);
+    } else {
+        if (dotOut) B2_PSPMV(false, true);
+        else B2_PSPMV(false, false);
+    }
+#undef B2_PSPMV
+}
+
 template <int MODE>
 static void spmv(b200ls_matrix_s* m, int level, double* out, double* out2, const double* x, const double* b) {
     DevLevel& D = DL(m, level);
     MatLevel& M = m->levels[level];
     if (D.nCells == 0) return;
+    static const bool noPencilSpmv = getenv("B200LS_NO_PENCIL_SPMV") != nullptr;
+    if (MODE == SPMV_AMUL && !noPencilSpmv && usePencil(D)) {
+        pencilSpmv(m, level, out, x, nullptr);
+        return;
+    }
     static const bool noSym = getenv("B200LS_NO_SYM_SPMV") != nullptr;
     static const bool x2 = getenv("B200LS_NO_SPMV_X2") == nullptr;   // two rows per thread: +7 % at 256^3
     if (MODE == SPMV_AMUL && m->symmetric && D.hasLslot && !noSym && x2) {
@@ -1466,7 +1498,10 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
             allReduce(scalar(m, cur), 1);
             LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
                    perf->nIterations == 0 ? 1 : 0, n);
-            if (fuseSpmvDot) {
+            static const bool noPencilSpmv = getenv("B200LS_NO_PENCIL_SPMV") != nullptr;
+            if (fuseSpmvDot && !noPencilSpmv && usePencil(D)) {
+                pencilSpmv(m, lv, wA, pA, scalar(m, S_WAPA));
+            } else if (fuseSpmvDot) {
                 if (m->symmetric && D.hasLslot) {
                     LAUNCH(k_spmv_dot<true>, spmvGrid, 256, wA, pA, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
                            D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p);
