@@ -116,6 +116,7 @@ struct Context {
     DevBuf<double> partials;
     DevBuf<unsigned int> ticket;
     DevBuf<int> errFlag;
+    DevBuf<int> stopFlag;                      // device-side loop condition of speculatively enqueued Krylov iterations
     double* pinned = nullptr;       // pinned host scratch for scalar read-back (64 doubles)
     int64_t launches = 0;           // kernels launched since the counter was last reset
     int sweepBlocksPerSM = 0;       // 0 = occupancy maximum

@@ -321,7 +321,8 @@ k_spmv_dot(double* __restrict__ out, const double* __restrict__ x, const double*
            const int* __restrict__ Lptr, const int* __restrict__ Lcol, const double* __restrict__ Lval,
            const unsigned char* __restrict__ Lslot, const int* __restrict__ Uptr, const int* __restrict__ Ucol,
            const double* __restrict__ Uval, int n, double* __restrict__ dotOut, double* __restrict__ partials,
-           unsigned int* __restrict__ ticket) {
+           unsigned int* __restrict__ ticket, const int* __restrict__ stop) {
+    if (stop && *stop) return;
     double v[1] = {0.0};
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int l0 = Lptr[p], l1 = Lptr[p + 1];
@@ -481,6 +482,7 @@ struct SweepArgs {
     double* dotOut;
     double* partials;
     unsigned int* ticket;
+    const int* stop;        // optional: a non-zero word makes the launch a no-op (speculatively enqueued iterations)
 };
 
 // Dependency gather of one row: acc -= (scale*val[j]) * y[col[j]] for j ascending (DESC=false) or descending
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(256) k_factor(SweepArgs a) {
 // forward substitution of DIC/DILU precondition with the scaling pass fused:
 //   y[u] = rD[u]*rA[u] - sum_{f ascending} (rD[u]*lower[f]) * y[lower(f)]
 __global__ void __launch_bounds__(256) k_sweep_fwd(SweepArgs a) {
+    if (a.stop && *a.stop) return;
     const double sent = sentinel();
     SWEEP_TASK_LOOP(a) {
         const int2 next = SWEEP_NEXT_TASK(a);
@@ -615,6 +618,7 @@ __global__ void __launch_bounds__(256) k_sweep_fwd(SweepArgs a) {
 
 // backward substitution:  z[l] = y[l] - sum_{f descending} (rD[l]*upper[f]) * z[upper(f)]
 __global__ void __launch_bounds__(256) k_sweep_bwd(SweepArgs a) {
+    if (a.stop && *a.stop) return;
     const double sent = sentinel();
     double dsum[1] = {0.0};
     SWEEP_TASK_LOOP(a) {
@@ -925,7 +929,8 @@ k_norm_factor(double* __restrict__ out, const double* __restrict__ Apsi, const d
 // pA = wA + (wArA/wArAold)*pA       (first iteration: pA = wA)
 __global__ void k_pcg_update_p(double* __restrict__ pA, const double* __restrict__ wA,
                                const double* __restrict__ wArA, const double* __restrict__ wArAold, int first,
-                               int n) {
+                               int n, const int* __restrict__ stop) {
+    if (stop && *stop) return;
     if (first) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pA[i] = wA[i];
         return;
@@ -940,7 +945,8 @@ __global__ void __launch_bounds__(kReduceThreads)
 k_pcg_update_xr(double* __restrict__ psi, double* __restrict__ rA, const double* __restrict__ pA,
                 const double* __restrict__ wA, const double* __restrict__ wArA, const double* __restrict__ wApA,
                 double normFactor, double* __restrict__ singularFlag, double* __restrict__ out, int n,
-                double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+                double* __restrict__ partials, unsigned int* __restrict__ ticket, const int* __restrict__ stop) {
+    if (stop && *stop) return;
     // checkSingularity(mag(wApA)/normFactor) (PCG.C:165): leave psi/rA untouched and raise the flag
     if (fabs(wApA[0]) / normFactor < 2.2250738585072014e-308) {
         if (blockIdx.x == 0 && threadIdx.x == 0) singularFlag[0] = 1.0;
@@ -955,6 +961,18 @@ k_pcg_update_xr(double* __restrict__ psi, double* __restrict__ rA, const double*
         v[0] += fabs(r);
     }
     if (grid_reduce<1>(v, partials, ticket)) out[0] = v[0];
+}
+
+// Device-side copy of the loop condition of PCG.C:182-190 for iterations enqueued ahead of the host's read-back:
+// stop = singular, or converged (SolverPerformance.C:75-82) once minIter allows it.  The host evaluates the same
+// expression on the same numbers one iteration later.
+__global__ void k_pcg_stop_flag(int* __restrict__ stop, const double* __restrict__ sumMagR,
+                                const double* __restrict__ singular, double normFactor, double tolerance,
+                                double relTol, double initialResidual, int mayStop) {
+    if (*stop) return;
+    const double fin = sumMagR[0] / normFactor;
+    const bool conv = fin < tolerance || (relTol > 1e-20 && fin < relTol * initialResidual);
+    if (singular[0] != 0.0 || (conv && mayStop)) *stop = 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ struct PencilArgs {
     // helper: polling rounds, cycles waiting for ring capacity
     unsigned long long* prof;
     int debug;              // B200LS_PENCIL_DEBUG bits: 2 = slow helper rounds
+    const int* stop;        // optional: a non-zero word makes the launch a no-op (speculatively enqueued iterations)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     constexpr int kNever = 0x7fffffff;
     static_assert((NS & (NS - 1)) == 0 && NS <= 8, "ring stages: a power of two, at most 8");
     extern __shared__ __align__(128) unsigned char pencilSmem[];
+    if (a.stop && *a.stop) return;   // (every CTA reads the same word: it only changes between launches)
     const bool doDot = MODE == PM_BWD && a.dotOut != nullptr;
     unsigned smBase = smem_u32(pencilSmem);
     asm volatile("mov.u32 %0, %0;" : "+r"(smBase));   // opaque: keep the base in a register (not re-derived from SR_CgaCtaId)
@@ -805,7 +807,9 @@ __global__ void __launch_bounds__(256)
 k_pencil_spmv(double* __restrict__ out, const double* __restrict__ x, const double* __restrict__ diag,
               const double* __restrict__ cL, const double* __restrict__ cU, size_t np,
               const PencilTileDev* __restrict__ tiles, int nTiles, int nx, int chunksPerTile,
-              double* __restrict__ dotOut, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+              double* __restrict__ dotOut, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+              const int* __restrict__ stop) {
+    if (stop && *stop) return;
     double v[1] = {0.0};
     const int nItems = nTiles * chunksPerTile;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x) {

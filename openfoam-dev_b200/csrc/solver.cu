@@ -46,6 +46,8 @@ void ensureInit() {
     c.partials.alloc(kMaxPartials);
     c.ticket.alloc(1);
     c.errFlag.alloc(1);
+    c.stopFlag.alloc(1);
+    B2_CUDA(cudaMemsetAsync(c.stopFlag.p, 0, sizeof(int), c.stream));
     B2_CUDA(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned int), c.stream));
     B2_CUDA(cudaMemsetAsync(c.errFlag.p, 0, sizeof(int), c.stream));
     B2_CUDA(cudaMallocHost(&c.pinned, 64 * sizeof(double)));
@@ -868,6 +870,10 @@ static void ifaceApply(b200ls_matrix_s* m, int level, double* result, double sig
 // SpMV family
 // ------------------------------------------------------------------------------------------------------------
 
+// Non-null while a Krylov loop enqueues iterations ahead of the host's convergence read-back: the kernels of such an
+// iteration return at once when the word it points to is set (solvePCG).
+static const int* g_stop = nullptr;
+
 static bool usePencil(const DevLevel& D);
 static void ensurePencilPlanes(b200ls_matrix_s* m, int level);
 static size_t planeStride(const DevLevel& D);
@@ -884,7 +890,7 @@ static void pencilSpmv(b200ls_matrix_s* m, int level, double* out, const double*
     const int grid = std::max(1, std::min(D.nPencilTiles * chunks, kMaxPartials / 2));
 #define B2_PSPMV(SYM, DOT)                                                                                            \
     LAUNCH((k_pencil_spmv<SYM, DOT>), grid, 256, out, x, M.diag.p, M.pcL.p, M.pcU.p, np, D.pTiles.p, D.nPencilTiles, \
-           D.pNx, chunks, dotOut, c.partials.p, c.ticket.p)
+           D.pNx, chunks, dotOut, c.partials.p, c.ticket.p, g_stop)
     if (m->symmetric) {
         if (dotOut) B2_PSPMV(true, true);
         else B2_PSPMV(true, false);
@@ -1105,12 +1111,14 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
         for (int q = 0; q < 3; q++) f.plane[2 + q] = M.ptL.p + q * np;
         f.out = M.tmpA.p;
         f.clear = wA;
+        f.stop = g_stop;
         launchPencil<PM_FWD>(f, D);
         PencilArgs b = pencilArgs(D, false);
         b.plane[0] = M.tmpA.p;
         for (int q = 0; q < 3; q++) b.plane[1 + q] = M.ptU.p + q * np;
         b.out = wA;
         b.clear = M.tmpA.p;
+        b.stop = g_stop;
         if (dotOut) {   // fused wA.rA
             b.plane[4] = rA;
             b.dotOut = dotOut;
@@ -1129,6 +1137,7 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
     f.in = rA;
     f.out = M.tmpA.p;
     f.clear = wA;
+    f.stop = g_stop;
     launchSweep(k_sweep_fwd, f);
 
     SweepArgs b{};
@@ -1142,6 +1151,7 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
     b.in = M.tmpA.p;
     b.out = wA;
     b.clear = M.tmpA.p;
+    b.stop = g_stop;
     if (dotOut) {   // fused wA.rA
         b.dotWith = rA;
         b.dotOut = dotOut;
@@ -1486,9 +1496,18 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
         const bool fuseSweepDot = (c.precond == B200LS_DIC || c.precond == B200LS_DILU);
         const bool fuseSpmvDot = (D.nIfaces == 0);
         const int spmvGrid = std::max(1, std::min(gridRows(n), kMaxPartials / 2));   // one row per thread when it fits
-        do {
-            const int cur = S_WARA0 + (perf->nIterations & 1);
-            const int old = S_WARA0 + ((perf->nIterations + 1) & 1);
+        static const bool noPencilSpmv = getenv("B200LS_NO_PENCIL_SPMV") != nullptr;
+        static const bool noPipeline = getenv("B200LS_NO_PCG_PIPELINE") != nullptr;
+        // One rank, no coupled patches: iteration k+1 is enqueued BEFORE the host has read the residual of iteration
+        // k, so the read-back round trip and the launch latencies hide behind the kernels.  The loop condition is
+        // evaluated on the device too (k_pcg_stop_flag) and every kernel of an iteration enqueued too far returns at
+        // once; the host applies the same test to the same numbers one step later, so the iteration count, the
+        // convergence flag and all fields are those of the synchronous loop.
+        const bool pipelined = cx.nRanks == 1 && D.nIfaces == 0 && fuseSweepDot && lv == 0 && !noPipeline;
+        const int* stop = pipelined ? cx.stopFlag.p : nullptr;
+        auto enqueue = [&](int it) {
+            const int cur = S_WARA0 + (it & 1);
+            const int old = S_WARA0 + ((it + 1) & 1);
             if (fuseSweepDot) {
                 opPrecondition(m, lv, c.precond, wA, rA, scalar(m, cur));
             } else {
@@ -1496,18 +1515,18 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
                 reduce<RED_DOT>(scalar(m, cur), wA, rA, n);
             }
             allReduce(scalar(m, cur), 1);
-            LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old),
-                   perf->nIterations == 0 ? 1 : 0, n);
-            static const bool noPencilSpmv = getenv("B200LS_NO_PENCIL_SPMV") != nullptr;
+            LAUNCH(k_pcg_update_p, gridStride(n), 256, pA, wA, scalar(m, cur), scalar(m, old), it == 0 ? 1 : 0, n, stop);
             if (fuseSpmvDot && !noPencilSpmv && usePencil(D)) {
                 pencilSpmv(m, lv, wA, pA, scalar(m, S_WAPA));
             } else if (fuseSpmvDot) {
                 if (m->symmetric && D.hasLslot) {
                     LAUNCH(k_spmv_dot<true>, spmvGrid, 256, wA, pA, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
-                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p);
+                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p,
+                           stop);
                 } else {
                     LAUNCH(k_spmv_dot<false>, spmvGrid, 256, wA, pA, M.diag.p, D.Lptr.p, D.Lcol.p, M.Lval(D.nFaces),
-                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p);
+                           D.Lslot.p, D.Uptr.p, D.Ucol.p, M.Uval(), n, scalar(m, S_WAPA), cx.partials.p, cx.ticket.p,
+                           stop);
                 }
             } else {
                 opAmul(m, lv, wA, pA);
@@ -1516,19 +1535,65 @@ static void solvePCG(b200ls_matrix_s* m, const b200ls_controls& c, int lv, doubl
             allReduce(scalar(m, S_WAPA), 1);
             // the singularity test (PCG.C:165) is evaluated on the device by every thread of the update kernel
             LAUNCH(k_pcg_update_xr, kReduceBlocks, kReduceThreads, psi, rA, pA, wA, scalar(m, cur),
-                   scalar(m, S_WAPA), nf, scalar(m, S_SINGULAR), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p);
+                   scalar(m, S_WAPA), nf, scalar(m, S_SINGULAR), scalar(m, S_RES), n, cx.partials.p, cx.ticket.p, stop);
             allReduce(scalar(m, S_RES), 1);
-            static_assert(S_SINGULAR - S_NUM == 2 && S_RES < S_NUM, "scalar layout");
-            readScalars(scalar(m, 0), S_SINGULAR + 1);   // one read-back per iteration
-            if (cx.pinned[S_SINGULAR] != 0.0) {
-                perf->singular = 1;
-                break;
+        };
+        static_assert(S_SINGULAR - S_NUM == 2 && S_RES < S_NUM, "scalar layout");
+        if (!pipelined) {
+            do {
+                enqueue(perf->nIterations);
+                readScalars(scalar(m, 0), S_SINGULAR + 1);   // one read-back per iteration
+                if (cx.pinned[S_SINGULAR] != 0.0) {
+                    perf->singular = 1;
+                    break;
+                }
+                perf->finalResidual = cx.pinned[S_RES] / nf;
+                record(perf, c, perf->finalResidual);
+            } while ((++perf->nIterations < c.maxIter &&
+                      !checkConvergence(perf, c)) ||
+                     perf->nIterations < c.minIter);
+        } else {
+            constexpr int kSlot = S_SINGULAR + 1;   // doubles per read-back slot of the pinned block
+            static_assert(2 * kSlot <= 64, "pinned scalar block");
+            struct StopGuard {
+                cudaEvent_t ev[2] = {nullptr, nullptr};
+                StopGuard() {
+                    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+                    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+                }
+                ~StopGuard() {
+                    g_stop = nullptr;
+                    cudaEventDestroy(ev[0]);
+                    cudaEventDestroy(ev[1]);
+                }
+            } guard;
+            B2_CUDA(cudaMemsetAsync(cx.stopFlag.p, 0, sizeof(int), S()));
+            g_stop = stop;
+            auto enqueueAll = [&](int it) {
+                enqueue(it);
+                LAUNCH(k_pcg_stop_flag, 1, 1, cx.stopFlag.p, scalar(m, S_RES), scalar(m, S_SINGULAR), nf, c.tolerance,
+                       c.relTol, perf->initialResidual, it + 1 >= c.minIter ? 1 : 0);
+                B2_CUDA(cudaMemcpyAsync(cx.pinned + kSlot * (it & 1), scalar(m, 0), kSlot * sizeof(double),
+                                        cudaMemcpyDeviceToHost, S()));
+                B2_CUDA(cudaEventRecord(guard.ev[it & 1], S()));
+            };
+            enqueueAll(0);
+            for (;;) {
+                const int it = perf->nIterations;
+                if (it + 1 < c.maxIter || it + 1 < c.minIter) enqueueAll(it + 1);   // ahead of the read-back of `it`
+                B2_CUDA(cudaEventSynchronize(guard.ev[it & 1]));
+                const double* h = cx.pinned + kSlot * (it & 1);
+                if (h[S_SINGULAR] != 0.0) {
+                    perf->singular = 1;
+                    break;
+                }
+                perf->finalResidual = h[S_RES] / nf;
+                record(perf, c, perf->finalResidual);
+                if (!((++perf->nIterations < c.maxIter && !checkConvergence(perf, c)) ||
+                      perf->nIterations < c.minIter))
+                    break;
             }
-            perf->finalResidual = cx.pinned[S_RES] / nf;
-            record(perf, c, perf->finalResidual);
-        } while ((++perf->nIterations < c.maxIter &&
-                  !checkConvergence(perf, c)) ||
-                 perf->nIterations < c.minIter);
+        }
     }
 }
 
