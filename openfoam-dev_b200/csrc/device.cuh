@@ -173,6 +173,8 @@ struct DevLevel {
     DevBuf<PencilTileDev> pTiles;
     DevBuf<int> pOrder;
     int nPencilTiles = 0;
+    DevBuf<int> pGroupTiles;                        // pairs of tiles consecutive along k, in group-wavefront order (k_pencil G = 2)
+    int nPencilGroups = 0;
     // interfaces
     int nIfaces = 0;
     std::vector<int> ifaceSize, ifaceNbr;

@@ -122,7 +122,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials,
                                             unsigned int* __restrict__ ticket) {
-    __shared__ double sm[NV][kReduceThreads / 32];
+    __shared__ double sm[NV][32];   // one entry per warp of the block (any block size)
     __shared__ bool isLast;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll

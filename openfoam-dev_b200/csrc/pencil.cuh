@@ -71,6 +71,10 @@ struct PencilArgs {
     unsigned long long* prof;
     int debug;              // B200LS_PENCIL_DEBUG bits: 2 = slow helper rounds
     const int* stop;        // optional: a non-zero word makes the launch a no-op (speculatively enqueued iterations)
+    // G > 1 tiles per CTA (consecutive along k; template parameter G of k_pencil): groups in launch order, G tile indices
+    // each (-1: the group has no such tile)
+    const int* groupTiles;
+    int nGroups;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -173,6 +177,7 @@ static constexpr int kPencilProfWords = 64;  // debugging counters per tile (B20
 static constexpr int kPencilD = 8;          // steps held by the record ring
 static constexpr int kPencilPrep = 2;       // prep warps (step s is prepared by warp s % kPencilPrep)
 static constexpr int kPencilThreads = 32 * (3 + kPencilPrep);   // chain, helper, writer + the prep warps
+static constexpr int kPencilGroup = 2;      // tiles per CTA of the grouped substitution sweeps (k_pencil template parameter G)
 static constexpr int kPencilOutRows = 64;   // steps held by the result ring (power of two, > largest skew + 26)
 static constexpr int kPencilHeaderBytes = 768;
 __host__ __device__ inline int pencilExtBytes(int extW) { return (kPencilE * extW * 8 + 127) / 128 * 128; }
@@ -198,8 +203,12 @@ __host__ __device__ constexpr bool pencilFits(int skewUnits, int SKEW, int NS, b
 //                   the other buffer with the sentinel; carries the fused dot product
 // Hand-overs inside the CTA are sentinel words in shared memory (the value is the flag), mbarriers for the bulk
 // copies, and three progress words.
-template <int MODE, int SKEW, int NS>
-__global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
+// G tiles per CTA: G such pipelines side by side (warp w: pipeline w / 5), working on G tiles that follow each other along
+// k.  The K-face values then never leave the SM: the writer warp of the producing tile deposits them straight into the
+// neighbour-value ring of the consuming pipeline (second arrival on its per-step barrier), so only the J faces and
+// the K faces between groups are handed over through L2.
+template <int MODE, int SKEW, int NS, int G>
+__global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) {
     using T = PencilTraits<MODE>;
     constexpr int DIR = T::DIR;
     constexpr bool GS = T::GS;
@@ -212,7 +221,11 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     extern __shared__ __align__(128) unsigned char pencilSmem[];
     if (a.stop && *a.stop) return;   // (every CTA reads the same word: it only changes between launches)
     const bool doDot = MODE == PM_BWD && a.dotOut != nullptr;
-    unsigned smBase = smem_u32(pencilSmem);
+    constexpr int kWarpsPerSub = kPencilThreads / 32;
+    const int sub = G == 1 ? 0 : int(threadIdx.x >> 5) / kWarpsPerSub;
+    const unsigned subBytes = unsigned(pencilSmemBytes<MODE, NS>(a.extW, doDot) + 127) & ~127u;
+    const unsigned smCta = smem_u32(pencilSmem);
+    unsigned smBase = smCta + unsigned(sub) * subBytes;
     asm volatile("mov.u32 %0, %0;" : "+r"(smBase));   // opaque: keep the base in a register (not re-derived from SR_CgaCtaId)
     // mbarriers: raw stages [8], record full / empty [8 each], result written [16], neighbour values of a step [32]
     const unsigned barFull = smBase, recFull = smBase + 64, recEmpty = smBase + 128, outFull = smBase + 192;
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     const unsigned dotRing = outRing + pencilOutBytes();
     const unsigned dataRing = dotRing + (doDot ? pencilOutBytes() : 0);
     const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
+    const int wid = int(threadIdx.x >> 5) - sub * kWarpsPerSub;
     // warp roles: 0 chain, 1 helper, 2 .. 1+kPencilPrep prep, last writer
     const int role = wid == 0 ? 0 : wid == 1 ? 1 : wid == 2 + kPencilPrep ? 3 : 2;
     const int prepId = wid - 2;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
     const int pad = DIR > 0 ? 0 : (R - nx % R) % R;   // backward: the first (top) chunk is the partial one
     double dsum[1] = {0.0};
 
-    if (threadIdx.x == 0) {
+    if (wid == 0 && lane == 0) {
         for (int q = 0; q < NS; q++) {
             mbar_init(barFull + q * 8, 1);
             mbar_init(rawDone + q * 8, kPencilPrep);
@@ -252,14 +265,35 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
 
     unsigned gchunk0 = 0;   // chunks / record groups handed over by earlier tiles of this CTA (same count in every warp)
     unsigned ggroup0 = 0;
-    for (int ti = blockIdx.x; ti < a.nTiles; ti += gridDim.x, gchunk0 += nChunks) {
-        const PencilTileDev* tp = a.tiles + a.order[DIR > 0 ? ti : a.nTiles - 1 - ti];
+    const int nWork = G == 1 ? a.nTiles : a.nGroups;
+    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+        // the tile of this pipeline; with G > 1 also who produces its chain-side K-face values (prodTile) and who
+        // consumes its own (consTile) inside the CTA
+        int ti, prodTile = -1, consTile = -1;
+        if (G == 1) {
+            ti = a.order[DIR > 0 ? wi : a.nTiles - 1 - wi];
+        } else {
+            const int* gt = a.groupTiles + size_t(DIR > 0 ? wi : a.nGroups - 1 - wi) * G;
+            ti = gt[sub];
+            if (sub - DIR >= 0 && sub - DIR < G) prodTile = gt[sub - DIR];
+            if (sub + DIR >= 0 && sub + DIR < G) consTile = gt[sub + DIR];
+            if (ti < 0) {          // no such tile in this group: keep the block barriers of the others company
+                __syncthreads();   // tile start
+                __syncthreads();   // tile end
+                continue;
+            }
+        }
+        const PencilTileDev* tp = a.tiles + ti;
         const int4 t0 = *reinterpret_cast<const int4*>(&tp->base);      // base, w, wj, wk
         const int4 tB = *reinterpret_cast<const int4*>(tp->nbrBase);
         const int tbase = t0.x, w = t0.y, wj = t0.z, wk = t0.w;
         const int skewMax = SKEW * ((wj - 1) + (wk - 1));
         const int S = nx + skewMax;
-        const int S8 = (S + kPencilD - 1) & ~(kPencilD - 1);   // the pipeline runs whole record groups; the extra steps are idle
+        int S8 = (S + kPencilD - 1) & ~(kPencilD - 1);   // the pipeline runs whole record groups; the extra steps are idle
+        // EXPERIMENTAL (G > 1 is opt-in): with an even number of record groups per tile a CTA that processes a second
+        // pair of tiles delivers wrong values or hangs (cause not found; one tile per CTA is not affected); an odd
+        // number of groups per tile was correct in every case tried, so one idle group is appended
+        if (G > 1 && !(a.debug & 8) && ((S8 / kPencilD) & 1) == 0) S8 += kPencilD;
         const unsigned group0 = ggroup0;
         ggroup0 += unsigned(S8 / kPencilD);
         // neighbour tiles: chain side = where the new values come from, static side = old values (Gauss-Seidel) and
@@ -269,6 +303,9 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
         const bool hasCJ = baseCJ >= 0, hasCK = baseCK >= 0;
         const bool hasSJ = GS && baseSJ >= 0, hasSK = GS && baseSK >= 0;
         const bool anyExt = hasCJ || hasCK || hasSJ || hasSK;
+        // K faces handed over inside the CTA (G > 1): the chain-side K neighbour is the tile of the pipeline next door
+        const bool ctaCK = G > 1 && hasCK && prodTile >= 0 && !(a.debug & 4);   // (debug bit 4: K faces through L2 after all)
+        const bool ctaCons = G > 1 && consTile >= 0 && !(a.debug & 4);
         // ring columns of a step: [chain J (wk) | chain K (wj) | static J (wk) | static K (wj)]
         const int colCK = wk, colSJ = wk + wj, colSK = 2 * wk + wj;
         const unsigned extRowB = unsigned(a.extW) * 8;
@@ -285,7 +322,10 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             // ------------------------------------------------------------------------------------------------
             if (lane == 0) {
                 // the per-step "neighbour values are in the ring" barriers start every tile in phase 0
-                for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, 1);
+                // (arrivals per step: this warp if it fetches any column, the producing pipeline's writer if the K face
+                //  comes from inside the CTA)
+                const bool fetches = hasCJ || (hasCK && !ctaCK) || hasSJ || hasSK;
+                for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, (fetches ? 1 : 0) + (ctaCK ? 1 : 0) > 1 ? 2 : 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 st_release_cta(wChainProg, 0);
                 st_release_cta(wWriterProg, 0);
@@ -298,7 +338,8 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             // ---- every lane streams up to kPencilCPL columns of the ring (one source pencil of a neighbour tile each) ----
             const int4 tW = *reinterpret_cast<const int4*>(tp->nbrW);
             const int4 tJ = *reinterpret_cast<const int4*>(tp->nbrWj);
-            const int nCols = (hasCJ ? wk : 0) + (hasCK ? wj : 0) + (hasSJ ? wk : 0) + (hasSK ? wj : 0);
+            const bool hasCKh = hasCK && !ctaCK;   // K-face columns this warp has to fetch from L2
+            const int nCols = (hasCJ ? wk : 0) + (hasCKh ? wj : 0) + (hasSJ ? wk : 0) + (hasSK ? wj : 0);
             const double* cSrc[kPencilCPL];   // element (row 0) of the source pencil; nullptr: no column
             int cStride[kPencilCPL];          // row stride of the source tile
             int cSkew[kPencilCPL];            // skew of the lane of this tile that consumes the column
@@ -317,7 +358,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                     // which group does column q of the compacted list belong to: 0 chain J, 1 chain K, 2 static J, 3 static K
                     int grp = -1, idx = 0;
                     if (hasCJ) { if (grp < 0 && q < wk) { grp = 0; idx = q; } q -= wk; }
-                    if (hasCK) { if (grp < 0 && q >= 0 && q < wj) { grp = 1; idx = q; } q -= wj; }
+                    if (hasCKh) { if (grp < 0 && q >= 0 && q < wj) { grp = 1; idx = q; } q -= wj; }
                     if (hasSJ) { if (grp < 0 && q >= 0 && q < wk) { grp = 2; idx = q; } q -= wk; }
                     if (hasSK) { if (grp < 0 && q >= 0 && q < wj) { grp = 3; idx = q; } q -= wj; }
                     const bool isJ = (grp == 0 || grp == 2), isChain = grp < 2;
@@ -743,7 +784,31 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
             // writer warp
             // ------------------------------------------------------------------------------------------------
             // the lanes on the high faces of the tile, whose values a neighbour tile is waiting for, publish at once
-            const bool faceLane = laneOn && ((jr == wj - 1 && baseSJ >= 0) || (kr == wk - 1 && baseSK >= 0));
+            const bool faceLane = laneOn && ((jr == wj - 1 && baseSJ >= 0) || (kr == wk - 1 && baseSK >= 0 && !ctaCons));
+            // in-CTA consumer of the K face: ring, per-step barriers and progress word of the pipeline next door
+            const unsigned consBase = smCta + unsigned(sub + DIR) * subBytes;
+            const unsigned consExtFull = consBase + 320, consProgW = consBase + 640;
+            const int consWk = ctaCons ? a.tiles[consTile].wk : 1;
+            const int consS = nx + SKEW * ((wj - 1) + (consWk - 1));
+            const unsigned consCol = consBase + kPencilHeaderBytes + unsigned(consWk + jj) * 8;   // column colCK + jj
+            const int consShift = SKEW * (wk - 1);   // consumer step = producer step - shift
+            const bool kFace = laneOn && kr == wk - 1;
+            int consProg = 0;
+            auto deposit = [&](int sc, double val) {   // K-face values of consumer step sc (uniform over the warp)
+                if (sc >= consProg + kPencilE) {       // ring capacity: wait for the consumer's chain warp
+                    unsigned spins = 0;
+                    while (sc >= consProg + kPencilE) {
+                        consProg = ld_acquire_cta(consProgW);
+                        if (++spins > kMaxSpins) {
+                            *a.err = 1;
+                            break;
+                        }
+                    }
+                }
+                if (kFace) sts_f64(consCol + unsigned(sc & (kPencilE - 1)) * extRowB, val);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(consExtFull + unsigned(sc & (kPencilE - 1)) * 8);
+            };
             const int delay = skewMax - skew;   // steps between this lane's result of a row and the row being complete
             const unsigned outLane = outRing + unsigned(lane) * 8;
             const unsigned dotLane = dotRing + unsigned(lane) * 8;
@@ -768,6 +833,7 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 const int r = s - skew;
                 const bool act = laneOn && unsigned(r) < unsigned(nx);
                 if (act && faceLane) st_l2(a.out + elem, v);
+                if (ctaCons && s >= consShift && s - consShift < consS) deposit(s - consShift, act ? v : NEUTRAL);
                 const int q = s - skewMax;   // processing row every lane has finished now
                 if (laneOn && unsigned(q) < unsigned(nx)) {
                     const unsigned slotQ = outLane + unsigned((s - delay) & (kPencilOutRows - 1)) * 256u;
@@ -781,9 +847,13 @@ __global__ void __launch_bounds__(kPencilThreads, 1) k_pencil(PencilArgs a) {
                 elemRow += DIR * w;
                 if ((s & 7) == 7 && lane == 0) st_release_cta(wWriterProg, s + 1);
             }
+            // consumer steps past our own last one only see rows outside the block
+            if (ctaCons)
+                for (int sc = max(0, S8 - consShift); sc < consS; sc++) deposit(sc, NEUTRAL);
             if (a.prof && lane == 0) a.prof[size_t(ti) * kPencilProfWords + 7] = pWait;
             __syncthreads();   // tile end
         }
+        gchunk0 += nChunks;
     }
     if (MODE == PM_BWD && a.dotOut) {
         if (grid_reduce<1>(dsum, a.partials, a.ticket)) a.dotOut[0] = dsum[0];

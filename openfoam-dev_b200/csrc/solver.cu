@@ -145,14 +145,14 @@ static void launchSweep(K kernel, SweepArgs& a) {
 
 // Pencil sweeps (pencil.cuh): one four-warp CTA per tile, persistent over the tile list.  Cooperative launch: a tile
 // polls values of tiles earlier in the launch order, which must be resident or finished.
-template <int MODE, int SKEW, int NS>
+template <int MODE, int SKEW, int NS, int G>
 static void launchPencilCfg(PencilArgs& a, int cols) {
     if (a.nTiles == 0) return;
     Context& c = ctx();
     constexpr bool GS = PencilTraits<MODE>::GS;
-    auto kernel = k_pencil<MODE, SKEW, NS>;
+    auto kernel = k_pencil<MODE, SKEW, NS, G>;
     if (cols * (GS ? 2 : 1) > 32 * kPencilCPL) throw CudaError("pencil sweep: too many neighbour columns for the helper warp");
-    const size_t smem = size_t(pencilSmemBytes<MODE, NS>(a.extW, a.dotOut != nullptr));
+    const size_t smem = G * ((size_t(pencilSmemBytes<MODE, NS>(a.extW, a.dotOut != nullptr)) + 127) & ~size_t(127));
     // per instantiation: the dynamic shared-memory limit only ever grows; occupancy per size
     static size_t smemLimit = 0;
     static std::map<size_t, int> occCache;
@@ -163,7 +163,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     int occ;
     auto it = occCache.find(smem);
     if (it == occCache.end()) {
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPencilThreads, smem));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kPencilThreads * G, smem));
         occCache[smem] = occ;
     } else {
         occ = it->second;
@@ -171,7 +171,9 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
     if (occ < 1) throw CudaError("pencil sweep kernel does not fit on an SM");
     static const int cap = getenv("B200LS_PENCIL_CTAS_PER_SM") ? atoi(getenv("B200LS_PENCIL_CTAS_PER_SM")) : 0;
     if (cap > 0) occ = std::min(occ, cap);
-    const int blocks = std::max(1, std::min(occ * c.numSMs, a.nTiles));
+    static const int maxCtas = getenv("B200LS_PENCIL_MAX_CTAS") ? atoi(getenv("B200LS_PENCIL_MAX_CTAS")) : 0;   // debugging
+    int blocks = std::max(1, std::min(occ * c.numSMs, G == 1 ? a.nTiles : a.nGroups));
+    if (maxCtas > 0) blocks = std::min(blocks, maxCtas);
     a.err = c.errFlag.p;
     a.partials = c.partials.p;
     a.ticket = c.ticket.p;
@@ -186,7 +188,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
         a.prof = profBuf.p;
     }
     void* args[] = {&a};
-    cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(kPencilThreads), args, smem, c.stream);
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(kPencilThreads * G), args, smem, c.stream);
     if (le != cudaSuccess)
         throw CudaError(std::string("pencil sweep launch failed: ") + cudaGetErrorString(le) + " (mode " +
                         std::to_string(MODE) + ", " + std::to_string(blocks) + " CTAs, " + std::to_string(smem) +
@@ -197,7 +199,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
         B2_CUDA(cudaMemcpyAsync(h.data(), profBuf.p, h.size() * 8, cudaMemcpyDeviceToHost, c.stream));
         B2_CUDA(cudaStreamSynchronize(c.stream));
         if (FILE* f = fopen(profFile, "a")) {
-            fprintf(f, "# mode %d skew %d stages %d tiles %d ctas %d\n", MODE, SKEW, NS, a.nTiles, blocks);
+            fprintf(f, "# mode %d skew %d stages %d tiles %d ctas %d group %d\n", MODE, SKEW, NS, a.nTiles, blocks, G);
             for (int t = 0; t < a.nTiles; t++) {
                 for (int q = 0; q < kPencilProfWords; q++) fprintf(f, "%llu ", h[size_t(t) * kPencilProfWords + q]);
                 fprintf(f, "\n");
@@ -228,10 +230,23 @@ static void launchPencil(PencilArgs& a, const DevLevel& D) {
     int skew = 0, stages = 0;
     if (!pencilConfig(D.pSkewUnits, PencilTraits<MODE>::GS, skew, stages))
         throw CudaError("pencil sweep: no ring configuration fits this tile shape");
-    if (skew == 1 && stages == 4) return launchPencilCfg<MODE, 1, 4>(a, D.pCols);
-    if (skew == 1) return launchPencilCfg<MODE, 1, 8>(a, D.pCols);
-    if (stages == 4) return launchPencilCfg<MODE, 2, 4>(a, D.pCols);
-    return launchPencilCfg<MODE, 2, 8>(a, D.pCols);
+    // EXPERIMENTAL, opt-in (B200LS_PENCIL_GROUP=2): two tiles per CTA, K faces handed over in shared memory, for the
+    // substitution sweeps of 3-D blocks (-10 % at 128^3).  Off by default: in multi-round launches it only works with
+    // an odd number of record groups per tile (see pencil.cuh) and the reason is not understood.  Gauss-Seidel (its
+    // prep warps wait on the same per-step barriers) and the profiling aid always keep one tile per CTA.
+    static const bool noGroup = !(getenv("B200LS_PENCIL_GROUP") && atoi(getenv("B200LS_PENCIL_GROUP")) >= 2);
+    static const bool prof = getenv("B200LS_PENCIL_PROF") != nullptr;
+    static const int groupModes = getenv("B200LS_PENCIL_GROUP_MODES") ? atoi(getenv("B200LS_PENCIL_GROUP_MODES")) : 7;   // debugging: bit MODE
+    if (!PencilTraits<MODE>::GS && ((groupModes >> MODE) & 1) && skew == 1 && stages == 4 && !noGroup && !prof && D.pNz > D.pWK &&
+        D.nPencilGroups > 0) {
+        a.groupTiles = D.pGroupTiles.p;
+        a.nGroups = D.nPencilGroups;
+        return launchPencilCfg<MODE, 1, 4, kPencilGroup>(a, D.pCols);
+    }
+    if (skew == 1 && stages == 4) return launchPencilCfg<MODE, 1, 4, 1>(a, D.pCols);
+    if (skew == 1) return launchPencilCfg<MODE, 1, 8, 1>(a, D.pCols);
+    if (stages == 4) return launchPencilCfg<MODE, 2, 4, 1>(a, D.pCols);
+    return launchPencilCfg<MODE, 2, 8, 1>(a, D.pCols);
 }
 
 void checkSweepError() {
@@ -331,6 +346,22 @@ static void uploadLevel(DevLevel& D, const LevelHost& H, bool coarsest) {
         D.pTiles.upload(tiles, s);
         D.pOrder.upload(P.fwdOrder, s);
         D.nPencilTiles = int(tiles.size());
+        // groups of kPencilGroup tiles that follow each other along k (tile index = J + nJ*K), in wavefront order J + M
+        {
+            const int nM = (P.nK + kPencilGroup - 1) / kPencilGroup;
+            std::vector<int> groups;
+            for (int d = 0; d <= P.nJ - 1 + nM - 1; d++)
+                for (int J = 0; J < P.nJ; J++) {
+                    const int Mg = d - J;
+                    if (Mg < 0 || Mg >= nM) continue;
+                    for (int q = 0; q < kPencilGroup; q++) {
+                        const int K = Mg * kPencilGroup + q;
+                        groups.push_back(K < P.nK ? J + P.nJ * K : -1);
+                    }
+                }
+            D.nPencilGroups = int(groups.size()) / kPencilGroup;
+            D.pGroupTiles.upload(groups, s);
+        }
         B2_CUDA(cudaStreamSynchronize(s));   // `tiles` is a temporary
     }
     static_assert(sizeof(SweepTask) == sizeof(int2), "task layout");
