@@ -169,15 +169,15 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
         occ = it->second;
     }
     if (occ < 1) throw CudaError("pencil sweep kernel does not fit on an SM");
-    static const int cap = getenv("B200LS_PENCIL_CTAS_PER_SM") ? atoi(getenv("B200LS_PENCIL_CTAS_PER_SM")) : 0;
+    const int cap = getenv("B200LS_PENCIL_CTAS_PER_SM") ? atoi(getenv("B200LS_PENCIL_CTAS_PER_SM")) : 0;
     if (cap > 0) occ = std::min(occ, cap);
-    static const int maxCtas = getenv("B200LS_PENCIL_MAX_CTAS") ? atoi(getenv("B200LS_PENCIL_MAX_CTAS")) : 0;   // debugging
+    const int maxCtas = getenv("B200LS_PENCIL_MAX_CTAS") ? atoi(getenv("B200LS_PENCIL_MAX_CTAS")) : 0;   // debugging
     int blocks = std::max(1, std::min(occ * c.numSMs, G == 1 ? a.nTiles : a.nGroups));
     if (maxCtas > 0) blocks = std::min(blocks, maxCtas);
     a.err = c.errFlag.p;
     a.partials = c.partials.p;
     a.ticket = c.ticket.p;
-    static const int dbg = getenv("B200LS_PENCIL_DEBUG") ? atoi(getenv("B200LS_PENCIL_DEBUG")) : 0;
+    const int dbg = getenv("B200LS_PENCIL_DEBUG") ? atoi(getenv("B200LS_PENCIL_DEBUG")) : 0;
     a.debug = dbg;
     // debugging aid: B200LS_PENCIL_PROF=<file> dumps 16 counters per tile of every pencil launch (pencil.cuh PencilArgs::prof)
     static const char* profFile = getenv("B200LS_PENCIL_PROF");
@@ -212,7 +212,7 @@ static void launchPencilCfg(PencilArgs& a, int cols) {
 // (skew, ring stages) of a pencil launch: the first configuration of the mode's list whose raw ring holds the rows a
 // step can touch (pencilFits); B200LS_PENCIL_CFG=<skew><stages> (14, 18, 24, 28) moves one to the front.
 static bool pencilConfig(int skewUnits, bool gs, int& skew, int& stages) {
-    static const int forced = getenv("B200LS_PENCIL_CFG") ? atoi(getenv("B200LS_PENCIL_CFG")) : 0;
+    const int forced = getenv("B200LS_PENCIL_CFG") ? atoi(getenv("B200LS_PENCIL_CFG")) : 0;
     const int order[5] = {forced, 14, 18, 24, 28};
     for (int q = forced ? 0 : 1; q < 5; q++) {
         const int sk = order[q] / 10, ns = order[q] % 10;
@@ -230,13 +230,14 @@ static void launchPencil(PencilArgs& a, const DevLevel& D) {
     int skew = 0, stages = 0;
     if (!pencilConfig(D.pSkewUnits, PencilTraits<MODE>::GS, skew, stages))
         throw CudaError("pencil sweep: no ring configuration fits this tile shape");
-    // EXPERIMENTAL, opt-in (B200LS_PENCIL_GROUP=2): two tiles per CTA, K faces handed over in shared memory, for the
-    // substitution sweeps of 3-D blocks (-10 % at 128^3).  Off by default: in multi-round launches it only works with
-    // an odd number of record groups per tile (see pencil.cuh) and the reason is not understood.  Gauss-Seidel (its
-    // prep warps wait on the same per-step barriers) and the profiling aid always keep one tile per CTA.
-    static const bool noGroup = !(getenv("B200LS_PENCIL_GROUP") && atoi(getenv("B200LS_PENCIL_GROUP")) >= 2);
+    // UNSTABLE EXPERIMENT, opt-in (B200LS_PENCIL_GROUP=2): two tiles per CTA, K faces handed over in shared memory, for
+    // the substitution sweeps of 3-D blocks (-10 % at 128^3 where it ran).  Off by default and not part of the test
+    // suite: when a CTA processes a second pair of tiles it can deliver wrong values or hang (always with an even
+    // number of record groups per tile, sometimes with the odd padding of pencil.cuh too); cause not found.
+    // Gauss-Seidel and the profiling aid always keep one tile per CTA.
+    const bool noGroup = !(getenv("B200LS_PENCIL_GROUP") && atoi(getenv("B200LS_PENCIL_GROUP")) >= 2);
     static const bool prof = getenv("B200LS_PENCIL_PROF") != nullptr;
-    static const int groupModes = getenv("B200LS_PENCIL_GROUP_MODES") ? atoi(getenv("B200LS_PENCIL_GROUP_MODES")) : 7;   // debugging: bit MODE
+    const int groupModes = getenv("B200LS_PENCIL_GROUP_MODES") ? atoi(getenv("B200LS_PENCIL_GROUP_MODES")) : 7;   // debugging: bit MODE
     if (!PencilTraits<MODE>::GS && ((groupModes >> MODE) & 1) && skew == 1 && stages == 4 && !noGroup && !prof && D.pNz > D.pWK &&
         D.nPencilGroups > 0) {
         a.groupTiles = D.pGroupTiles.p;

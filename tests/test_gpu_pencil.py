@@ -118,24 +118,3 @@ def test_pencil_solvers_match_oracle(shape, sym, gamg_keeps_pencil, monkeypatch)
             tol = 1e-9 if solver != "PBiCGStab" or perf.nIterations <= 12 else 1e-8
             assert max_rel_diff(psi, xo) <= tol, (solver, max_rel_diff(psi, xo))
 
-
-@pytest.mark.parametrize("shape", [(20, 8, 16), (40, 33, 17), (24, 8, 16), (9, 9, 9)])
-@pytest.mark.parametrize("max_ctas", ["1", "3", "0"])
-def test_experimental_two_tiles_per_cta(shape, max_ctas, monkeypatch):
-    """Opt-in B200LS_PENCIL_GROUP=2 (two tiles per CTA, K faces handed over in shared memory): bit-exact, also when a
-    CTA processes several tile pairs in a row (B200LS_PENCIL_MAX_CTAS caps the grid) -- with the odd-group padding the
-    kernel needs for that (pencil.cuh); the default remains one tile per CTA."""
-    monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
-    monkeypatch.setenv("B200LS_PENCIL_GROUP", "2")
-    monkeypatch.setenv("B200LS_PENCIL_MAX_CTAS", max_ctas)
-    for sym in (True, False):
-        s = _system(shape, sym)
-        mesh, mat = capi.from_system(s)
-        S = orc.System(s)
-        kind = "DIC" if sym else "DILU"
-        assert np.array_equal(mat.reciprocal_d(kind), orc.reciprocal_d(S))
-        for seed in (0.37, 0.11):
-            rA = np.cos(seed * np.arange(s.n_cells)) + 0.1
-            assert np.array_equal(mat.precondition(kind, rA), orc.precondition(S, kind, rA))
-        mat.close()
-        mesh.close()
