@@ -1145,6 +1145,12 @@ void opPrecondition(b200ls_matrix_s* m, int level, int precond, double* wA, cons
         f.clear = wA;
         f.stop = g_stop;
         launchPencil<PM_FWD>(f, D);
+        static const bool fwdOnly = getenv("B200LS_DEBUG_FWD_ONLY") != nullptr;
+        if (fwdOnly) {   // debugging aid (benchmarks/pencil_group_fwd.py): return the forward sweep's result
+            B2_CUDA(cudaMemcpyAsync(wA, M.tmpA.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, S()));
+            M.tmpASentinel = false;
+            return;
+        }
         PencilArgs b = pencilArgs(D, false);
         b.plane[0] = M.tmpA.p;
         for (int q = 0; q < 3; q++) b.plane[1 + q] = M.ptU.p + q * np;
