@@ -259,12 +259,19 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
             mbar_init(recEmpty + q * 8, 1);    // chain warp: record loaded
         }
         for (int q = 0; q < 16; q++) mbar_init(outFull + q * 8, 1);   // chain warp: result stored
+        // G > 1: the per-step "neighbour values" barriers receive arrivals from another pipeline's writer as well, so
+        // they are initialised ONCE (two arrivals per step, always) and their phase parity is carried across tiles;
+        // re-initialising them at tile starts, as the one-tile-per-CTA path does, lost or duplicated the other warp's
+        // last arrivals of the previous tile
+        if (G > 1)
+            for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     unsigned gchunk0 = 0;   // chunks / record groups handed over by earlier tiles of this CTA (same count in every warp)
     unsigned ggroup0 = 0;
+    unsigned gext0 = 0;     // G > 1: laps of the neighbour-value ring (kPencilE steps each) completed by earlier tiles
     const int nWork = G == 1 ? a.nTiles : a.nGroups;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
         // the tile of this pipeline; with G > 1 also who produces its chain-side K-face values (prodTile) and who
@@ -289,13 +296,13 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
         const int tbase = t0.x, w = t0.y, wj = t0.z, wk = t0.w;
         const int skewMax = SKEW * ((wj - 1) + (wk - 1));
         const int S = nx + skewMax;
-        int S8 = (S + kPencilD - 1) & ~(kPencilD - 1);   // the pipeline runs whole record groups; the extra steps are idle
-        // EXPERIMENTAL (G > 1 is opt-in): with an even number of record groups per tile a CTA that processes a second
-        // pair of tiles delivers wrong values or hangs (cause not found; one tile per CTA is not affected); an odd
-        // number of groups per tile was correct in every case tried, so one idle group is appended
-        if (G > 1 && !(a.debug & 8) && ((S8 / kPencilD) & 1) == 0) S8 += kPencilD;
+        const int S8 = (S + kPencilD - 1) & ~(kPencilD - 1);   // the pipeline runs whole record groups; the extra steps are idle
         const unsigned group0 = ggroup0;
         ggroup0 += unsigned(S8 / kPencilD);
+        // G > 1: every tile completes whole laps of the neighbour-value barriers (arrivals padded to E32 steps)
+        const int E32 = (S + kPencilE - 1) & ~(kPencilE - 1);
+        const unsigned ext0 = G > 1 ? gext0 : 0u;
+        gext0 += unsigned(E32 / kPencilE);
         // neighbour tiles: chain side = where the new values come from, static side = old values (Gauss-Seidel) and
         // the tiles that wait for our results
         const int baseCJ = DIR > 0 ? tB.x : tB.z, baseCK = DIR > 0 ? tB.y : tB.w;
@@ -324,9 +331,10 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
                 // the per-step "neighbour values are in the ring" barriers start every tile in phase 0
                 // (arrivals per step: this warp if it fetches any column, the producing pipeline's writer if the K face
                 //  comes from inside the CTA)
-                const bool fetches = hasCJ || (hasCK && !ctaCK) || hasSJ || hasSK;
-                for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, (fetches ? 1 : 0) + (ctaCK ? 1 : 0) > 1 ? 2 : 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                if (G == 1) {
+                    for (int q = 0; q < kPencilE; q++) mbar_init(extFull + q * 8, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
                 st_release_cta(wChainProg, 0);
                 st_release_cta(wWriterProg, 0);
             }
@@ -393,10 +401,11 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
             // the values that have arrived -- a producer publishes a pencil in order, so they form a prefix -- and the
             // steps complete in EVERY column are handed over (one barrier per step).
             unsigned long long pRounds = 0, pCap = 0;
-            if (nCols > 0) {
+            if (nCols > 0 || G > 1) {
                 int published = 0, chainProg = 0;
                 unsigned spins = 0;
-                while (published < S) {
+                const int target = G > 1 ? E32 : S;   // G > 1: also the idle steps that complete the last ring lap
+                while (published < target) {
                     pRounds++;
                     if (a.debug & 2) __nanosleep(1000);
                     // ring capacity: rows of steps the chain warp (the last reader) has finished may be overwritten
@@ -433,12 +442,23 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
                             myMin = min(myMin, cProg[c]);
                         }
                     }
-                    const int ready = __reduce_min_sync(0xffffffffu, myMin);
+                    int ready = __reduce_min_sync(0xffffffffu, myMin);
+                    if (G > 1) {
+                        // lanes without a column report S: steps are still only handed over inside the ring window,
+                        // and past S (no data) the window is the only condition
+                        ready = min(ready, limit);
+                        if (ready >= S) ready = min(E32, chainProg + kPencilE);
+                    }
                     __syncwarp();
                     if (ready > published) {
                         // arrive = release of the ring stores above; the chain / prep warps sleep on these barriers
                         if (lane == 0)
-                            for (int q = published; q < ready; q++) mbar_arrive(extFull + unsigned(q & (kPencilE - 1)) * 8);
+                            for (int q = published; q < ready; q++) {
+                                mbar_arrive(extFull + unsigned(q & (kPencilE - 1)) * 8);
+                                // G > 1: two arrivals per step -- the second one is the in-CTA producer's for the
+                                // steps it deposits (q < S), ours otherwise
+                                if (G > 1 && !(ctaCK && q < S)) mbar_arrive(extFull + unsigned(q & (kPencilE - 1)) * 8);
+                            }
                         published = ready;
                         spins = 0;
                     } else if (++spins > kMaxSpins) {
@@ -657,7 +677,7 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
             const bool chainExt = hasCJ || hasCK;
             auto fetch = [&](double2 (&v)[NV], double2& e, int slot, unsigned parity, int s) {
                 const unsigned rb = recFull + slot * 8;
-                const unsigned eb = extFull + unsigned(s & (kPencilE - 1)) * 8, ep = unsigned(s >> 5) & 1;
+                const unsigned eb = extFull + unsigned(s & (kPencilE - 1)) * 8, ep = (ext0 + unsigned(s >> 5)) & 1;
                 const unsigned er = unsigned(s & (kPencilE - 1)) * extRowB;
                 const bool needExt = chainExt && s < S;
                 const bool recOk = mbar_test_wait(rb, parity);
@@ -672,7 +692,7 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
                 const long long c0 = a.prof ? clock64() : 0;
                 mbar_wait(recFull + slot * 8, parity, a.err);
                 const long long c1 = a.prof ? clock64() : 0;
-                if (chainExt && s < S) mbar_wait(extFull + unsigned(s & (kPencilE - 1)) * 8, unsigned(s >> 5) & 1, a.err);
+                if (chainExt && s < S) mbar_wait(extFull + unsigned(s & (kPencilE - 1)) * 8, (ext0 + unsigned(s >> 5)) & 1, a.err);
                 if (a.prof) {
                     pRec += c1 - c0;
                     pExt += clock64() - c1;
@@ -767,7 +787,7 @@ __global__ void __launch_bounds__(kPencilThreads * G, 1) k_pencil(PencilArgs a) 
                     if (!okA && s0 + k + 2 < S8) refetch(vA, eA, kn, pn, s0 + k + 2);
                 }
                 // tell the helper how far the neighbour ring has been consumed
-                if (anyExt && lane == 0) st_release_cta(wChainProg, s0 + kPencilD - 1);
+                if ((anyExt || G > 1) && lane == 0) st_release_cta(wChainProg, s0 + kPencilD - 1);
             }
             if (a.prof && lane == 0) {
                 unsigned long long* q = a.prof + size_t(ti) * kPencilProfWords;

@@ -118,3 +118,24 @@ def test_pencil_solvers_match_oracle(shape, sym, gamg_keeps_pencil, monkeypatch)
             tol = 1e-9 if solver != "PBiCGStab" or perf.nIterations <= 12 else 1e-8
             assert max_rel_diff(psi, xo) <= tol, (solver, max_rel_diff(psi, xo))
 
+
+
+@pytest.mark.parametrize("shape", [(20, 8, 16), (40, 33, 17), (9, 9, 9), (24, 8, 16)])
+@pytest.mark.parametrize("max_ctas", ["1", "3"])
+def test_persistent_ctas_over_many_tiles(shape, max_ctas, monkeypatch):
+    """Capping the grid (B200LS_PENCIL_MAX_CTAS) makes every CTA process many tiles in a row -- what happens at 128^3
+    and beyond, here on small blocks with even and odd numbers of record groups per tile, partial tiles and partial
+    operand chunks: ring stages, barrier phases and the per-tile re-initialisation carry over correctly."""
+    monkeypatch.setenv("B200LS_PENCIL_MIN_CELLS", "0")
+    monkeypatch.setenv("B200LS_PENCIL_MAX_CTAS", max_ctas)
+    for sym in (True, False):
+        s = _system(shape, sym)
+        mesh, mat = capi.from_system(s)
+        S = orc.System(s)
+        kind = "DIC" if sym else "DILU"
+        assert np.array_equal(mat.reciprocal_d(kind), orc.reciprocal_d(S))
+        for seed in (0.37, 0.11):
+            rA = np.cos(seed * np.arange(s.n_cells)) + 0.1
+            assert np.array_equal(mat.precondition(kind, rA), orc.precondition(S, kind, rA))
+        mat.close()
+        mesh.close()
